@@ -1,0 +1,596 @@
+// sg_conv_umma.cu — tcgen05 implicit-GEMM kernels for the GAN's 4x4 stride-2 (transposed) convolutions.
+//
+// Layout: activations NHWC bf16, weights packed [Cout][ky*4+kx][Cin] bf16 (K contiguous).
+// One CTA computes a 128 x BN output tile. Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// owner), warps 2..5 = epilogue (TMEM -> registers -> global). The im2col gather is done by TMA
+// itself: for every filter tap the producer loads one 4-D box {BK channels, GW, BH, BN_img} of the
+// (parity-split) input at a shifted coordinate; out-of-bounds rows/cols are zero-filled by TMA, which
+// implements the padding. The 128 box rows land as a canonical K-major swizzled UMMA operand.
+#include "sg_conv_umma.cuh"
+#include "sg_umma.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace sg {
+
+static thread_local char g_err[512] = "";
+const char* umma_last_error() { return g_err; }
+#define SG_FAIL(...)                                \
+    do {                                            \
+        snprintf(g_err, sizeof(g_err), __VA_ARGS__); \
+        return -1;                                  \
+    } while (0)
+
+// ----------------------------------------------------------------------------
+// Tensor maps
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(uint32_t inner_bytes) {
+    return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SG_FAIL("cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstr[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_inner * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        SG_FAIL("cuTensorMapEncodeTiled(2d) failed: %d (inner=%llu outer=%llu box=%u,%u)", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+    return 0;
+}
+
+int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int step, int yp, int xp,
+                  uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SG_FAIL("cuTensorMapEncodeTiled entry point unavailable");
+    const char* b = static_cast<const char*>(base) + (static_cast<size_t>(yp) * W + xp) * C * 2;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)(W / step), (cuuint64_t)(H / step), (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)step * C * 2, (cuuint64_t)step * W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {box_c, box_w, box_h, box_n};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        SG_FAIL("cuTensorMapEncodeTiled(4d) failed: %d (N=%d H=%d W=%d C=%d step=%d box=%u,%u,%u,%u)", (int)r, N, H, W,
+                C, step, box_c, box_w, box_h, box_n);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// Forward / dgrad implicit GEMM
+// ----------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+
+template <int BN, int BK>
+struct ConvCfg {
+    static constexpr int kABytes = kTileM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    // Keep two CTAs per SM resident when the tile allows it so one CTA's epilogue overlaps another's mainloop.
+    static constexpr int kStages = (BN == 256) ? 4 : (kStageBytes >= 32768 ? 3 : 4);
+    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
+    static constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of one swizzle atom
+};
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
+    using Cfg = ConvCfg<BN, BK>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x;
+    const int tile_n = blockIdx.y;
+    const int phase = blockIdx.z;
+    const int mode = args.mode;
+    const int cc_n = args.Cin / BK;
+    const int taps = (mode == kConvS2) ? 16 : (mode == kConvT ? 4 : 1);
+    const int num_k = taps * cc_n;
+    const int R = args.GH * args.GW;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.amap[0]);
+        tma_prefetch_desc(&args.bmap);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int n0 = 0, y0 = 0;
+            if (mode != kPlain) {
+                if (R >= kTileM) {
+                    const int tpi = R / kTileM;
+                    n0 = tile_m / tpi;
+                    y0 = (tile_m % tpi) * (kTileM / args.GW);
+                } else {
+                    n0 = tile_m * (kTileM / R);
+                }
+            }
+            const int py = phase >> 1, px = phase & 1;
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + s * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                if (mode == kPlain) {
+                    tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tile_m * kTileM);
+                    tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tile_n * BN);
+                } else {
+                    const int tap = it / cc_n, cc = it - tap * cc_n;
+                    if (mode == kConvS2) {
+                        const int ky = tap >> 2, kx = tap & 3;
+                        const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
+                        const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+                        tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
+                        tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tile_n * BN);
+                    } else {
+                        const int ty = tap >> 1, tx = tap & 1;
+                        const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                        tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
+                        tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK, tile_n * BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                    const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                    umma_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ---------------- Epilogue: TMEM -> registers -> global ----------------
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        const long gm = static_cast<long>(tile_m) * kTileM + r;
+        const bool row_ok = gm < args.M_total;
+        long opix = gm;
+        int img = 0;
+        if (mode != kPlain) {
+            img = static_cast<int>(gm / R);
+            if (mode == kConvT) {
+                const int rem = static_cast<int>(gm - static_cast<long>(img) * R);
+                const int yh = rem / args.GW, xh = rem - yh * args.GW;
+                opix = (static_cast<long>(img) * 2 * args.GH + 2 * yh + (phase >> 1)) * (2 * args.GW) + 2 * xh +
+                       (phase & 1);
+            }
+        }
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            const int n_base = tile_n * BN + c0;
+            if (row_ok && n_base < args.N_total) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (args.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + n_base + j);
+                }
+                if (args.scale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        f[j] = fmaf(f[j], __ldg(args.scale + n_base + j), __ldg(args.shift + n_base + j));
+                }
+                if (args.act == kActRelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (args.act == kActLeaky) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * args.slope;
+                }
+                if (args.mask) {
+                    const float* mk = args.mask + static_cast<long>(img) * args.ldmask + n_base;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= __ldg(mk + j);
+                }
+                if (args.gate) {
+                    const uint4* g = reinterpret_cast<const uint4*>(args.gate + opix * args.ldo + n_base);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const uint4 u = __ldg(g + j4);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            f[j4 * 8 + t * 2] *= bf16_lo(w[t]) > 0.f ? 1.f : args.slope;
+                            f[j4 * 8 + t * 2 + 1] *= bf16_hi(w[t]) > 0.f ? 1.f : args.slope;
+                        }
+                    }
+                }
+                if (args.out_fp32) {
+                    float4* o = reinterpret_cast<float4*>(static_cast<float*>(args.out) + opix * args.ldo + n_base);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* o =
+                        reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + opix * args.ldo + n_base);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BN, int BK>
+static int launch_cfg(const ConvGemmArgs& a, dim3 grid, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN, BK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(conv_umma<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    conv_umma_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) SG_FAIL("conv_umma<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
+    return 0;
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
+                     int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
+    a.mode = mode;
+    a.nimg = nimg;
+    a.Cin = Cin;
+    a.N_total = Cout;
+    const int BK = (Cin % 64 == 0) ? 64 : 32;
+    if (Cin % BK != 0) SG_FAIL("conv_gemm: Cin=%d must be a multiple of 32", Cin);
+    int BN = Cout >= 256 ? 256 : Cout;
+    if (!(BN == 32 || BN == 64 || BN == 128 || BN == 256) || Cout % BN != 0)
+        SG_FAIL("conv_gemm: unsupported Cout=%d", Cout);
+    int taps;
+    if (mode == kPlain) {
+        a.GH = 1;
+        a.GW = kTileM;
+        a.M_total = nimg;
+        taps = 1;
+        if (make_map_2d(&a.amap[0], in, Cin, nimg, Cin, BK, kTileM)) return -1;
+    } else {
+        a.GH = (mode == kConvS2) ? inH / 2 : inH;
+        a.GW = (mode == kConvS2) ? inW / 2 : inW;
+        taps = 16;
+        if (!is_pow2(a.GH) || !is_pow2(a.GW) || a.GW > kTileM) SG_FAIL("conv_gemm: grid %dx%d unsupported", a.GH, a.GW);
+        a.M_total = nimg * a.GH * a.GW;
+        const int R = a.GH * a.GW;
+        const uint32_t bw = a.GW;
+        const uint32_t bh = R >= kTileM ? kTileM / a.GW : a.GH;
+        const uint32_t bn = R >= kTileM ? 1 : kTileM / R;
+        if (mode == kConvS2) {
+            for (int p = 0; p < 4; ++p)
+                if (make_map_nhwc(&a.amap[p], in, nimg, inH, inW, Cin, 2, p >> 1, p & 1, BK, bw, bh, bn)) return -1;
+        } else {
+            if (make_map_nhwc(&a.amap[0], in, nimg, inH, inW, Cin, 1, 0, 0, BK, bw, bh, bn)) return -1;
+        }
+    }
+    if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN)) return -1;
+    dim3 grid((a.M_total + kTileM - 1) / kTileM, Cout / BN, mode == kConvT ? 4 : 1);
+#define SG_DISPATCH(bn, bk) \
+    if (BN == bn && BK == bk) return launch_cfg<bn, bk>(a, grid, stream);
+    SG_DISPATCH(256, 64)
+    SG_DISPATCH(128, 64)
+    SG_DISPATCH(64, 64)
+    SG_DISPATCH(32, 64)
+    SG_DISPATCH(256, 32)
+    SG_DISPATCH(128, 32)
+    SG_DISPATCH(64, 32)
+    SG_DISPATCH(32, 32)
+#undef SG_DISPATCH
+    SG_FAIL("conv_gemm: no kernel for BN=%d BK=%d", BN, BK);
+}
+
+// ----------------------------------------------------------------------------
+// Weight gradient: dW[m][tap][n] = sum_pix coarse[pix][m] * fine[2*pix - 1 + tap][n]
+// Both operands are "MN-major" (the contraction runs over rows of NHWC tensors).
+// ----------------------------------------------------------------------------
+constexpr int kWgK = 64;  // pixels per pipeline stage
+
+template <int BN>
+struct WgCfg {
+    static constexpr int kAtomBytes = kWgK * 128;  // 64 pixel rows x 64 channels bf16
+    static constexpr int kABytes = 2 * kAtomBytes;
+    static constexpr int kBBytes = (BN / 64) * kAtomBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int kTmemCols = BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) wgrad_umma_kernel(const __grid_constant__ WgradArgs args) {
+    using Cfg = WgCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x;
+    const int n_tiles = (args.Nf + BN - 1) / BN;
+    const int tap = blockIdx.y / n_tiles;
+    const int tile_n = blockIdx.y - tap * n_tiles;
+    const int split = blockIdx.z;
+    const int kt_begin = static_cast<int>(static_cast<long>(args.k_tiles) * split / args.splits);
+    const int kt_end = static_cast<int>(static_cast<long>(args.k_tiles) * (split + 1) / args.splits);
+    const int num_k = kt_end - kt_begin;
+    const int R = args.GH * args.GW;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.cmap);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int ky = tap >> 2, kx = tap & 3;
+            const CUtensorMap* fm = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
+            const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + s * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                const int kt = kt_begin + it;
+                int n0, y0;
+                if (R >= kWgK) {
+                    const int tpi = R / kWgK;
+                    n0 = kt / tpi;
+                    y0 = (kt % tpi) * (kWgK / args.GW);
+                } else {
+                    n0 = kt * (kWgK / R);
+                    y0 = 0;
+                }
+                tma_load_2d(sa, &args.cmap, &full_bar[s], tile_m * 128, kt * kWgK);
+                tma_load_2d(sa + Cfg::kAtomBytes, &args.cmap, &full_bar[s], tile_m * 128 + 64, kt * kWgK);
+#pragma unroll
+                for (int a = 0; a < BN / 64; ++a)
+                    tma_load_4d(sb + a * Cfg::kAtomBytes, fm, &full_bar[s], tile_n * BN + a * 64, dx, y0 + dy, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < kWgK / 16; ++k) {
+                    // 16 pixel rows per MMA = 2 swizzle atoms of 8 rows (SBO); 64-channel column blocks are LBO apart.
+                    const uint64_t da = make_smem_desc(a_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
+                    const uint64_t db = make_smem_desc(b_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
+                    umma_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = tile_m * 128 + q * 32 + lane;
+        if (num_k > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+        float* dst = args.partial + ((static_cast<size_t>(split) * 16 + tap) * args.Mc + m) * args.Nf;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (num_k > 0) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0;
+            }
+            const int n_base = tile_n * BN + c0;
+            if (m < args.Mc && n_base < args.Nf) {
+                float4* o = reinterpret_cast<float4*>(dst + n_base);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// partial [S][16][M][N] -> dW [M][N][16]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int S, int M, int N,
+                                    int accumulate) {
+    const long total = static_cast<long>(M) * N * 16;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        // i enumerates (tap, m, n) so reads are coalesced; the 16x smaller output is written strided.
+        const int n = static_cast<int>(i % N);
+        const long t = i / N;
+        const int m = static_cast<int>(t % M);
+        const int tap = static_cast<int>(t / M);
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += partial[(static_cast<size_t>(s) * 16 + tap) * M * N + static_cast<size_t>(m) * N + n];
+        float* o = dW + (static_cast<size_t>(m) * N + n) * 16 + tap;
+        *o = accumulate ? *o + acc : acc;
+    }
+}
+
+static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles) {
+    // Aim for ~2 waves of 148 SMs, at least 8 K-tiles per CTA.
+    const int base = m_tiles * n_tiles * 16;
+    int s = (2 * 148 + base - 1) / base;
+    if (s < 1) s = 1;
+    const int max_s = k_tiles / 8 > 0 ? k_tiles / 8 : 1;
+    if (s > max_s) s = max_s;
+    if (s > 32) s = 32;
+    return s;
+}
+
+static int wgrad_bn(int Nf) { return Nf >= 256 ? 256 : (Nf >= 128 ? 128 : 64); }
+
+size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf) {
+    const int k_tiles = (nimg * cH * cW + kWgK - 1) / kWgK;
+    const int BN = wgrad_bn(Nf);
+    const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN);
+    return static_cast<size_t>(s) * 16 * Mc * Nf;
+}
+
+template <int BN>
+static int launch_wg(const WgradArgs& a, dim3 grid, cudaStream_t stream) {
+    using Cfg = WgCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(wgrad_umma<%d>): %s", BN, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    wgrad_umma_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) SG_FAIL("wgrad_umma<%d> launch: %s", BN, cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
+                 float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream) {
+    if (!is_pow2(cH) || !is_pow2(cW) || cW > kWgK) SG_FAIL("wgrad: coarse grid %dx%d unsupported", cH, cW);
+    if (Mc % 8 != 0 || Nf % 8 != 0) SG_FAIL("wgrad: channels must be multiples of 8 (Mc=%d Nf=%d)", Mc, Nf);
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.GH = cH;
+    a.GW = cW;
+    a.nimg = nimg;
+    a.Mc = Mc;
+    a.Nf = Nf;
+    const long pix = static_cast<long>(nimg) * cH * cW;
+    a.k_tiles = static_cast<int>((pix + kWgK - 1) / kWgK);
+    const int BN = wgrad_bn(Nf);
+    const int m_tiles = (Mc + 127) / 128, n_tiles = (Nf + BN - 1) / BN;
+    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles);
+    a.partial = partial;
+    if (static_cast<size_t>(a.splits) * 16 * Mc * Nf > partial_floats) SG_FAIL("wgrad: partial workspace too small");
+    if (make_map_2d(&a.cmap, coarse, Mc, pix, Mc, 64, kWgK)) return -1;
+    const int R = cH * cW;
+    const uint32_t bw = cW, bh = R >= kWgK ? kWgK / cW : cH, bn = R >= kWgK ? 1 : kWgK / R;
+    for (int p = 0; p < 4; ++p)
+        if (make_map_nhwc(&a.fmap[p], fine, nimg, 2 * cH, 2 * cW, Nf, 2, p >> 1, p & 1, 64, bw, bh, bn)) return -1;
+    dim3 grid(m_tiles, 16 * n_tiles, a.splits);
+    int rc;
+    if (BN == 256)
+        rc = launch_wg<256>(a, grid, stream);
+    else if (BN == 128)
+        rc = launch_wg<128>(a, grid, stream);
+    else
+        rc = launch_wg<64>(a, grid, stream);
+    if (rc) return rc;
+    const long total = static_cast<long>(Mc) * Nf * 16;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, a.splits, Mc, Nf, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) SG_FAIL("wgrad_reduce launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace sg

@@ -1,0 +1,76 @@
+// sg_conv_umma.cuh — host-side interface of the tcgen05 implicit-GEMM kernels.
+//
+// Activations are NHWC bf16. Three GEMM "row gather" modes share one kernel:
+//   kConvS2 : 4x4 stride-2 pad-1 convolution (Discriminator forward, disc…:51-58;
+//             also the data-gradient of ConvTranspose2d, gen…:46-54).
+//   kConvT  : 4x4 stride-2 pad-1 transposed convolution, one output parity phase per
+//             grid.z (Generator forward, gen…:46-54; also the data-gradient of Conv2d).
+//   kPlain  : row-major [M][K] x [N][K]^T (Generator fc, gen…:125).
+// The weight-gradient kernel contracts over pixels with both operands MN-major.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sg {
+
+enum ConvMode : int { kConvS2 = 0, kConvT = 1, kPlain = 2 };
+enum EpiAct : int { kActNone = 0, kActRelu = 1, kActLeaky = 2 };
+
+// Arguments of the forward/dgrad implicit GEMM. `GH x GW` is the grid the GEMM rows
+// enumerate: the OUTPUT grid for kConvS2, the INPUT grid for kConvT.
+struct ConvGemmArgs {
+    CUtensorMap amap[4];  // kConvS2: the four (row,col) parity views of the input; else [0]
+    CUtensorMap bmap;     // packed weights [N_total][taps*Cin] bf16, K contiguous
+    int mode;
+    int GH, GW, nimg;
+    int M_total;  // nimg*GH*GW (kPlain: rows)
+    int N_total;  // output channels
+    int Cin;      // channels per tap (K = taps*Cin)
+    // epilogue: v = acc (+bias[n]) ; (v = v*scale[n]+shift[n]) ; act ; (*mask[img][n]) ; (*gate')
+    void* out;  // bf16 (or fp32 when out_fp32) rows of `ldo` elements
+    int ldo;
+    int out_fp32;
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    int act;
+    float slope;
+    const float* mask;  // [nimg][ldmask] dropout keep-scale, or null
+    int ldmask;
+    const __nv_bfloat16* gate;  // saved activation at the output position: v *= (g>0 ? 1 : slope)
+    float* colsum;              // optional [2][N_total]: per-column sum / sum of squares of v (atomic)
+};
+
+struct WgradArgs {
+    CUtensorMap cmap;     // coarse-grid tensor as [pixels][Cc] (2-D)
+    CUtensorMap fmap[4];  // the four parity views of the fine-grid (2x) tensor
+    int GH, GW, nimg;     // coarse grid
+    int Mc, Nf;           // channels of coarse / fine tensors
+    int k_tiles;          // ceil(nimg*GH*GW / 64)
+    int splits;
+    float* partial;  // [splits][16][Mc][Nf]
+};
+
+// Tensor-map builders (host). Return 0 on success.
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                uint32_t box_inner, uint32_t box_outer);
+// NHWC tensor [N][H][W][C] viewed with (row,col) parity (yp,xp) and step `step` (1 = plain view, 2 = parity view).
+int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int step, int yp, int xp,
+                  uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n);
+
+// Fills maps + geometry and launches. `w_packed` is [Cout][taps][Cin] bf16 with taps = 16 (ky*4+kx) for conv
+// modes and 1 for kPlain. For kConvT all four phases are launched (grid.z = 4).
+int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
+                     int Cin, int Cout, ConvGemmArgs epi /* only epilogue fields read */, cudaStream_t stream);
+
+// dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
+// `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.
+int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
+                 float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream);
+size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf);
+
+const char* umma_last_error();
+
+}  // namespace sg

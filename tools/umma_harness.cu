@@ -1,0 +1,374 @@
+// umma_harness.cu — standalone GPU check of the tcgen05 kernels against straightforward CPU loops.
+// Build: make -C signature-gan_b200/csrc harness     Run (GPU box): build/umma_harness [perf]
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../signature-gan_b200/csrc/sg_conv_umma.cuh"
+
+using bf16 = __nv_bfloat16;
+
+#define CK(x)                                                                             \
+    do {                                                                                  \
+        cudaError_t e_ = (x);                                                             \
+        if (e_ != cudaSuccess) {                                                          \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                      \
+        }                                                                                 \
+    } while (0)
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+    rng_state = rng_state * 1664525u + 1013904223u;
+    return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+static float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct Dev {
+    std::vector<float> h;  // bf16-rounded values as float
+    bf16* d = nullptr;
+    void init(size_t n, float scale) {
+        h.resize(n);
+        std::vector<bf16> t(n);
+        for (size_t i = 0; i < n; ++i) {
+            t[i] = __float2bfloat16(frand() * scale);
+            h[i] = __bfloat162float(t[i]);
+        }
+        CK(cudaMalloc(&d, n * 2));
+        CK(cudaMemcpy(d, t.data(), n * 2, cudaMemcpyHostToDevice));
+    }
+    ~Dev() {
+        if (d) cudaFree(d);
+    }
+};
+
+static int report(const char* name, const std::vector<float>& got, const std::vector<float>& ref, float tol) {
+    double max_err = 0, max_ref = 0;
+    size_t bad = 0, worst = 0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+        double e = fabs((double)got[i] - ref[i]);
+        if (!(e <= max_err)) {
+            if (e > max_err || std::isnan(e)) {
+                max_err = e;
+                worst = i;
+            }
+        }
+        if (fabs(ref[i]) > max_ref) max_ref = fabs(ref[i]);
+        if (!(e <= tol * (1.0 + fabs(ref[i])))) ++bad;
+    }
+    printf("%-34s max_err=%.4g max_ref=%.4g bad=%zu/%zu (worst idx %zu got %.5g ref %.5g) %s\n", name, max_err, max_ref,
+           bad, ref.size(), worst, got[worst], ref[worst], bad == 0 ? "PASS" : "FAIL");
+    return bad == 0 ? 0 : 1;
+}
+
+static std::vector<float> fetch_bf16(const bf16* d, size_t n) {
+    std::vector<bf16> t(n);
+    CK(cudaMemcpy(t.data(), d, n * 2, cudaMemcpyDeviceToHost));
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; ++i) f[i] = __bfloat162float(t[i]);
+    return f;
+}
+
+// ---- CPU references (NHWC, weights packed [Cout][16][Cin]) ----
+static void cpu_conv_s2(const std::vector<float>& x, const std::vector<float>& w, int N, int H, int W, int Cin,
+                        int Cout, std::vector<float>& y) {
+    const int OH = H / 2, OW = W / 2;
+    y.assign((size_t)N * OH * OW * Cout, 0.f);
+    for (int n = 0; n < N; ++n)
+        for (int oy = 0; oy < OH; ++oy)
+            for (int ox = 0; ox < OW; ++ox)
+                for (int co = 0; co < Cout; ++co) {
+                    float acc = 0;
+                    for (int ky = 0; ky < 4; ++ky) {
+                        const int iy = 2 * oy - 1 + ky;
+                        if (iy < 0 || iy >= H) continue;
+                        for (int kx = 0; kx < 4; ++kx) {
+                            const int ix = 2 * ox - 1 + kx;
+                            if (ix < 0 || ix >= W) continue;
+                            const float* xp = &x[(((size_t)n * H + iy) * W + ix) * Cin];
+                            const float* wp = &w[((size_t)co * 16 + ky * 4 + kx) * Cin];
+                            for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * wp[ci];
+                        }
+                    }
+                    y[(((size_t)n * OH + oy) * OW + ox) * Cout + co] = acc;
+                }
+}
+// out[n, oy, ox, co] = sum_{iy,ky: 2iy-1+ky = oy} x[n,iy,ix,ci] * w[co][ky*4+kx][ci]
+static void cpu_convT(const std::vector<float>& x, const std::vector<float>& w, int N, int H, int W, int Cin, int Cout,
+                      std::vector<float>& y) {
+    const int OH = 2 * H, OW = 2 * W;
+    y.assign((size_t)N * OH * OW * Cout, 0.f);
+    for (int n = 0; n < N; ++n)
+        for (int iy = 0; iy < H; ++iy)
+            for (int ix = 0; ix < W; ++ix) {
+                const float* xp = &x[(((size_t)n * H + iy) * W + ix) * Cin];
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int oy = 2 * iy - 1 + ky;
+                    if (oy < 0 || oy >= OH) continue;
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const int ox = 2 * ix - 1 + kx;
+                        if (ox < 0 || ox >= OW) continue;
+                        float* yp = &y[(((size_t)n * OH + oy) * OW + ox) * Cout];
+                        for (int co = 0; co < Cout; ++co) {
+                            const float* wp = &w[((size_t)co * 16 + ky * 4 + kx) * Cin];
+                            float acc = 0;
+                            for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * wp[ci];
+                            yp[co] += acc;
+                        }
+                    }
+                }
+            }
+}
+// dW[m][n][tap] = sum coarse[pix][m] * fine[2*pix-1+tap][n]
+static void cpu_wgrad(const std::vector<float>& c, const std::vector<float>& f, int N, int cH, int cW, int Mc, int Nf,
+                      std::vector<float>& dW) {
+    dW.assign((size_t)Mc * Nf * 16, 0.f);
+    const int fH = 2 * cH, fW = 2 * cW;
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < cH; ++y)
+            for (int x = 0; x < cW; ++x) {
+                const float* cp = &c[(((size_t)n * cH + y) * cW + x) * Mc];
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int fy = 2 * y - 1 + ky;
+                    if (fy < 0 || fy >= fH) continue;
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const int fx = 2 * x - 1 + kx;
+                        if (fx < 0 || fx >= fW) continue;
+                        const float* fp = &f[(((size_t)n * fH + fy) * fW + fx) * Nf];
+                        for (int m = 0; m < Mc; ++m)
+                            for (int j = 0; j < Nf; ++j) dW[((size_t)m * Nf + j) * 16 + ky * 4 + kx] += cp[m] * fp[j];
+                    }
+                }
+            }
+}
+
+static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout, bool epi) {
+    Dev x, w;
+    const int taps = mode == sg::kPlain ? 1 : 16;
+    x.init(mode == sg::kPlain ? (size_t)N * Cin : (size_t)N * H * W * Cin, 1.0f);
+    w.init((size_t)Cout * taps * Cin, 0.1f);
+    std::vector<float> ref;
+    size_t out_pix;
+    if (mode == sg::kConvS2) {
+        cpu_conv_s2(x.h, w.h, N, H, W, Cin, Cout, ref);
+        out_pix = (size_t)N * (H / 2) * (W / 2);
+    } else if (mode == sg::kConvT) {
+        cpu_convT(x.h, w.h, N, H, W, Cin, Cout, ref);
+        out_pix = (size_t)N * 4 * H * W;
+    } else {
+        ref.assign((size_t)N * Cout, 0.f);
+        for (int m = 0; m < N; ++m)
+            for (int co = 0; co < Cout; ++co) {
+                float acc = 0;
+                for (int k = 0; k < Cin; ++k) acc += x.h[(size_t)m * Cin + k] * w.h[(size_t)co * Cin + k];
+                ref[(size_t)m * Cout + co] = acc;
+            }
+        out_pix = N;
+    }
+    const size_t out_n = out_pix * Cout;
+    const int opi = (int)(out_pix / N);  // output pixels per image
+    sg::ConvGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    bf16* out;
+    CK(cudaMalloc(&out, out_n * 2));
+    CK(cudaMemset(out, 0xFF, out_n * 2));
+    a.out = out;
+    a.ldo = Cout;
+    float *bias = nullptr, *mask = nullptr;
+    Dev gate;
+    if (epi) {
+        std::vector<float> hb(Cout), hm((size_t)N * Cout);
+        for (auto& v : hb) v = frand() * 0.5f;
+        for (auto& v : hm) v = frand() > -0.5f ? 4.f / 3.f : 0.f;
+        CK(cudaMalloc(&bias, Cout * 4));
+        CK(cudaMemcpy(bias, hb.data(), Cout * 4, cudaMemcpyHostToDevice));
+        a.bias = bias;
+        a.act = sg::kActLeaky;
+        a.slope = 0.2f;
+        if (mode != sg::kPlain) {
+            CK(cudaMalloc(&mask, hm.size() * 4));
+            CK(cudaMemcpy(mask, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice));
+            a.mask = mask;
+            a.ldmask = Cout;
+            gate.init(out_n, 1.0f);
+            a.gate = gate.d;
+        }
+        for (size_t i = 0; i < out_n; ++i) {
+            const int co = (int)(i % Cout);
+            const size_t pix = i / Cout;
+            float v = ref[i] + hb[co];
+            v = v > 0 ? v : 0.2f * v;
+            if (mode != sg::kPlain) {
+                v *= hm[(pix / opi) * Cout + co];
+                v *= gate.h[i] > 0 ? 1.f : 0.2f;
+            }
+            ref[i] = v;
+        }
+    }
+    int rc = sg::launch_conv_gemm(mode, x.d, w.d, N, H, W, Cin, Cout, a, 0);
+    if (rc) {
+        printf("%-34s LAUNCH ERROR: %s\n", name, sg::umma_last_error());
+        return 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("%-34s KERNEL ERROR: %s\n", name, cudaGetErrorString(e));
+        exit(3);
+    }
+    std::vector<float> got = fetch_bf16(out, out_n);
+    for (auto& v : ref) v = rbf(v);
+    int bad = report(name, got, ref, 0.02f);
+    cudaFree(out);
+    if (bias) cudaFree(bias);
+    if (mask) cudaFree(mask);
+    return bad;
+}
+
+static int test_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
+    Dev c, f;
+    c.init((size_t)N * cH * cW * Mc, 1.0f);
+    f.init((size_t)N * 4 * cH * cW * Nf, 1.0f);
+    std::vector<float> ref;
+    cpu_wgrad(c.h, f.h, N, cH, cW, Mc, Nf, ref);
+    const size_t pf = sg::wgrad_partial_floats(N, cH, cW, Mc, Nf);
+    float *partial, *dW;
+    CK(cudaMalloc(&partial, pf * 4));
+    CK(cudaMalloc(&dW, ref.size() * 4));
+    CK(cudaMemset(dW, 0xFF, ref.size() * 4));
+    int rc = sg::launch_wgrad(c.d, f.d, N, cH, cW, Mc, Nf, partial, pf, dW, 0, 0);
+    if (rc) {
+        printf("%-34s LAUNCH ERROR: %s\n", name, sg::umma_last_error());
+        return 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("%-34s KERNEL ERROR: %s\n", name, cudaGetErrorString(e));
+        exit(3);
+    }
+    std::vector<float> got(ref.size());
+    CK(cudaMemcpy(got.data(), dW, ref.size() * 4, cudaMemcpyDeviceToHost));
+    double scale = sqrt((double)N * cH * cW);
+    int bad = report(name, got, ref, 2e-3f * (float)scale / 10.f + 1e-3f);
+    cudaFree(partial);
+    cudaFree(dW);
+    return bad;
+}
+
+static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout) {
+    bf16 *x, *w, *out;
+    const size_t xn = (size_t)N * H * W * Cin, wn = (size_t)Cout * 16 * Cin;
+    const size_t on = mode == sg::kConvS2 ? (size_t)N * H / 2 * W / 2 * Cout : (size_t)N * H * 2 * W * 2 * Cout;
+    CK(cudaMalloc(&x, xn * 2));
+    CK(cudaMalloc(&w, wn * 2));
+    CK(cudaMalloc(&out, on * 2));
+    CK(cudaMemset(x, 0, xn * 2));
+    CK(cudaMemset(w, 0, wn * 2));
+    sg::ConvGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out = out;
+    a.ldo = Cout;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) sg::launch_conv_gemm(mode, x, w, N, H, W, Cin, Cout, a, 0);
+    CK(cudaDeviceSynchronize());
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) sg::launch_conv_gemm(mode, x, w, N, H, W, Cin, Cout, a, 0);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * (mode == sg::kConvS2 ? (double)N * H / 2 * W / 2 * 16 : (double)N * H * W * 16) * Cin * Cout;
+    printf("PERF %-28s %.3f ms  %.1f TFLOP/s  (in %.0f MB, out %.0f MB)\n", name, ms, flops / ms * 1e-9, xn * 2e-6,
+           on * 2e-6);
+    cudaFree(x);
+    cudaFree(w);
+    cudaFree(out);
+}
+
+static void perf_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
+    bf16 *c, *f;
+    const size_t cn = (size_t)N * cH * cW * Mc, fn = (size_t)N * 4 * cH * cW * Nf;
+    CK(cudaMalloc(&c, cn * 2));
+    CK(cudaMalloc(&f, fn * 2));
+    CK(cudaMemset(c, 0, cn * 2));
+    CK(cudaMemset(f, 0, fn * 2));
+    const size_t pf = sg::wgrad_partial_floats(N, cH, cW, Mc, Nf);
+    float *partial, *dW;
+    CK(cudaMalloc(&partial, pf * 4));
+    CK(cudaMalloc(&dW, (size_t)Mc * Nf * 64));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) sg::launch_wgrad(c, f, N, cH, cW, Mc, Nf, partial, pf, dW, 0, 0);
+    CK(cudaDeviceSynchronize());
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) sg::launch_wgrad(c, f, N, cH, cW, Mc, Nf, partial, pf, dW, 0, 0);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * (double)N * cH * cW * 16 * Mc * Nf;
+    printf("PERF %-28s %.3f ms  %.1f TFLOP/s (partial %.0f MB)\n", name, ms, flops / ms * 1e-9, pf * 4e-6);
+    cudaFree(c);
+    cudaFree(f);
+    cudaFree(partial);
+    cudaFree(dW);
+}
+
+int main(int argc, char** argv) {
+    int only = argc > 2 ? atoi(argv[2]) : -1;
+    int fails = 0, t = 0;
+#define RUN(expr)                          \
+    do {                                   \
+        if (only < 0 || only == t) fails += (expr); \
+        ++t;                               \
+    } while (0)
+    RUN(test_conv("plain 256x128x256", sg::kPlain, 256, 1, 1, 256, 128, false));
+    RUN(test_conv("plain 200x4096x128 +epi", sg::kPlain, 200, 1, 1, 128, 4096, true));
+    RUN(test_conv("convS2 8x32x32x64->128", sg::kConvS2, 8, 32, 32, 64, 128, false));
+    RUN(test_conv("convS2 8x32x32x64->128 +epi", sg::kConvS2, 8, 32, 32, 64, 128, true));
+    RUN(test_conv("convS2 16x8x8x256->512", sg::kConvS2, 16, 8, 8, 256, 512, true));
+    RUN(test_conv("convS2 5x8x8x128->256 (tail)", sg::kConvS2, 5, 8, 8, 128, 256, true));
+    RUN(test_conv("convS2 4x64x64x32->32 (thin)", sg::kConvS2, 4, 64, 64, 32, 32, true));
+    RUN(test_conv("convS2 4x32x32x32->64 (thin)", sg::kConvS2, 4, 32, 32, 32, 64, false));
+    RUN(test_conv("convT 8x4x4x256->128", sg::kConvT, 8, 4, 4, 256, 128, false));
+    RUN(test_conv("convT 8x4x4x256->128 +epi", sg::kConvT, 8, 4, 4, 256, 128, true));
+    RUN(test_conv("convT 4x16x16x64->32", sg::kConvT, 4, 16, 16, 64, 32, true));
+    RUN(test_conv("convT 2x32x32x32->32 (thin)", sg::kConvT, 2, 32, 32, 32, 32, true));
+    RUN(test_conv("convT 3x8x8x512->256", sg::kConvT, 3, 8, 8, 512, 256, false));
+    RUN(test_wgrad("wgrad 8x16x16 128|64", 8, 16, 16, 128, 64));
+    RUN(test_wgrad("wgrad 16x4x4 512|256", 16, 4, 4, 512, 256));
+    RUN(test_wgrad("wgrad 8x8x8 256|128", 8, 8, 8, 256, 128));
+    RUN(test_wgrad("wgrad 2x32x32 32|32 (thin)", 2, 32, 32, 32, 32));
+    RUN(test_wgrad("wgrad 3x16x16 64|32 (thin)", 3, 16, 16, 64, 32));
+    RUN(test_wgrad("wgrad 5x4x4 256|128 (tail)", 5, 4, 4, 256, 128));
+    printf("harness: %d failing tests\n", fails);
+    if (argc > 1 && !strcmp(argv[1], "perf") && fails == 0) {
+        const int B = 4096;
+        perf_conv("D c1 64->128 @32x32", sg::kConvS2, B, 32, 32, 64, 128);
+        perf_conv("D c2 128->256 @16x16", sg::kConvS2, B, 16, 16, 128, 256);
+        perf_conv("D c3 256->512 @8x8", sg::kConvS2, B, 8, 8, 256, 512);
+        perf_conv("G up0 256->128 @4x4", sg::kConvT, B, 4, 4, 256, 128);
+        perf_conv("G up1 128->64 @8x8", sg::kConvT, B, 8, 8, 128, 64);
+        perf_conv("G up2 64->32 @16x16", sg::kConvT, B, 16, 16, 64, 32);
+        perf_conv("G up3 32->32 @32x32", sg::kConvT, B, 32, 32, 32, 32);
+        perf_conv("D dgrad c3 512->256 @4x4", sg::kConvT, B, 4, 4, 512, 256);
+        perf_conv("D dgrad c2 256->128 @8x8", sg::kConvT, B, 8, 8, 256, 128);
+        perf_conv("D dgrad c1 128->64 @16x16", sg::kConvT, B, 16, 16, 128, 64);
+        perf_wgrad("wgrad c3 512|256 @4x4", B, 4, 4, 512, 256);
+        perf_wgrad("wgrad c2 256|128 @8x8", B, 8, 8, 256, 128);
+        perf_wgrad("wgrad c1 128|64 @16x16", B, 16, 16, 128, 64);
+        perf_wgrad("wgrad up3 32|32 @32x32", B, 32, 32, 32, 32);
+    }
+    return fails ? 1 : 0;
+}
