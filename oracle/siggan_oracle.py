@@ -294,8 +294,9 @@ def g_step(g_sd, d_sd, g_opt: AdamState, noise: Tensor, image_size: int = 64, lr
 def _hash_uniform(n: int, seed: int) -> Tensor:
     """Counter-based uniform(0,1) floats that do not depend on torch's RNG streams (splitmix64)."""
     import numpy as np
-    x = (np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    base = np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
     with np.errstate(over="ignore"):
+        x = np.arange(n, dtype=np.uint64) + base
         x = (x + np.uint64(0x9E3779B97F4A7C15))
         x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)

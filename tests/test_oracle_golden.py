@@ -1,0 +1,118 @@
+"""Pins oracle/siggan_oracle.py to the reference through the committed golden fixtures
+(tests/golden/*.pt, produced by tests/golden/make_golden.py from /root/reference/src)."""
+import os
+
+import pytest
+import torch
+
+import siggan_oracle as O
+
+RTOL = 2e-4   # fp32 CPU forward
+GTOL = 5e-3   # gradients: hand-written backward vs autograd differ by summation order, amplified by the
+              # B=4 BatchNorm chain (rstd up to ~300)
+
+
+def check_probe(name, t, pr, rtol=RTOL, atol=1e-6):
+    t = t.detach().to(torch.float32).reshape(-1)
+    assert t.numel() == pr["numel"], name
+    scale = pr["norm"] / max(pr["numel"], 1) ** 0.5
+    got = t[pr["idx"]]
+    # norm-relative over the sampled elements (long fp32 reductions cancel, max-abs is too brittle)
+    err = (got - pr["vals"]).double().norm().item()
+    ref = pr["vals"].double().norm().item()
+    assert err <= rtol * max(ref, scale * len(got) ** 0.5) + atol * len(got) ** 0.5, \
+        f"{name}: sampled err {err} vs ref {ref} (rms {scale})"
+    assert abs(float(t.double().norm()) - pr["norm"]) <= rtol * pr["norm"] + atol, f"{name}: norm"
+
+
+@pytest.mark.parametrize("size", [64, 128])
+def test_forward_and_backward_match_reference(golden_dir, size):
+    gold = torch.load(os.path.join(golden_dir, f"forward_{size}.pt"), weights_only=False)
+    B = gold["B"]
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=1)
+    z = O.hash_normal((B, 100), 11)
+    real = O.synthetic_signatures(B, size, seed=5)
+    nb = len(O.g_channels(size)) - 1
+    for mode in ("eval", "train"):
+        img, cache, stats = O.g_forward(g_sd, z, size, train=(mode == "train"))
+        check_probe(f"g_{mode}.out", img, gold[f"g_{mode}.out"])
+        check_probe(f"g_{mode}.fc", cache["fc.a"], gold[f"g_{mode}.fc"])
+        for i in range(nb):
+            check_probe(f"g_{mode}.up{i}", cache[f"up{i}.a"], gold[f"g_{mode}.up{i}"])
+        if mode == "train":
+            for k, v in stats.items():
+                ref = gold[f"g_train.stats.{k}"]
+                if isinstance(ref, dict):
+                    check_probe(k, v, ref)
+                else:
+                    assert int(v) == int(ref), k
+    p, cache = O.d_forward(d_sd, real, size, None)
+    assert torch.allclose(p, gold["d_eval.prob"], rtol=RTOL, atol=1e-6)
+    check_probe("d_eval.feat", cache["feat"], gold["d_eval.feat"])
+    for i in range(len(O.d_channels(size)) - 1):
+        check_probe(f"d_eval.c{i}", cache[f"c{i}.a"], gold[f"d_eval.c{i}"])
+    p, _ = O.d_forward(d_sd, real, size, gold["d_train.masks"])
+    assert torch.allclose(p, gold["d_train.prob"], rtol=RTOL, atol=1e-6)
+    # hand-written backward vs the reference's autograd
+    img, gc, _ = O.g_forward(g_sd, z, size, train=True)
+    pr, dc = O.d_forward(d_sd, img, size, None)
+    ones = torch.ones_like(pr)
+    assert abs(float(O.bce(pr, ones)) - gold["bwd.loss"]) < 1e-5
+    dg = O.d_backward(d_sd, dc, O.bce_grad(pr, ones), size, None, need_dx=True)
+    gg = O.g_backward(g_sd, gc, dg["__dx"], size, train=True)
+    for k in O.trainable_names(g_sd):
+        # fc.0.bias feeds a BatchNorm: its gradient is mathematically zero (pure rounding noise in both).
+        check_probe(f"g_grad.{k}", gg[k], gold[f"bwd.g_grad.{k}"], rtol=GTOL, atol=2e-8 if k != "fc.0.bias" else 1e-6)
+    for k in O.trainable_names(d_sd):
+        check_probe(f"d_grad.{k}", dg[k], gold[f"bwd.d_grad.{k}"], rtol=GTOL, atol=2e-8)
+
+
+@pytest.mark.parametrize("size", [64, 128])
+def test_training_steps_match_reference(golden_dir, size):
+    gold = torch.load(os.path.join(golden_dir, f"steps_{size}.pt"), weights_only=False)
+    B = gold["B"]
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=2)
+    g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
+    d_opt = O.AdamState(d_sd, O.trainable_names(d_sd))
+    for s in range(gold["steps"]):
+        real = O.synthetic_signatures(B, size, seed=100 + s)
+        nd, ng = O.hash_normal((B, 100), 200 + s), O.hash_normal((B, 100), 300 + s)
+        mk = gold["masks"][s]
+        md, dgr, _ = O.d_step(g_sd, d_sd, d_opt, real, nd, size, mk["real"], mk["fake"])
+        for k in O.trainable_names(d_sd):
+            check_probe(f"s{s}.d_grad.{k}", dgr[k], gold[f"s{s}.d_grad.{k}"], rtol=GTOL, atol=2e-8)
+            check_probe(f"s{s}.d_param.{k}", d_sd[k], gold[f"s{s}.d_param.{k}"])
+        mg, ggr, _ = O.g_step(g_sd, d_sd, g_opt, ng, size)
+        for k in O.trainable_names(g_sd):
+            if k != "fc.0.bias":
+                check_probe(f"s{s}.g_grad.{k}", ggr[k], gold[f"s{s}.g_grad.{k}"], rtol=GTOL, atol=2e-8)
+                check_probe(f"s{s}.g_param.{k}", g_sd[k], gold[f"s{s}.g_param.{k}"])
+        for k in g_sd:
+            if "running" in k:
+                check_probe(f"s{s}.g_stats.{k}", g_sd[k], gold[f"s{s}.g_stats.{k}"])
+        md.update(mg)
+        for k, v in gold["metrics"][s].items():
+            assert abs(md[k] - v) <= 2e-4 * max(1.0, abs(v)), (s, k, md[k], v)
+    assert gold["d_adam.keys"] == ["exp_avg", "exp_avg_sq", "step"]
+    assert gold["d_adam.step"] == gold["steps"]
+    check_probe("d_adam.exp_avg", d_opt.m["conv_blocks.0.block.0.weight"], gold["d_adam.exp_avg.0"], atol=2e-8)
+    check_probe("d_adam.exp_avg_sq", d_opt.v["conv_blocks.0.block.0.weight"], gold["d_adam.exp_avg_sq.0"], atol=1e-12)
+
+
+def test_closed_form_facts():
+    """Facts SURVEY.md §8c lists, restated numerically on the oracle."""
+    # ConvTranspose index rule oy = 2*iy - 1 + ky
+    x = torch.zeros(1, 1, 4, 4); x[0, 0, 1, 2] = 1.0
+    w = torch.zeros(1, 1, 4, 4); w[0, 0, 3, 0] = 1.0
+    y = torch.nn.functional.conv_transpose2d(x, w, stride=2, padding=1)
+    assert y[0, 0, 2 * 1 - 1 + 3, 2 * 2 - 1 + 0] == 1.0 and y.sum() == 1.0
+    # BCE clamp and gradient epsilon
+    p = torch.tensor([[0.0], [1.0]]); t = torch.tensor([[1.0], [1.0]])
+    assert float(O.bce(p, t)) == 50.0
+    assert float(O.bce_grad(p, t)[0]) == pytest.approx(-1.0 / 1e-12 / 2)
+    # dropout masks take values {0, 4/3}
+    m = O.make_dropout_masks(8, 64, seed=3)
+    vals = torch.cat([v.reshape(-1) for v in m]).unique().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and vals[1] == pytest.approx(4 / 3)
+    img = O.synthetic_signatures(4, 64)
+    assert img.shape == (4, 1, 64, 64) and img.max() <= 1 and img.min() >= -1 and (img < 0).any()
