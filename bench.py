@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — training images/sec (full D+G step) and sampling images/sec of the B200 signature-GAN path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, NCCL)
+
+One "step" = one full adversarial training step (D step + G step, vanilla_gan_model.VanillaGAN.train_step) over a
+batch of 4096 synthetic 64x64 signatures per GPU (BASELINE.json configs[2]); weak scaling over data-parallel ranks
+with an NCCL all-reduce of the flat D and G gradient buckets. Rank 0 prints ONE JSON line.
+`--impl reference` times the CPU implementation of the same step (the oracle port of the reference's algorithm, torch
+CPU fp32, all host threads) on a bounded sample (batch 64 per step, the reference's own default configuration).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "signature-gan_b200"))
+
+FLOP_PER_IMG_TRAIN = {64: 1.9707e9, 128: 9.2199e9}     # algorithmically necessary conv/linear FLOPs
+FLOP_PER_IMG_SAMPLE = {64: 87.06e6, 128: 413.73e6}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--sampling-batch", type=int, default=16384)
+    ap.add_argument("--cpu-batch", type=int, default=64)
+    ap.add_argument("--no-extras", action="store_true", help="skip sampling / cpu baseline / per-op profile")
+    return ap.parse_args()
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic signatures (white background +1, dark strokes -1), generated with torch on the target device
+# ------------------------------------------------------------------------------------------------
+def synthetic_signatures(n, size, device, seed=1234):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.linspace(0, 1, 192, device=device).view(1, 1, -1)
+    u = torch.rand(n, 3, 16, device=device, generator=g)
+
+    def U(k, lo, hi):
+        return (lo + (hi - lo) * u[:, :, k]).unsqueeze(-1)
+
+    x = U(0, .4, .6) + U(2, .5, .8) * (t - .5)
+    y = U(1, .35, .65) + U(3, -.1, .1) * (t - .5)
+    for k in range(1, 4):
+        x = x + U(3 + k, -.06, .06) / k * torch.sin(2 * math.pi * (k * t + U(9 + k, 0, 1)))
+        y = y + U(6 + k, -.18, .18) / k * torch.sin(2 * math.pi * (k * t + U(12 + k, 0, 1)))
+    xi = (x.clamp(0, 1) * (size - 1)).round().long().reshape(n, -1)
+    yi = (y.clamp(0, 1) * (size - 1)).round().long().reshape(n, -1)
+    ink = torch.zeros(n, size * size, device=device)
+    ink.scatter_(1, yi * size + xi, 1.0)
+    ink = ink.view(n, 1, size, size)
+    ink = torch.nn.functional.avg_pool2d(torch.nn.functional.max_pool2d(ink, 3, 1, 1), 3, 1, 1)
+    return (1.0 - 2.0 * ink).clamp(-1, 1).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={ident}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                        "reasons": sorted(reasons), "samples": len(sm)})
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's D step + G step (torch CPU fp32, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_imgs_per_s(size, batch, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import siggan_oracle as O
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=0)
+    g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
+    d_opt = O.AdamState(d_sd, O.trainable_names(d_sd))
+    real = O.synthetic_signatures(batch, size, seed=1234)
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        masks_r, masks_f = O.make_dropout_masks(batch, size, 2 * i), O.make_dropout_masks(batch, size, 2 * i + 1)
+        O.d_step(g_sd, d_sd, d_opt, real, torch.randn(batch, 100), size, masks_r, masks_f)
+        O.g_step(g_sd, d_sd, g_opt, torch.randn(batch, 100), size)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ips, spp, threads = cpu_train_imgs_per_s(args.size, args.cpu_batch, args.steps, args.warmup)
+    sample = f"{args.steps} steps of batch {args.cpu_batch} ({args.size}x{args.size}) on the host CPU, {args.warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": "training images/sec (G+D step)", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"train_step_{args.size}x{args.size}", "batch_per_step": args.cpu_batch,
+                   "note": "oracle port of the reference algorithm on torch CPU (the reference is pure PyTorch)"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import _siggan_lib as L
+    from vanilla_gan_model import VanillaGAN
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S = args.batch, args.size
+    torch.manual_seed(1234 + rank)
+    gan = VanillaGAN(latent_dim=100, image_size=S, device=str(dev))
+    gan._fused_ready()
+    if world > 1:   # identical initial replicas
+        dist.broadcast(gan.generator._flat.flat, 0)
+        dist.broadcast(gan.generator._flat.stats, 0)
+        dist.broadcast(gan.discriminator._flat.flat, 0)
+    lib = L.load_library()
+    n_pool = 4     # 4 distinct real batches (268 MB fp32 at B=4096) > 126 MB L2; activations per step are several GB
+    pool = synthetic_signatures(n_pool * B, S, dev, seed=1234 + rank).view(n_pool, B, 1, S, S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region --------------------------------------------------------------
+    for i in range(args.warmup):
+        gan.train_step_async(pool[i % n_pool])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.sg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        metrics = gan.train_step_async(pool[i % n_pool])
+    e1.record()
+    barrier()
+    launches = lib.sg_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    last_metrics = metrics.tolist()
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host-resident (pinned) real batches, H2D copy + D2H metric read every step ----
+    host_pool = torch.empty(n_pool, B, 1, S, S, dtype=torch.float32).pin_memory()
+    host_pool.copy_(pool)
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [torch.empty(B, 1, S, S, device=dev), torch.empty(B, 1, S, S, device=dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2].copy_(host_pool[i % n_pool], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for phase_steps, timed in ((2, False), (e2e_steps, True)):
+        barrier()
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        prefetch(0)
+        t0 = time.perf_counter()
+        for i in range(phase_steps):
+            torch.cuda.current_stream(dev).wait_event(ready[i % 2])
+            if i + 1 < phase_steps:   # buffer (i+1)%2 was last read by step i-1, which has completed (train_step syncs)
+                prefetch(i + 1)
+            out = gan.train_step(bufs[i % 2])        # public API: returns python floats (device->host read)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t)
+    clocks = sampler.stop() if sampler else None
+
+    line = {
+        "metric": "training images/sec (G+D step)", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"train_step_{S}x{S}_b{B}_per_gpu", "global_batch": world * B, "image_size": S,
+                   "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1,
+                   "l2": "4 rotating real batches (268 MB) and multi-GB per-step activations exceed the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": 48,
+                "steps": e2e_steps, "api": "VanillaGAN.train_step(real) from pinned host batches, double-buffered H2D"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "last_metrics": {k: round(v, 5) for k, v in zip(
+            ["d_loss", "d_loss_real", "d_loss_fake", "d_real_acc", "d_fake_acc", "d_real_mean", "d_fake_mean", "g_loss",
+             "g_fake_mean"], last_metrics)},
+    }
+    pk = peaks()
+    step_tflops = FLOP_PER_IMG_TRAIN[S] * value / world / 1e12
+    line["step_tensor"] = {"achieved": step_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                           "frac": step_tflops / pk["bf16_tflops_sustained"], "peak_source": pk["source"],
+                           "flop_per_image": FLOP_PER_IMG_TRAIN[S]}
+
+    if not args.no_extras:
+        sctx = gan.generator._ctx
+        # ---- per-op device times (CUDA events inside the library, on the launch stream) ----------------
+        prof_steps = 3
+        barrier()
+        sctx.profile(True)
+        for i in range(prof_steps):
+            gan.train_step_async(pool[i % n_pool])
+        recs = sctx.profile_records()
+        sctx.profile(False)
+        agg = {}
+        for name, ms_, fl, by in recs:
+            a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            a[0] += ms_; a[1] += fl; a[2] += by; a[3] += 1
+        tot = sum(a[0] for a in agg.values())
+        ops = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        tensor_ops = [(k, a) for k, a in ops if a[1] > 0 and ("wgrad" in k or "dgrad" in k or k[-1].isdigit() or k == "g.fc")
+                      and not k.startswith("d.c0")]
+        if tensor_ops:
+            k, a = tensor_ops[0]
+            ach = a[1] / (a[0] * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": k, "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                                "ms_per_launch": a[0] / a[3], "share_of_step": a[0] / tot, "peak_source": pk["source"]}
+        line["ops_ms_per_step"] = {k: round(a[0] / prof_steps, 4) for k, a in ops[:24]}
+        line["ops_total_ms_per_step"] = tot / prof_steps
+        tens = sum(a[0] for k, a in tensor_ops)
+        tfl = sum(a[1] for k, a in tensor_ops)
+        line["tensor_ops"] = {"share_of_step": tens / tot, "achieved_tflops": tfl / (tens * 1e-3) / 1e12 if tens else None}
+
+        # ---- sampling (BASELINE.json configs[1]): generator only, eval mode ----------------------------
+        if rank == 0:
+            SB = args.sampling_batch
+            G = gan.generator
+            G.eval()
+            gz = torch.Generator(device=dev).manual_seed(0)
+            z = torch.randn(SB, 100, device=dev, generator=gz)
+            with torch.no_grad():
+                for _ in range(3):
+                    G(z)
+                torch.cuda.synchronize()
+                e0.record()
+                iters = 10
+                for _ in range(iters):
+                    G(z)
+                e1.record()
+                torch.cuda.synchronize()
+                samp_ms = e0.elapsed_time(e1) / iters
+                for _ in range(2):
+                    G.sample_uint8(z)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(iters):
+                    G.sample_uint8(z)
+                e1.record()
+                torch.cuda.synchronize()
+                samp8_ms = e0.elapsed_time(e1) / iters
+                zh = z.cpu().pin_memory()
+                out_h = torch.empty(SB, 1, S, S, dtype=torch.uint8).pin_memory()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    out_h.copy_(G.sample_uint8(zh.to(dev, non_blocking=True)), non_blocking=True)
+                    torch.cuda.synchronize()
+                samp_e2e = 5 * SB / (time.perf_counter() - t0)
+            sf = FLOP_PER_IMG_SAMPLE[S] * SB / (samp_ms * 1e-3) / 1e12
+            line["sampling"] = {"batch": SB, "images_per_s_fp32_out": SB / (samp_ms * 1e-3),
+                                "images_per_s_uint8_out": SB / (samp8_ms * 1e-3), "ms_fp32_out": samp_ms,
+                                "achieved_tflops": sf, "tensor_frac": sf / pk["bf16_tflops"],
+                                "e2e_images_per_s_uint8_host": samp_e2e,
+                                "e2e_bytes": {"h2d": SB * 400, "d2h": SB * S * S}}
+        # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------
+        if rank == 0 and world == 1:
+            steps_cpu = 12
+            ips, spp, threads = cpu_train_imgs_per_s(S, args.cpu_batch, steps_cpu, 2)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"{steps_cpu} D+G steps of batch {args.cpu_batch} ({S}x{S}), torch CPU fp32, "
+                                              f"{os.cpu_count()} logical cpus"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under the launcher so that there is one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

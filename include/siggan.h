@@ -1,0 +1,133 @@
+/* siggan.h — C ABI of libsiggan.so, the B200 (sm_100a) implementation of signature-Gan's
+ * adversarial-training and sampling hot path.
+ *
+ * The reference (Nobita421/signature-Gan) is pure Python/PyTorch and has no FFI of its own; the
+ * "operator interface" this library replaces is the set of torch.nn / torch.optim calls made by
+ *   src/generator_vanilla_gan.py:189-209      Generator.forward            -> sg_g_forward / sg_g_backward
+ *   src/discriminator_vanilla_gan.py:241-274  Discriminator.forward(_features) -> sg_d_forward / sg_d_backward
+ *   src/vanilla_gan_model.py:107              nn.BCELoss                   -> sg_bce_forward / sg_bce_backward
+ *   src/vanilla_gan_model.py:110-120          optim.Adam(...).step()       -> sg_adam_step
+ *   src/vanilla_gan_model.py:180-336          train_*_step / train_step    -> sg_train_step
+ *   src/utils/inference.py:129                ((x+1)*127.5).clip -> uint8  -> `out_u8` of sg_g_forward
+ * The Python drop-in modules (the .py files in signature-gan_b200) bind these with ctypes; INTEGRATION.md shows
+ * the stub.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless named host_*. Images are (B,1,S,S) fp32, latents (B,latent) fp32.
+ *  - Parameters / gradients / Adam moments are flat fp32 buffers laid out in the reference's
+ *    `named_parameters()` order (sg_tensor_info gives offset + shape); BatchNorm running statistics are
+ *    a flat fp32 buffer laid out as [running_mean | running_var] per BN layer in module order.
+ *  - All calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*); no call synchronises unless
+ *    it has to grow library-owned scratch (first call at a new maximum batch).
+ *  - Return value: 0 = ok, negative = error (message from sg_last_error(), thread-local). Nothing throws
+ *    or exits across this boundary. One sg_ctx per (process, device); a ctx is not re-entrant.
+ *  - There is no CPU implementation behind these symbols.
+ */
+#ifndef SIGGAN_H
+#define SIGGAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+enum { SG_PREC_BF16 = 0, SG_PREC_FP32 = 1 };
+enum { SG_NET_G = 0, SG_NET_D = 1 };
+
+typedef struct sg_ctx sg_ctx;
+
+typedef struct sg_config {
+    int image_size;   /* 64 or 128 (gen…:106-107, disc…:121-122) */
+    int latent_dim;   /* default 100 */
+    int precision;    /* SG_PREC_BF16: bf16 operands, fp32 accumulate, tcgen05; SG_PREC_FP32: validation mode */
+    float leaky_slope; /* 0.2 (disc…:46) */
+    float bn_eps;      /* 1e-5 */
+    float bn_momentum; /* 0.1 */
+} sg_config;
+
+int sg_abi_version(void);
+const char* sg_last_error(void);
+
+/* Kernels enqueued by this library in this process so far (host-side count; bench.py's gpu_launches). */
+unsigned long long sg_launch_count(void);
+
+int sg_create(const sg_config* cfg, sg_ctx** out);
+void sg_destroy(sg_ctx* ctx);
+
+/* ---- layout of the flat buffers -------------------------------------------------------------- */
+int sg_num_tensors(const sg_ctx* ctx, int net);
+/* name is the reference state_dict key; shape has up to 4 dims (unused = 0). */
+int sg_tensor_info(const sg_ctx* ctx, int net, int index, const char** name, long long* offset, int shape[4]);
+long long sg_param_count(const sg_ctx* ctx, int net);
+long long sg_g_stat_count(const sg_ctx* ctx);          /* floats in the running-stat buffer */
+int sg_g_num_bn(const sg_ctx* ctx);
+int sg_g_bn_info(const sg_ctx* ctx, int index, long long* mean_offset, long long* var_offset, int* channels);
+size_t sg_g_workspace_bytes(const sg_ctx* ctx, int batch);   /* saved activations of one G forward */
+size_t sg_d_workspace_bytes(const sg_ctx* ctx, int batch);   /* saved activations of one D forward */
+long long sg_d_mask_count(const sg_ctx* ctx, int batch);     /* floats: sum_i batch*C_i */
+long long sg_d_feature_count(const sg_ctx* ctx);             /* 512*4*4 */
+
+/* ---- Generator ------------------------------------------------------------------------------ */
+/* bn_batch_stats != 0: training-mode BatchNorm (batch statistics; running stats updated in place).
+ * ws may be NULL when no backward will follow (sampling). out_u8 (optional) receives the
+ * ((x+1)*127.5).clip(0,255) uint8 image of utils/inference.py:129. */
+int sg_g_forward(sg_ctx* ctx, const float* params, float* running_stats, const float* z, int batch,
+                 int bn_batch_stats, void* ws, float* out_image, uint8_t* out_u8, void* stream);
+/* grads_out: flat fp32, overwritten. dz_out optional (batch x latent). Must follow sg_g_forward with the same ws. */
+int sg_g_backward(sg_ctx* ctx, const float* params, const void* ws, const float* grad_image, int batch,
+                  int bn_batch_stats, float* grads_out, float* dz_out, void* stream);
+
+/* ---- Discriminator -------------------------------------------------------------------------- */
+/* masks: Dropout2d keep-scale per (n,c) for each block (sg_d_mask_count floats) or NULL for eval mode. */
+int sg_d_forward(sg_ctx* ctx, const float* params, const float* x, int batch, const float* masks, void* ws,
+                 float* prob_out, float* features_out, void* stream);
+/* grads_out NULL => skip weight gradients; dx_out NULL => skip the image gradient. */
+int sg_d_backward(sg_ctx* ctx, const float* params, const float* x, const void* ws, const float* masks,
+                  const float* grad_prob, int batch, float* grads_out, float* dx_out, void* stream);
+/* Fills masks with {0, 1/(1-p)} from a counter-based generator (seed, offset). */
+int sg_dropout_masks(sg_ctx* ctx, uint64_t seed, uint64_t offset, int batch, float p, float* masks_out, void* stream);
+
+/* ---- nn.BCELoss on probabilities (log clamp -100, grad eps 1e-12) ----------------------------- */
+int sg_bce_forward(const float* prob, const float* target, int n, float* loss_out, void* stream);
+/* dprob = grad_loss[0] * (p - y) / max(p(1-p), 1e-12) / n */
+int sg_bce_backward(const float* prob, const float* target, int n, const float* grad_loss, float* dprob_out,
+                    void* stream);
+
+/* ---- torch.optim.Adam (wd = 0, amsgrad = False) over a flat buffer ---------------------------- */
+int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                 float beta1, float beta2, float eps, long long step, void* stream);
+
+/* ---- Fused D step + G step (vanilla…:308-336 with n_critic = 1) ------------------------------- */
+typedef struct sg_train_state {
+    float* g_params; float* g_running_stats; float* g_exp_avg; float* g_exp_avg_sq;
+    float* d_params; float* d_exp_avg; float* d_exp_avg_sq;
+    long long g_step; long long d_step;            /* Adam step counts BEFORE this call */
+    float g_lr, d_lr, beta1, beta2, eps;
+    float label_smoothing;                         /* 0.9 */
+    float dropout_p;                               /* 0.25; <= 0 disables */
+    uint64_t seed; uint64_t offset;                /* dropout RNG counter (ignored when masks given) */
+    const float* masks_real; const float* masks_fake; /* optional injected masks (parity tests) */
+    int world_size;                                /* >1: caller all-reduces the gradient buckets between phases */
+} sg_train_state;
+
+/* metrics_out (device, 12 floats): d_loss, d_loss_real, d_loss_fake, d_real_acc, d_fake_acc, d_real_mean,
+ * d_fake_mean, g_loss, g_fake_mean, 0, 0, 0.  phase: 0 = whole step; 1 = D forward+backward only (grads in
+ * d_grads), 2 = D Adam, 3 = G forward+backward (grads in g_grads), 4 = G Adam — phases let a data-parallel
+ * caller all-reduce the flat gradient buckets between backward and update. */
+int sg_train_step(sg_ctx* ctx, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
+                  int batch, float* d_grads, float* g_grads, float* metrics_out, int phase, void* stream);
+
+/* ---- measurement aid: per-operation device time (CUDA events on the launch stream) --------------- */
+/* on != 0 starts recording (and clears earlier records); every op of the plans is bracketed by two events. */
+int sg_profile_enable(sg_ctx* ctx, int on);
+/* Synchronises, then writes "name<TAB>ms<TAB>algorithmic flops<TAB>algorithmic bytes" lines; returns bytes written. */
+long long sg_profile_dump(sg_ctx* ctx, char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGGAN_H */

@@ -8,6 +8,7 @@
 // implements the padding. The 128 box rows land as a canonical K-major swizzled UMMA operand.
 #include "sg_conv_umma.cuh"
 #include "sg_umma.cuh"
+#include "sg_kernels.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -301,6 +302,7 @@ static int launch_cfg(const ConvGemmArgs& a, dim3 grid, cudaStream_t stream) {
         if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(conv_umma<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
         attr_set = true;
     }
+    note_launch();
     conv_umma_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("conv_umma<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_umma_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x;
     const int n_tiles = (args.Nf + BN - 1) / BN;
+    const int taps = args.plain ? 1 : 16;
     const int tap = blockIdx.y / n_tiles;
     const int tile_n = blockIdx.y - tap * n_tiles;
     const int split = blockIdx.z;
@@ -439,9 +442,16 @@ __global__ void __launch_bounds__(kThreads) wgrad_umma_kernel(const __grid_const
                 }
                 tma_load_2d(sa, &args.cmap, &full_bar[s], tile_m * 128, kt * kWgK);
                 tma_load_2d(sa + Cfg::kAtomBytes, &args.cmap, &full_bar[s], tile_m * 128 + 64, kt * kWgK);
+                if (args.plain) {
 #pragma unroll
-                for (int a = 0; a < BN / 64; ++a)
-                    tma_load_4d(sb + a * Cfg::kAtomBytes, fm, &full_bar[s], tile_n * BN + a * 64, dx, y0 + dy, n0);
+                    for (int a = 0; a < BN / 64; ++a)
+                        tma_load_2d(sb + a * Cfg::kAtomBytes, &args.fmap[0], &full_bar[s], tile_n * BN + a * 64,
+                                    kt * kWgK);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < BN / 64; ++a)
+                        tma_load_4d(sb + a * Cfg::kAtomBytes, fm, &full_bar[s], tile_n * BN + a * 64, dx, y0 + dy, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_umma_kernel(const __grid_const
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        float* dst = args.partial + ((static_cast<size_t>(split) * 16 + tap) * args.Mc + m) * args.Nf;
+        float* dst = args.partial + ((static_cast<size_t>(split) * taps + tap) * args.Mc + m) * args.Nf;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -516,9 +526,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
-static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles) {
+static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16) {
     // Aim for ~2 waves of 148 SMs, at least 8 K-tiles per CTA.
-    const int base = m_tiles * n_tiles * 16;
+    const int base = m_tiles * n_tiles * taps;
     int s = (2 * 148 + base - 1) / base;
     if (s < 1) s = 1;
     const int max_s = k_tiles / 8 > 0 ? k_tiles / 8 : 1;
@@ -546,6 +556,7 @@ static int launch_wg(const WgradArgs& a, dim3 grid, cudaStream_t stream) {
         if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(wgrad_umma<%d>): %s", BN, cudaGetErrorString(e));
         attr_set = true;
     }
+    note_launch();
     wgrad_umma_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("wgrad_umma<%d> launch: %s", BN, cudaGetErrorString(e));
@@ -587,9 +598,64 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     const long total = static_cast<long>(Mc) * Nf * 16;
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    note_launch();
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, a.splits, Mc, Nf, accumulate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("wgrad_reduce launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Generator fc weight gradient: dW[f(j)][i] = sum_b dy[b][j] * zp[b][i]  (j = NHWC column, f = NCHW feature).
+__global__ void fc_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int S, int F, int Kp,
+                                       int C0, int latent) {
+    const long total = static_cast<long>(F) * latent;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % latent);
+        const int j = static_cast<int>(i / latent);
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += partial[(static_cast<size_t>(s) * F + j) * Kp + k];
+        const int f = (j % C0) * 16 + j / C0;
+        dW[static_cast<long>(f) * latent + k] = acc;
+    }
+}
+
+size_t fc_wgrad_partial_floats(int B, int F, int Kp) {
+    const int k_tiles = (B + kWgK - 1) / kWgK;
+    const int BN = wgrad_bn(Kp);
+    const int s = wgrad_splits(k_tiles, (F + 127) / 128, (Kp + BN - 1) / BN, 1);
+    return static_cast<size_t>(s) * F * Kp;
+}
+
+int launch_fc_wgrad(const __nv_bfloat16* dy, const __nv_bfloat16* zp, int B, int C0, int Kp, int latent, float* partial,
+                    size_t partial_floats, float* dW, cudaStream_t stream) {
+    const int F = C0 * 16;
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.plain = 1;
+    a.GH = 1;
+    a.GW = kWgK;
+    a.nimg = B;
+    a.Mc = F;
+    a.Nf = Kp;
+    a.k_tiles = (B + kWgK - 1) / kWgK;
+    const int BN = wgrad_bn(Kp);
+    const int m_tiles = (F + 127) / 128, n_tiles = (Kp + BN - 1) / BN;
+    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 1);
+    a.partial = partial;
+    if (static_cast<size_t>(a.splits) * F * Kp > partial_floats) SG_FAIL("fc_wgrad: partial workspace too small");
+    if (make_map_2d(&a.cmap, dy, F, B, F, 64, kWgK)) return -1;
+    if (make_map_2d(&a.fmap[0], zp, Kp, B, Kp, 64, kWgK)) return -1;
+    dim3 grid(m_tiles, n_tiles, a.splits);
+    int rc = BN == 256 ? launch_wg<256>(a, grid, stream) : (BN == 128 ? launch_wg<128>(a, grid, stream) : launch_wg<64>(a, grid, stream));
+    if (rc) return rc;
+    const long total = static_cast<long>(F) * latent;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    note_launch();
+    fc_wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, a.splits, F, Kp, C0, latent);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) SG_FAIL("fc_wgrad_reduce launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -50,6 +50,7 @@ struct WgradArgs {
     int Mc, Nf;           // channels of coarse / fine tensors
     int k_tiles;          // ceil(nimg*GH*GW / 64)
     int splits;
+    int plain;            // 1: no taps, fmap[0] is a 2-D [pixels][Nf] map (Generator fc weight gradient)
     float* partial;  // [splits][16][Mc][Nf]
 };
 
@@ -70,6 +71,11 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
 int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
                  float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream);
 size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf);
+
+// Generator fc weight gradient (plain MN-major GEMM over the batch), un-permuting rows into dW (F, latent).
+size_t fc_wgrad_partial_floats(int B, int F, int Kp);
+int launch_fc_wgrad(const __nv_bfloat16* dy, const __nv_bfloat16* zp, int B, int C0, int Kp, int latent, float* partial,
+                    size_t partial_floats, float* dW, cudaStream_t stream);
 
 const char* umma_last_error();
 

@@ -1,0 +1,1182 @@
+// sg_kernels.cu — CUDA-core kernels of the siggan hot path (see sg_kernels.cuh).
+#include "sg_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+
+namespace sg {
+
+unsigned long long g_launches = 0;
+static thread_local char k_err[256] = "";
+const char* kernels_last_error() { return k_err; }
+int kernels_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(k_err, sizeof(k_err), "%s: %s", what, cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element access helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+static inline int blocks_for(long n, int threads, int cap = 148 * 16) {
+    long b = (n + threads - 1) / threads;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_w16_kernel(const float* __restrict__ src, bf16* __restrict__ dstAB, bf16* __restrict__ dstBA,
+                                int A, int B) {
+    const long total = static_cast<long>(A) * B * 16;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i & 15);
+        const long ab = i >> 4;
+        const int b = static_cast<int>(ab % B);
+        const int a = static_cast<int>(ab / B);
+        const bf16 v = __float2bfloat16(src[i]);
+        if (dstAB) dstAB[(static_cast<long>(a) * 16 + t) * B + b] = v;
+        if (dstBA) dstBA[(static_cast<long>(b) * 16 + t) * A + a] = v;
+    }
+}
+void pack_w16(const float* src, bf16* dstAB, bf16* dstBA, int A, int B, cudaStream_t s) {
+    note_launch();
+    pack_w16_kernel<<<blocks_for(static_cast<long>(A) * B * 16, 256), 256, 0, s>>>(src, dstAB, dstBA, A, B);
+}
+
+__global__ void pack_fc_kernel(const float* __restrict__ W, const float* __restrict__ bias, bf16* __restrict__ Wp,
+                               float* __restrict__ biasp, int C0, int latent, int Kp) {
+    const int F = C0 * 16;
+    const long total = static_cast<long>(F) * Kp;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kp);
+        const int j = static_cast<int>(i / Kp);
+        const int f = (j % C0) * 16 + j / C0;
+        Wp[i] = __float2bfloat16(k < latent ? W[static_cast<long>(f) * latent + k] : 0.f);
+        if (k == 0) biasp[j] = bias[f];
+    }
+}
+void pack_fc(const float* W, const float* bias, bf16* Wp, float* biasp, int C0, int latent, int Kp, cudaStream_t s) {
+    note_launch();
+    pack_fc_kernel<<<blocks_for(static_cast<long>(C0) * 16 * Kp, 256), 256, 0, s>>>(W, bias, Wp, biasp, C0, latent, Kp);
+}
+
+__global__ void pack_classifier_kernel(const float* __restrict__ w, float* __restrict__ wp, int C) {
+    const int F = C * 16;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < F; j += gridDim.x * blockDim.x)
+        wp[j] = w[(j % C) * 16 + j / C];
+}
+void pack_classifier(const float* w, float* wp, int C, cudaStream_t s) {
+    note_launch();
+    pack_classifier_kernel<<<blocks_for(C * 16, 256), 256, 0, s>>>(w, wp, C);
+}
+
+template <typename T>
+__global__ void cast_pad_z_kernel(const float* __restrict__ z, T* __restrict__ zp, int B, int latent, int Kp) {
+    const long total = static_cast<long>(B) * Kp;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kp);
+        const long b = i / Kp;
+        zp[i] = from_f<T>(k < latent ? z[b * latent + k] : 0.f);
+    }
+}
+template <typename T>
+void cast_pad_z(const float* z, T* zp, int B, int latent, int Kp, cudaStream_t s) {
+    note_launch();
+    cast_pad_z_kernel<T><<<blocks_for(static_cast<long>(B) * Kp, 256), 256, 0, s>>>(z, zp, B, latent, Kp);
+}
+template void cast_pad_z<float>(const float*, float*, int, int, int, cudaStream_t);
+template void cast_pad_z<bf16>(const float*, bf16*, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// two-stage deterministic column reductions
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const T* __restrict__ a, const T* __restrict__ y, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ rowscale, long rows, int C,
+                  int cols_per_block, long rows_per_chunk, float* __restrict__ partial) {
+    __shared__ float sm[256 * 8];
+    const int tpr = cols_per_block >> 3;
+    const int rpi = 256 / tpr;
+    const int tcol = threadIdx.x % tpr, trow = threadIdx.x / tpr;
+    const int c0 = blockIdx.x * cols_per_block + tcol * 8;
+    float s0[8], s1[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s0[j] = 0.f;
+        s1[j] = 0.f;
+        mu[j] = (MODE == 1) ? mean[c0 + j] : 0.f;
+        rs[j] = (MODE == 1) ? rstd[c0 + j] : 0.f;
+    }
+    const long r_begin = blockIdx.y * rows_per_chunk;
+    long r_end = r_begin + rows_per_chunk;
+    if (r_end > rows) r_end = rows;
+    for (long r = r_begin + trow; r < r_end; r += rpi) {
+        float v[8];
+        load8(a + r * C + c0, v);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s0[j] += v[j];
+                s1[j] = fmaf(v[j], v[j], s1[j]);
+            }
+        } else if (MODE == 1) {
+            float yv[8];
+            load8(y + r * C + c0, yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s0[j] += v[j];
+                s1[j] = fmaf(v[j], (yv[j] - mu[j]) * rs[j], s1[j]);
+            }
+        } else {
+            const float w = rowscale[r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s0[j] = fmaf(v[j], w, s0[j]);
+        }
+    }
+    float* out = partial + static_cast<long>(blockIdx.y) * 2 * C + c0;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        if (which == 1 && MODE == 2) break;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] = which == 0 ? s0[j] : s1[j];
+        __syncthreads();
+        if (trow == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float acc = 0.f;
+                for (int t = 0; t < rpi; ++t) acc += sm[(t * tpr + tcol) * 8 + j];
+                out[which * C + j] = acc;
+            }
+        }
+    }
+}
+
+template <typename T>
+int col_reduce(int mode, const T* a, const T* y, const float* mean, const float* rstd, const float* rowscale,
+               long rows, int C, float* partial, cudaStream_t s) {
+    const int cpb = C > 2048 ? 2048 : C;
+    const int col_blocks = C / cpb;
+    const int rpi = 256 / (cpb / 8);
+    long chunks = (rows + static_cast<long>(rpi) * 8 - 1) / (static_cast<long>(rpi) * 8);
+    const long cap = kMaxChunks / col_blocks > 0 ? kMaxChunks / col_blocks : 1;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    long rpc = (rows + chunks - 1) / chunks;
+    rpc = (rpc + rpi - 1) / rpi * rpi;
+    chunks = (rows + rpc - 1) / rpc;
+    dim3 grid(col_blocks, static_cast<unsigned>(chunks));
+    note_launch();
+    if (mode == 0)
+        col_reduce_kernel<T, 0><<<grid, 256, 0, s>>>(a, y, mean, rstd, rowscale, rows, C, cpb, rpc, partial);
+    else if (mode == 1)
+        col_reduce_kernel<T, 1><<<grid, 256, 0, s>>>(a, y, mean, rstd, rowscale, rows, C, cpb, rpc, partial);
+    else
+        col_reduce_kernel<T, 2><<<grid, 256, 0, s>>>(a, y, mean, rstd, rowscale, rows, C, cpb, rpc, partial);
+    return static_cast<int>(chunks);
+}
+template int col_reduce<float>(int, const float*, const float*, const float*, const float*, const float*, long, int,
+                               float*, cudaStream_t);
+template int col_reduce<bf16>(int, const bf16*, const bf16*, const float*, const float*, const float*, long, int,
+                              float*, cudaStream_t);
+
+__device__ __forceinline__ int perm_index(int j, int perm_c0) {
+    return perm_c0 > 0 ? (j % perm_c0) * 16 + j / perm_c0 : j;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, long rows, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, int batch_stats, int perm_c0, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= C) return;
+    const int p = perm_index(j, perm_c0);
+    float mu, var;
+    if (batch_stats) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < chunks; ++k) {
+            s0 += partial[static_cast<long>(k) * 2 * C + j];
+            s1 += partial[static_cast<long>(k) * 2 * C + C + j];
+        }
+        const double m = s0 / rows;
+        double v = s1 / rows - m * m;
+        if (v < 0.0) v = 0.0;
+        mu = static_cast<float>(m);
+        var = static_cast<float>(v);
+        const double unbiased = rows > 1 ? v * rows / (rows - 1) : v;
+        running_mean[p] = (1.f - momentum) * running_mean[p] + momentum * mu;
+        running_var[p] = (1.f - momentum) * running_var[p] + momentum * static_cast<float>(unbiased);
+    } else {
+        mu = running_mean[p];
+        var = running_var[p];
+    }
+    const float r = 1.0f / sqrtf(var + eps);
+    mean[j] = mu;
+    rstd[j] = r;
+    const float sc = gamma[p] * r;
+    scale[j] = sc;
+    shift[j] = beta[p] - mu * sc;
+}
+void bn_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
+                 float* mean, float* rstd, float* scale, float* shift, cudaStream_t s) {
+    note_launch();
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, beta, running_mean,
+                                                      running_var, momentum, eps, batch_stats, perm_c0, mean, rstd,
+                                                      scale, shift);
+}
+
+template <typename T>
+__global__ void bn_apply_relu_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, T* __restrict__ a, long n8, int C) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>((i * 8) % C);
+        float v[8];
+        load8(y + i * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], scale[c0 + j], shift[c0 + j]), 0.f);
+        store8(a + i * 8, v);
+    }
+}
+template <typename T>
+void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, cudaStream_t s) {
+    const long n8 = rows * C / 8;
+    note_launch();
+    bn_apply_relu_kernel<T><<<blocks_for(n8, 256), 256, 0, s>>>(y, scale, shift, a, n8, C);
+}
+template void bn_apply_relu<float>(const float*, const float*, const float*, float*, long, int, cudaStream_t);
+template void bn_apply_relu<bf16>(const bf16*, const float*, const float*, bf16*, long, int, cudaStream_t);
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, long rows, int C,
+                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       int batch_stats, int perm_c0, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
+                                       float* __restrict__ k3) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= C) return;
+    const int p = perm_index(j, perm_c0);
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        s0 += partial[static_cast<long>(k) * 2 * C + j];
+        s1 += partial[static_cast<long>(k) * 2 * C + C + j];
+    }
+    dbeta[p] = static_cast<float>(s0);
+    dgamma[p] = static_cast<float>(s1);
+    k1[j] = gamma[p] * rstd[j];
+    k2[j] = batch_stats ? static_cast<float>(s0 / rows) : 0.f;
+    k3[j] = batch_stats ? static_cast<float>(s1 / rows) : 0.f;
+}
+void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* rstd,
+                     int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                     cudaStream_t s) {
+    note_launch();
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, rstd, batch_stats, perm_c0,
+                                                          dgamma, dbeta, k1, k2, k3);
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ d, const T* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ k1,
+                                    const float* __restrict__ k2, const float* __restrict__ k3, T* __restrict__ dy,
+                                    long n8, int C) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>((i * 8) % C);
+        float dv[8], yv[8];
+        load8(d + i * 8, dv);
+        load8(y + i * 8, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float xhat = (yv[j] - mean[c]) * rstd[c];
+            dv[j] = k1[c] * (dv[j] - k2[c] - xhat * k3[c]);
+        }
+        store8(dy + i * 8, dv);
+    }
+}
+template <typename T>
+void bn_bwd_apply(const T* d, const T* y, const float* mean, const float* rstd, const float* k1, const float* k2,
+                  const float* k3, T* dy, long rows, int C, cudaStream_t s) {
+    const long n8 = rows * C / 8;
+    note_launch();
+    bn_bwd_apply_kernel<T><<<blocks_for(n8, 256), 256, 0, s>>>(d, y, mean, rstd, k1, k2, k3, dy, n8, C);
+}
+template void bn_bwd_apply<float>(const float*, const float*, const float*, const float*, const float*, const float*,
+                                  const float*, float*, long, int, cudaStream_t);
+template void bn_bwd_apply<bf16>(const bf16*, const bf16*, const float*, const float*, const float*, const float*,
+                                 const float*, bf16*, long, int, cudaStream_t);
+
+__global__ void col_finalize_kernel(const float* __restrict__ partial, int chunks, int C, int perm_c0,
+                                    float* __restrict__ out0, float* __restrict__ out1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= C) return;
+    const int p = perm_index(j, perm_c0);
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        s0 += partial[static_cast<long>(k) * 2 * C + j];
+        if (out1) s1 += partial[static_cast<long>(k) * 2 * C + C + j];
+    }
+    if (out0) out0[p] = static_cast<float>(s0);
+    if (out1) out1[p] = static_cast<float>(s1);
+}
+void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* out0, float* out1, cudaStream_t s) {
+    note_launch();
+    col_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, C, perm_c0, out0, out1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generator tail: Conv3x3 (C -> 1) + tanh, and its backward
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_conv_tanh_kernel(const T* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ out, uint8_t* __restrict__ out_u8, int B, int S, int C) {
+    extern __shared__ float wsm[];  // [C*9]
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    const long total = static_cast<long>(B) * S * S;
+    const float b0 = bias[0];
+    for (long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; pix < total;
+         pix += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(pix % S);
+        const int yy = static_cast<int>((pix / S) % S);
+        const long n = pix / (static_cast<long>(S) * S);
+        float acc = b0;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = yy + ky - 1;
+            if (iy < 0 || iy >= S) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = x + kx - 1;
+                if (ix < 0 || ix >= S) continue;
+                const T* p = a + ((n * S + iy) * S + ix) * C;
+                const int tap = ky * 3 + kx;
+                for (int c8 = 0; c8 < C; c8 += 8) {
+                    float v[8];
+                    load8(p + c8, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wsm[(c8 + j) * 9 + tap], acc);
+                }
+            }
+        }
+        const float t = tanhf(acc);
+        out[pix] = t;
+        if (out_u8) {
+            float q = (t + 1.f) * 127.5f;
+            q = fminf(fmaxf(q, 0.f), 255.f);
+            out_u8[pix] = static_cast<uint8_t>(q);  // numpy astype(uint8) truncates (utils/inference.py:129)
+        }
+    }
+}
+template <typename T>
+void final_conv_tanh(const T* a, const float* w, const float* bias, float* out, uint8_t* out_u8, int B, int S, int C,
+                     cudaStream_t s) {
+    const long total = static_cast<long>(B) * S * S;
+    note_launch();
+    final_conv_tanh_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, C * 9 * sizeof(float), s>>>(a, w, bias, out,
+                                                                                                  out_u8, B, S, C);
+}
+template void final_conv_tanh<float>(const float*, const float*, const float*, float*, uint8_t*, int, int, int,
+                                     cudaStream_t);
+template void final_conv_tanh<bf16>(const bf16*, const float*, const float*, float*, uint8_t*, int, int, int,
+                                    cudaStream_t);
+
+__global__ void tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                float* __restrict__ dpre, long n) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float o = out[i];
+        dpre[i] = dout[i] * (1.f - o * o);
+    }
+}
+
+// dbn[n,y,x,c] = [a>0] * sum_{ky,kx} dpre[n, y+1-ky, x+1-kx] * w[c][ky][kx]
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, const T* __restrict__ a,
+                   T* __restrict__ dbn, int B, int S, int C) {
+    extern __shared__ float wsm[];  // [9][C]
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) wsm[(i % 9) * C + i / 9] = w[i];
+    __syncthreads();
+    const int g = C / 8;
+    const long total = static_cast<long>(B) * S * S * g;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % g) * 8;
+        const long pix = i / g;
+        const int x = static_cast<int>(pix % S);
+        const int yy = static_cast<int>((pix / S) % S);
+        const long n = pix / (static_cast<long>(S) * S);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int sy = yy + 1 - ky;
+            if (sy < 0 || sy >= S) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int sx = x + 1 - kx;
+                if (sx < 0 || sx >= S) continue;
+                const float d = dpre[(n * S + sy) * S + sx];
+                const float* ww = wsm + (ky * 3 + kx) * C + c0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, ww[j], acc[j]);
+            }
+        }
+        float av[8];
+        load8(a + pix * C + c0, av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = av[j] > 0.f ? acc[j] : 0.f;
+        store8(dbn + pix * C + c0, acc);
+    }
+}
+
+// partial[chunk][C*9 + 1]: thread (tap, c) accumulates sum dpre[pix] * a[pix + tap offset][c]; slot C*9 = sum dpre
+template <typename T>
+__global__ void final_wgrad_kernel(const float* __restrict__ dpre, const T* __restrict__ a, float* __restrict__ partial,
+                                   int B, int S, int C, long pix_per_chunk) {
+    const int c = threadIdx.x % C;
+    const int tap = threadIdx.x / C;  // blockDim = 9*C
+    const int ky = tap / 3, kx = tap % 3;
+    const long total = static_cast<long>(B) * S * S;
+    const long p0 = blockIdx.x * pix_per_chunk;
+    long p1 = p0 + pix_per_chunk;
+    if (p1 > total) p1 = total;
+    float acc = 0.f, dsum = 0.f;
+    for (long pix = p0; pix < p1; ++pix) {
+        const float d = dpre[pix];
+        const int x = static_cast<int>(pix % S);
+        const int yy = static_cast<int>((pix / S) % S);
+        const int iy = yy + ky - 1, ix = x + kx - 1;
+        dsum += d;
+        if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+            const long q = pix + static_cast<long>(ky - 1) * S + (kx - 1);
+            acc = fmaf(d, to_f(a[q * C + c]), acc);
+        }
+    }
+    float* out = partial + static_cast<long>(blockIdx.x) * (C * 9 + 1);
+    out[c * 9 + tap] = acc;
+    if (threadIdx.x == 0) out[C * 9] = dsum;
+}
+__global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunks, int n, float* __restrict__ out_a,
+                                    int na, float* __restrict__ out_b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < chunks; ++k) s += partial[static_cast<long>(k) * n + j];
+    if (j < na)
+        out_a[j] = static_cast<float>(s);
+    else if (out_b)
+        out_b[j - na] = static_cast<float>(s);
+}
+
+template <typename T>
+void final_conv_bwd(const float* dout, const float* out, const T* a, const float* w, float* dpre, T* dbn, float* dW,
+                    float* dbias, float* partial, int B, int S, int C, cudaStream_t s) {
+    const long total = static_cast<long>(B) * S * S;
+    note_launch();
+    tanh_bwd_kernel<<<blocks_for(total, 256), 256, 0, s>>>(dout, out, dpre, total);
+    note_launch();
+    final_dgrad_kernel<T><<<blocks_for(total * (C / 8), 256, 148 * 32), 256, C * 9 * sizeof(float), s>>>(dpre, w, a, dbn,
+                                                                                                        B, S, C);
+    long chunks = (total + 1023) / 1024;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    const long ppc = (total + chunks - 1) / chunks;
+    chunks = (total + ppc - 1) / ppc;
+    note_launch();
+    final_wgrad_kernel<T><<<static_cast<unsigned>(chunks), 9 * C, 0, s>>>(dpre, a, partial, B, S, C, ppc);
+    const int n = C * 9 + 1;
+    note_launch();
+    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, static_cast<int>(chunks), n, dW, C * 9, dbias);
+}
+template void final_conv_bwd<float>(const float*, const float*, const float*, const float*, float*, float*, float*,
+                                    float*, float*, int, int, int, cudaStream_t);
+template void final_conv_bwd<bf16>(const float*, const float*, const bf16*, const float*, float*, bf16*, float*, float*,
+                                   float*, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// Discriminator head: Conv 4x4 s2 p1 from the 1-channel image, forward / wgrad / dgrad
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+d_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               const float* __restrict__ mask, float slope, T* __restrict__ a, int B, int S, int C) {
+    extern __shared__ float wsm[];  // [16][C] then bias[C]
+    for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i % 16) * C + i / 16] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[16 * C + i] = bias[i];
+    __syncthreads();
+    const int O = S / 2, g = C / 8;
+    const long total = static_cast<long>(B) * O * O * g;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % g) * 8;
+        const long pix = i / g;
+        const int ox = static_cast<int>(pix % O);
+        const int oy = static_cast<int>((pix / O) % O);
+        const long n = pix / (static_cast<long>(O) * O);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = wsm[16 * C + c0 + j];
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= S) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= S) continue;
+                const float xv = __ldg(x + (n * S + iy) * S + ix);
+                const float* ww = wsm + (ky * 4 + kx) * C + c0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ww[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+            if (mask) v *= mask[n * C + c0 + j];
+            acc[j] = v;
+        }
+        store8(a + pix * C + c0, acc);
+    }
+}
+template <typename T>
+void d_conv0(const float* x, const float* w, const float* bias, const float* mask, float slope, T* a, int B, int S,
+             int C, cudaStream_t s) {
+    const long total = static_cast<long>(B) * (S / 2) * (S / 2) * (C / 8);
+    note_launch();
+    d_conv0_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, 17 * C * sizeof(float), s>>>(x, w, bias, mask, slope, a,
+                                                                                           B, S, C);
+}
+template void d_conv0<float>(const float*, const float*, const float*, const float*, float, float*, int, int, int,
+                             cudaStream_t);
+template void d_conv0<bf16>(const float*, const float*, const float*, const float*, float, bf16*, int, int, int,
+                            cudaStream_t);
+
+// partial[chunk][C*16 + C]: dW[c][ky][kx] and dbias[c]. blockDim = 4*C: thread (ky = t / C, c = t % C) keeps 4 kx taps.
+template <typename T>
+__global__ void d_conv0_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ partial,
+                                     int B, int S, int C, long pix_per_chunk) {
+    const int c = threadIdx.x % C;
+    const int ky = threadIdx.x / C;
+    const int O = S / 2;
+    const long total = static_cast<long>(B) * O * O;
+    const long p0 = blockIdx.x * pix_per_chunk;
+    long p1 = p0 + pix_per_chunk;
+    if (p1 > total) p1 = total;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+    for (long pix = p0; pix < p1; ++pix) {
+        const int ox = static_cast<int>(pix % O);
+        const int oy = static_cast<int>((pix / O) % O);
+        const long n = pix / (static_cast<long>(O) * O);
+        const float d = to_f(dy[pix * C + c]);
+        bsum += d;
+        const int iy = 2 * oy - 1 + ky;
+        if (iy < 0 || iy >= S) continue;
+        const float* row = x + (n * S + iy) * S;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+            const int ix = 2 * ox - 1 + kx;
+            if (ix >= 0 && ix < S) acc[kx] = fmaf(d, __ldg(row + ix), acc[kx]);
+        }
+    }
+    float* out = partial + static_cast<long>(blockIdx.x) * (C * 17);
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) out[c * 16 + ky * 4 + kx] = acc[kx];
+    if (ky == 0) out[C * 16 + c] = bsum;
+}
+template <typename T>
+void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s) {
+    const long total = static_cast<long>(B) * (S / 2) * (S / 2);
+    long chunks = (total + 255) / 256;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    const long ppc = (total + chunks - 1) / chunks;
+    chunks = (total + ppc - 1) / ppc;
+    note_launch();
+    d_conv0_wgrad_kernel<T><<<static_cast<unsigned>(chunks), 4 * C, 0, s>>>(x, dy, partial, B, S, C, ppc);
+    const int n = C * 17;
+    // dW (C*16 floats) is immediately followed by dbias (C floats) in the flat gradient buffer
+    note_launch();
+    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, static_cast<int>(chunks), n, dW, n, nullptr);
+}
+template void d_conv0_wgrad<float>(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+template void d_conv0_wgrad<bf16>(const float*, const bf16*, float*, float*, int, int, int, cudaStream_t);
+
+// dx[n,iy,ix] = sum over (oy,ky): 2oy-1+ky = iy, same for x, and channels: dy[n,oy,ox,c] * w[c][ky][kx]
+template <typename T>
+__global__ void __launch_bounds__(256)
+d_conv0_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S,
+                     int C) {
+    extern __shared__ float wsm[];  // [16][C]
+    for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i % 16) * C + i / 16] = w[i];
+    __syncthreads();
+    const int O = S / 2;
+    const long total = static_cast<long>(B) * S * S;
+    for (long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; pix < total;
+         pix += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int ix = static_cast<int>(pix % S);
+        const int iy = static_cast<int>((pix / S) % S);
+        const long n = pix / (static_cast<long>(S) * S);
+        float acc = 0.f;
+        for (int ty = 0; ty < 2; ++ty) {
+            const int ky = ((iy + 1) & 1) + 2 * ty;
+            const int oy = (iy + 1 - ky) >> 1;
+            if (oy < 0 || oy >= O || (iy + 1 - ky) < 0) continue;
+            for (int tx = 0; tx < 2; ++tx) {
+                const int kx = ((ix + 1) & 1) + 2 * tx;
+                const int ox = (ix + 1 - kx) >> 1;
+                if (ox < 0 || ox >= O || (ix + 1 - kx) < 0) continue;
+                const T* p = dy + ((n * O + oy) * O + ox) * C;
+                const float* ww = wsm + (ky * 4 + kx) * C;
+                for (int c8 = 0; c8 < C; c8 += 8) {
+                    float v[8];
+                    load8(p + c8, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], ww[c8 + j], acc);
+                }
+            }
+        }
+        dx[pix] = acc;
+    }
+}
+template <typename T>
+void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s) {
+    const long total = static_cast<long>(B) * S * S;
+    note_launch();
+    d_conv0_dgrad_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, 16 * C * sizeof(float), s>>>(dy, w, dx, B, S, C);
+}
+template void d_conv0_dgrad<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
+template void d_conv0_dgrad<bf16>(const bf16*, const float*, float*, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// classifier + sigmoid, and backward pieces
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void classifier_sigmoid_kernel(const T* __restrict__ a, const float* __restrict__ wp,
+                                          const float* __restrict__ bias, float* __restrict__ prob, int B, int F) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const T* row = a + static_cast<long>(warp) * F;
+    float acc = 0.f;
+    for (int j = lane * 8; j < F; j += 256) {
+        float v[8], w[8];
+        load8(row + j, v);
+        load8(wp + j, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(v[k], w[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float logit = acc + bias[0];
+        prob[warp] = 1.f / (1.f + expf(-logit));
+    }
+}
+template <typename T>
+void classifier_sigmoid(const T* a, const float* wp, const float* bias, float* prob, int B, int F, cudaStream_t s) {
+    note_launch();
+    classifier_sigmoid_kernel<T><<<(B * 32 + 255) / 256, 256, 0, s>>>(a, wp, bias, prob, B, F);
+}
+template void classifier_sigmoid<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
+template void classifier_sigmoid<bf16>(const bf16*, const float*, const float*, float*, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void features_nchw_kernel(const T* __restrict__ a, float* __restrict__ feat, int B, int C) {
+    const int F = C * 16;
+    const long total = static_cast<long>(B) * F;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(i % F);
+        const long b = i / F;
+        const int c = f / 16, hw = f % 16;
+        feat[i] = to_f(a[b * F + hw * C + c]);
+    }
+}
+template <typename T>
+void features_nchw(const T* a, float* feat, int B, int C, cudaStream_t s) {
+    note_launch();
+    features_nchw_kernel<T><<<blocks_for(static_cast<long>(B) * C * 16, 256), 256, 0, s>>>(a, feat, B, C);
+}
+template void features_nchw<float>(const float*, float*, int, int, cudaStream_t);
+template void features_nchw<bf16>(const bf16*, float*, int, int, cudaStream_t);
+
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob,
+                                   float* __restrict__ dlogit, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        const float p = prob[i];
+        dlogit[i] = dprob[i] * p * (1.f - p);
+    }
+}
+void sigmoid_bwd(const float* prob, const float* dprob, float* dlogit, int B, cudaStream_t s) {
+    note_launch();
+    sigmoid_bwd_kernel<<<(B + 255) / 256, 256, 0, s>>>(prob, dprob, dlogit, B);
+}
+
+template <typename T>
+__global__ void classifier_bwd_dy_kernel(const float* __restrict__ dlogit, const float* __restrict__ wp,
+                                         const float* __restrict__ mask, const T* __restrict__ a, float slope,
+                                         T* __restrict__ dy, int B, int C) {
+    const int F = C * 16;
+    const long n8 = static_cast<long>(B) * F / 8;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int j0 = static_cast<int>((i * 8) % F);
+        const long b = (i * 8) / F;
+        const int c0 = j0 % C;
+        const float dl = dlogit[b];
+        float av[8], w[8];
+        load8(a + i * 8, av);
+        load8(wp + j0, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = dl * w[k] * (av[k] > 0.f ? 1.f : slope);
+            if (mask) v *= mask[b * C + c0 + k];
+            av[k] = v;
+        }
+        store8(dy + i * 8, av);
+    }
+}
+template <typename T>
+void classifier_bwd_dy(const float* dlogit, const float* wp, const float* mask, const T* a, float slope, T* dy, int B,
+                       int C, cudaStream_t s) {
+    const long n8 = static_cast<long>(B) * C * 16 / 8;
+    note_launch();
+    classifier_bwd_dy_kernel<T><<<blocks_for(n8, 256), 256, 0, s>>>(dlogit, wp, mask, a, slope, dy, B, C);
+}
+template void classifier_bwd_dy<float>(const float*, const float*, const float*, const float*, float, float*, int, int,
+                                       cudaStream_t);
+template void classifier_bwd_dy<bf16>(const float*, const float*, const float*, const bf16*, float, bf16*, int, int,
+                                      cudaStream_t);
+
+// single-block deterministic reductions -----------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_sum(float (&v)[N], float* sm /*[32*N]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sm[warp * N + k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            float t = lane < nw ? sm[lane * N + k] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            v[k] = t;
+        }
+    }
+}
+
+__global__ void sum_vector_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+    __shared__ float sm[32];
+    float acc[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] += v[i];
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) out[0] = acc[0];
+}
+void sum_vector(const float* v, int n, float* out, cudaStream_t s) { sum_vector_kernel<<<1, 1024, 0, s>>>(v, n, out); }
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void dropout_masks_kernel(uint64_t seed, uint64_t offset, long n, float p, float* __restrict__ out) {
+    const float keep = 1.f / (1.f - p);
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const uint64_t h = splitmix64(splitmix64(seed) ^ (offset + static_cast<uint64_t>(i)));
+        const float u = static_cast<float>(h >> 40) * (1.0f / 16777216.0f);
+        out[i] = u >= p ? keep : 0.f;
+    }
+}
+void dropout_masks(uint64_t seed, uint64_t offset, long n, float p, float* out, cudaStream_t s) {
+    note_launch();
+    dropout_masks_kernel<<<blocks_for(n, 256), 256, 0, s>>>(seed, offset, n, p, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BCE on probabilities
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bce_term(float p, float y) {
+    const float lp = fmaxf(logf(p), -100.f);
+    const float l1p = fmaxf(logf(1.f - p), -100.f);
+    return -(y * lp + (1.f - y) * l1p);
+}
+__device__ __forceinline__ float bce_dp(float p, float y, float inv_n) {
+    return (p - y) / fmaxf(p * (1.f - p), 1e-12f) * inv_n;
+}
+
+__global__ void bce_forward_kernel(const float* __restrict__ prob, const float* __restrict__ target, int n,
+                                   float* __restrict__ loss) {
+    __shared__ float sm[32];
+    float acc[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] += bce_term(prob[i], target[i]);
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) loss[0] = acc[0] / n;
+}
+void bce_forward(const float* prob, const float* target, int n, float* loss, cudaStream_t s) {
+    note_launch();
+    bce_forward_kernel<<<1, 1024, 0, s>>>(prob, target, n, loss);
+}
+__global__ void bce_backward_kernel(const float* __restrict__ prob, const float* __restrict__ target, int n,
+                                    const float* __restrict__ grad_loss, float* __restrict__ dprob) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dprob[i] = grad_loss[0] * bce_dp(prob[i], target[i], 1.f / n);
+}
+void bce_backward(const float* prob, const float* target, int n, const float* grad_loss, float* dprob,
+                  cudaStream_t s) {
+    note_launch();
+    bce_backward_kernel<<<(n + 255) / 256, 256, 0, s>>>(prob, target, n, grad_loss, dprob);
+}
+
+__global__ void d_loss_metrics_kernel(const float* __restrict__ prob, int B, float smoothing,
+                                      float* __restrict__ metrics, float* __restrict__ dlogit) {
+    __shared__ float sm[32 * 6];
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // loss_r, loss_f, acc_r, acc_f, mean_r, mean_f
+    const float inv = 1.f / B;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float pr = prob[i], pf = prob[B + i];
+        acc[0] += bce_term(pr, smoothing);
+        acc[1] += bce_term(pf, 0.f);
+        acc[2] += pr > 0.5f ? 1.f : 0.f;
+        acc[3] += pf < 0.5f ? 1.f : 0.f;
+        acc[4] += pr;
+        acc[5] += pf;
+        dlogit[i] = bce_dp(pr, smoothing, inv) * pr * (1.f - pr);
+        dlogit[B + i] = bce_dp(pf, 0.f, inv) * pf * (1.f - pf);
+    }
+    block_sum<6>(acc, sm);
+    if (threadIdx.x == 0) {
+        const float lr = acc[0] * inv, lf = acc[1] * inv;
+        metrics[0] = lr + lf;
+        metrics[1] = lr;
+        metrics[2] = lf;
+        metrics[3] = acc[2] * inv;
+        metrics[4] = acc[3] * inv;
+        metrics[5] = acc[4] * inv;
+        metrics[6] = acc[5] * inv;
+    }
+}
+void d_loss_metrics(const float* prob, int B, float smoothing, float* metrics, float* dlogit, cudaStream_t s) {
+    note_launch();
+    d_loss_metrics_kernel<<<1, 1024, 0, s>>>(prob, B, smoothing, metrics, dlogit);
+}
+__global__ void g_loss_metrics_kernel(const float* __restrict__ prob, int B, float* __restrict__ metrics,
+                                      float* __restrict__ dlogit) {
+    __shared__ float sm[32 * 2];
+    float acc[2] = {0.f, 0.f};
+    const float inv = 1.f / B;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float p = prob[i];
+        acc[0] += bce_term(p, 1.f);
+        acc[1] += p;
+        dlogit[i] = bce_dp(p, 1.f, inv) * p * (1.f - p);
+    }
+    block_sum<2>(acc, sm);
+    if (threadIdx.x == 0) {
+        metrics[7] = acc[0] * inv;
+        metrics[8] = acc[1] * inv;
+    }
+}
+void g_loss_metrics(const float* prob, int B, float* metrics, float* dlogit, cudaStream_t s) {
+    note_launch();
+    g_loss_metrics_kernel<<<1, 1024, 0, s>>>(prob, B, metrics, dlogit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam over a flat buffer (torch.optim.Adam single-tensor formulas, vanilla…:110-120)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, float b1, float b2, float eps, float step_size,
+                            float inv_bc2_sqrt) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp form used by torch
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+void adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, long step,
+               cudaStream_t s) {
+    const double bc1 = 1.0 - std::pow(static_cast<double>(b1), static_cast<double>(step));
+    const double bc2 = 1.0 - std::pow(static_cast<double>(b2), static_cast<double>(step));
+    note_launch();
+    adam_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, b1, b2, eps, static_cast<float>(lr / bc1),
+                                                   static_cast<float>(1.0 / std::sqrt(bc2)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct convolutions (validation mode)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float epi_apply(float v, int n, long img, long oidx, const Epi& e) {
+    if (e.bias) v += e.bias[n];
+    if (e.scale) v = fmaf(v, e.scale[n], e.shift[n]);
+    if (e.act == 1)
+        v = fmaxf(v, 0.f);
+    else if (e.act == 2)
+        v = v > 0.f ? v : v * e.slope;
+    if (e.mask) v *= e.mask[img * e.ldmask + n];
+    if (e.gate) v *= to_f(static_cast<const T*>(e.gate)[oidx]) > 0.f ? 1.f : e.slope;
+    return v;
+}
+
+template <typename T>
+__global__ void conv_s2_direct_kernel(const T* __restrict__ in, const float* __restrict__ w, long so, long si, Epi e,
+                                      T* __restrict__ out, int B, int inH, int inW, int Cin, int Cout) {
+    const int OH = inH / 2, OW = inW / 2;
+    const long total = static_cast<long>(B) * OH * OW * Cout;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const long pix = i / Cout;
+        const int ox = static_cast<int>(pix % OW);
+        const int oy = static_cast<int>((pix / OW) % OH);
+        const long n = pix / (static_cast<long>(OW) * OH);
+        float acc = 0.f;
+        for (int ky = 0; ky < 4; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= inH) continue;
+            for (int kx = 0; kx < 4; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= inW) continue;
+                const T* p = in + ((n * inH + iy) * inW + ix) * Cin;
+                const float* ww = w + co * so + ky * 4 + kx;
+                for (int ci = 0; ci < Cin; ++ci) acc = fmaf(to_f(p[ci]), ww[ci * si], acc);
+            }
+        }
+        out[i] = from_f<T>(epi_apply<T>(acc, co, n, i, e));
+    }
+}
+template <typename T>
+void conv_s2_direct(const T* in, const float* w, long so, long si, const Epi& e, T* out, int B, int inH, int inW,
+                    int Cin, int Cout, cudaStream_t s) {
+    const long total = static_cast<long>(B) * (inH / 2) * (inW / 2) * Cout;
+    note_launch();
+    conv_s2_direct_kernel<T><<<blocks_for(total, 256, 148 * 64), 256, 0, s>>>(in, w, so, si, e, out, B, inH, inW, Cin,
+                                                                             Cout);
+}
+template void conv_s2_direct<float>(const float*, const float*, long, long, const Epi&, float*, int, int, int, int, int,
+                                    cudaStream_t);
+template void conv_s2_direct<bf16>(const bf16*, const float*, long, long, const Epi&, bf16*, int, int, int, int, int,
+                                   cudaStream_t);
+
+template <typename T>
+__global__ void convT_direct_kernel(const T* __restrict__ in, const float* __restrict__ w, long so, long si, Epi e,
+                                    T* __restrict__ out, int B, int inH, int inW, int Cin, int Cout) {
+    const int OH = inH * 2, OW = inW * 2;
+    const long total = static_cast<long>(B) * OH * OW * Cout;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const long pix = i / Cout;
+        const int ox = static_cast<int>(pix % OW);
+        const int oy = static_cast<int>((pix / OW) % OH);
+        const long n = pix / (static_cast<long>(OW) * OH);
+        float acc = 0.f;
+        for (int ty = 0; ty < 2; ++ty) {
+            const int ky = ((oy + 1) & 1) + 2 * ty;
+            const int t = oy + 1 - ky;
+            if (t < 0 || (t >> 1) >= inH) continue;
+            const int iy = t >> 1;
+            for (int tx = 0; tx < 2; ++tx) {
+                const int kx = ((ox + 1) & 1) + 2 * tx;
+                const int u = ox + 1 - kx;
+                if (u < 0 || (u >> 1) >= inW) continue;
+                const int ix = u >> 1;
+                const T* p = in + ((n * inH + iy) * inW + ix) * Cin;
+                const float* ww = w + co * so + ky * 4 + kx;
+                for (int ci = 0; ci < Cin; ++ci) acc = fmaf(to_f(p[ci]), ww[ci * si], acc);
+            }
+        }
+        out[i] = from_f<T>(epi_apply<T>(acc, co, n, i, e));
+    }
+}
+template <typename T>
+void convT_direct(const T* in, const float* w, long so, long si, const Epi& e, T* out, int B, int inH, int inW, int Cin,
+                  int Cout, cudaStream_t s) {
+    const long total = static_cast<long>(B) * inH * 2 * inW * 2 * Cout;
+    note_launch();
+    convT_direct_kernel<T><<<blocks_for(total, 256, 148 * 64), 256, 0, s>>>(in, w, so, si, e, out, B, inH, inW, Cin,
+                                                                           Cout);
+}
+template void convT_direct<float>(const float*, const float*, long, long, const Epi&, float*, int, int, int, int, int,
+                                  cudaStream_t);
+template void convT_direct<bf16>(const bf16*, const float*, long, long, const Epi&, bf16*, int, int, int, int, int,
+                                 cudaStream_t);
+
+// one warp per (m, n, tap): lanes stride over pixels, shuffle-reduce (fixed order => deterministic)
+template <typename T>
+__global__ void wgrad_direct_kernel(const T* __restrict__ coarse, const T* __restrict__ fine, float* __restrict__ dW,
+                                    int B, int cH, int cW, int Mc, int Nf) {
+    const long warp = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long total = static_cast<long>(Mc) * Nf * 16;
+    if (warp >= total) return;
+    const int tap = static_cast<int>(warp & 15);
+    const int n = static_cast<int>((warp >> 4) % Nf);
+    const int m = static_cast<int>((warp >> 4) / Nf);
+    const int ky = tap >> 2, kx = tap & 3;
+    const int fH = 2 * cH, fW = 2 * cW;
+    const long pixels = static_cast<long>(B) * cH * cW;
+    float acc = 0.f;
+    for (long pix = lane; pix < pixels; pix += 32) {
+        const int x = static_cast<int>(pix % cW);
+        const int y = static_cast<int>((pix / cW) % cH);
+        const long b = pix / (static_cast<long>(cW) * cH);
+        const int fy = 2 * y - 1 + ky, fx = 2 * x - 1 + kx;
+        if (fy < 0 || fy >= fH || fx < 0 || fx >= fW) continue;
+        acc = fmaf(to_f(coarse[pix * Mc + m]), to_f(fine[((b * fH + fy) * fW + fx) * Nf + n]), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dW[warp] = acc;
+}
+template <typename T>
+void wgrad_direct(const T* coarse, const T* fine, float* dW, int B, int cH, int cW, int Mc, int Nf, cudaStream_t s) {
+    const long total = static_cast<long>(Mc) * Nf * 16;
+    note_launch();
+    wgrad_direct_kernel<T><<<static_cast<unsigned>((total * 32 + 255) / 256), 256, 0, s>>>(coarse, fine, dW, B, cH, cW,
+                                                                                           Mc, Nf);
+}
+template void wgrad_direct<float>(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template void wgrad_direct<bf16>(const bf16*, const bf16*, float*, int, int, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void fc_direct_kernel(const T* __restrict__ zp, int Kp, const float* __restrict__ W,
+                                 const float* __restrict__ bias, T* __restrict__ y, int B, int C0, int latent) {
+    const int F = C0 * 16;
+    const long total = static_cast<long>(B) * F;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(i % F);
+        const long b = i / F;
+        const int f = (j % C0) * 16 + j / C0;
+        float acc = 0.f;
+        for (int k = 0; k < latent; ++k) acc = fmaf(to_f(zp[b * Kp + k]), W[static_cast<long>(f) * latent + k], acc);
+        y[i] = from_f<T>(acc + bias[f]);
+    }
+}
+template <typename T>
+void fc_direct(const T* zp, int Kp, const float* W, const float* bias, T* y, int B, int C0, int latent,
+               cudaStream_t s) {
+    note_launch();
+    fc_direct_kernel<T><<<blocks_for(static_cast<long>(B) * C0 * 16, 256, 148 * 64), 256, 0, s>>>(zp, Kp, W, bias, y, B,
+                                                                                                 C0, latent);
+}
+template void fc_direct<float>(const float*, int, const float*, const float*, float*, int, int, int, cudaStream_t);
+template void fc_direct<bf16>(const bf16*, int, const float*, const float*, bf16*, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void fc_wgrad_direct_kernel(const T* __restrict__ dy, const T* __restrict__ zp, int Kp,
+                                       float* __restrict__ dW, int B, int C0, int latent) {
+    const int F = C0 * 16;
+    const long total = static_cast<long>(F) * latent;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(i % F);  // consecutive threads -> consecutive columns of dy (coalesced)
+        const int k = static_cast<int>(i / F);
+        const int f = (j % C0) * 16 + j / C0;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc = fmaf(to_f(dy[static_cast<long>(b) * F + j]), to_f(zp[static_cast<long>(b) * Kp + k]), acc);
+        dW[static_cast<long>(f) * latent + k] = acc;
+    }
+}
+template <typename T>
+void fc_wgrad_direct(const T* dy, const T* zp, int Kp, float* dW, int B, int C0, int latent, cudaStream_t s) {
+    note_launch();
+    fc_wgrad_direct_kernel<T><<<blocks_for(static_cast<long>(C0) * 16 * latent, 256, 148 * 64), 256, 0, s>>>(
+        dy, zp, Kp, dW, B, C0, latent);
+}
+template void fc_wgrad_direct<float>(const float*, const float*, int, float*, int, int, int, cudaStream_t);
+template void fc_wgrad_direct<bf16>(const bf16*, const bf16*, int, float*, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void fc_dz_direct_kernel(const T* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dz,
+                                    int B, int C0, int latent) {
+    const int F = C0 * 16;
+    const long total = static_cast<long>(B) * latent;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % latent);
+        const long b = i / latent;
+        float acc = 0.f;
+        for (int j = 0; j < F; ++j) {
+            const int f = (j % C0) * 16 + j / C0;
+            acc = fmaf(to_f(dy[b * F + j]), W[static_cast<long>(f) * latent + k], acc);
+        }
+        dz[i] = acc;
+    }
+}
+template <typename T>
+void fc_dz_direct(const T* dy, const float* W, float* dz, int B, int C0, int latent, cudaStream_t s) {
+    note_launch();
+    fc_dz_direct_kernel<T><<<blocks_for(static_cast<long>(B) * latent, 256), 256, 0, s>>>(dy, W, dz, B, C0, latent);
+}
+template void fc_dz_direct<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
+template void fc_dz_direct<bf16>(const bf16*, const float*, float*, int, int, int, cudaStream_t);
+
+}  // namespace sg

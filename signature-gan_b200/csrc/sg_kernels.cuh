@@ -1,0 +1,136 @@
+// sg_kernels.cuh — launchers of the CUDA-core kernels: everything on the path that is not a fat
+// implicit GEMM (BatchNorm statistics/apply/backward, the 1-channel convolutions at either end of the
+// networks, classifier + sigmoid + BCE, dropout masks, weight packing, Adam) plus the direct fp32
+// convolutions used by the validation mode. Activations are NHWC, element type T in {float, bf16}.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sg {
+
+using bf16 = __nv_bfloat16;
+
+// Fused epilogue shared by the direct convolutions (mirrors the tcgen05 epilogue in sg_conv_umma.cu).
+struct Epi {
+    const float* bias = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    int act = 0;  // 0 none, 1 relu, 2 leaky(slope)
+    float slope = 0.f;
+    const float* mask = nullptr;  // [nimg][ldmask]
+    int ldmask = 0;
+    const void* gate = nullptr;  // T activation at the output position: v *= (g > 0 ? 1 : slope)
+};
+
+// Every launcher bumps this (host-side) counter once per kernel it enqueues; bench.py reports it as gpu_launches.
+extern unsigned long long g_launches;
+inline void note_launch(int n = 1) { g_launches += static_cast<unsigned long long>(n); }
+
+constexpr int kMaxChunks = 592;  // 148 SMs x 4: upper bound on partial-sum rows of the column reductions
+
+// ---- packing ---------------------------------------------------------------------------------
+// src fp32 [A][B][16] -> dstAB bf16 [A][16][B], dstBA bf16 [B][16][A] (either may be null)
+void pack_w16(const float* src, bf16* dstAB, bf16* dstBA, int A, int B, cudaStream_t s);
+// Generator fc: rows permuted from NCHW feature f = c*16+hw to NHWC j = hw*C0+c, K padded to Kp.
+void pack_fc(const float* W, const float* bias, bf16* Wp, float* biasp, int C0, int latent, int Kp, cudaStream_t s);
+// Classifier weight (1, C*16) NCHW order -> NHWC order fp32
+void pack_classifier(const float* w, float* wp, int C, cudaStream_t s);
+
+// ---- generator side --------------------------------------------------------------------------
+template <typename T>
+void cast_pad_z(const float* z, T* zp, int B, int latent, int Kp, cudaStream_t s);
+
+// Column reductions over a [rows][C] matrix, two-stage and deterministic.
+//   mode 0: p0 = sum y,            p1 = sum y^2
+//   mode 1: p0 = sum d,            p1 = sum d * (y - mean[c]) * rstd[c]       (d = first operand)
+//   mode 2: p0 = sum y * rs[row],  p1 unused                                   (rs = per-row scale)
+// partial must hold chunks*2*C floats; returns the number of chunks used.
+template <typename T>
+int col_reduce(int mode, const T* a, const T* y, const float* mean, const float* rstd, const float* rowscale,
+               long rows, int C, float* partial, cudaStream_t s);
+
+// BatchNorm forward bookkeeping. perm_c0 > 0: parameter index of column j is (j % perm_c0)*16 + j / perm_c0.
+void bn_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
+                 float* mean, float* rstd, float* scale, float* shift, cudaStream_t s);
+template <typename T>
+void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, cudaStream_t s);
+// BatchNorm backward bookkeeping: dgamma/dbeta (parameter order) and the per-channel coefficients.
+void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* rstd,
+                     int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                     cudaStream_t s);
+template <typename T>
+void bn_bwd_apply(const T* d, const T* y, const float* mean, const float* rstd, const float* k1, const float* k2,
+                  const float* k3, T* dy, long rows, int C, cudaStream_t s);
+// Generic: out0[pidx] = sum_chunks p0, out1[pidx] = sum_chunks p1 (null = skip); accumulate adds into out.
+void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* out0, float* out1, cudaStream_t s);
+
+// Conv3x3(C->1) + bias + tanh (gen…:153-163). out fp32 (B,1,S,S); out_u8 optional.
+template <typename T>
+void final_conv_tanh(const T* a, const float* w, const float* bias, float* out, uint8_t* out_u8, int B, int S, int C,
+                     cudaStream_t s);
+// Backward of the above: dpre = dout*(1-out^2) (scratch fp32), dbn = relu'(a) * convT3x3(dpre), dW, dbias.
+template <typename T>
+void final_conv_bwd(const float* dout, const float* out, const T* a, const float* w, float* dpre, T* dbn, float* dW,
+                    float* dbias, float* partial, int B, int S, int C, cudaStream_t s);
+
+// ---- discriminator side ----------------------------------------------------------------------
+// Conv 4x4 s2 p1, 1 -> C channels (disc…:134-139) with bias + LeakyReLU + dropout mask.
+template <typename T>
+void d_conv0(const float* x, const float* w, const float* bias, const float* mask, float slope, T* a, int B, int S,
+             int C, cudaStream_t s);
+template <typename T>
+void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s);
+template <typename T>
+void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s);
+// logit = <a, wp> + b ; prob = sigmoid(logit). a is [B][F] NHWC-flattened.
+template <typename T>
+void classifier_sigmoid(const T* a, const float* wp, const float* bias, float* prob, int B, int F, cudaStream_t s);
+template <typename T>
+void features_nchw(const T* a, float* feat, int B, int C, cudaStream_t s);  // (B, C*16) in reference order
+// dlogit = dprob * p * (1-p)
+void sigmoid_bwd(const float* prob, const float* dprob, float* dlogit, int B, cudaStream_t s);
+// dy[b][j] = dlogit[b] * wp[j] * mask[b][c] * leaky'(a[b][j])
+template <typename T>
+void classifier_bwd_dy(const float* dlogit, const float* wp, const float* mask, const T* a, float slope, T* dy, int B,
+                       int C, cudaStream_t s);
+void sum_vector(const float* v, int n, float* out, cudaStream_t s);  // out[0] = sum v (deterministic)
+void dropout_masks(uint64_t seed, uint64_t offset, long n, float p, float* out, cudaStream_t s);
+
+// ---- loss ------------------------------------------------------------------------------------
+void bce_forward(const float* prob, const float* target, int n, float* loss, cudaStream_t s);
+void bce_backward(const float* prob, const float* target, int n, const float* grad_loss, float* dprob, cudaStream_t s);
+// Fused metrics + dlogit for the training step. prob holds [real B | fake B].
+void d_loss_metrics(const float* prob, int B, float smoothing, float* metrics, float* dlogit, cudaStream_t s);
+void g_loss_metrics(const float* prob, int B, float* metrics, float* dlogit, cudaStream_t s);
+
+// ---- optimizer -------------------------------------------------------------------------------
+void adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, long step,
+               cudaStream_t s);
+
+// ---- direct convolutions (validation mode / fallback). Weights are the fp32 master tensors in PyTorch
+// layout, addressed as w[o*so + i*si + ky*4 + kx] where o = output channel of THIS op, i = input channel.
+template <typename T>
+void conv_s2_direct(const T* in, const float* w, long so, long si, const Epi& e, T* out, int B, int inH, int inW,
+                    int Cin, int Cout, cudaStream_t s);
+template <typename T>
+void convT_direct(const T* in, const float* w, long so, long si, const Epi& e, T* out, int B, int inH, int inW, int Cin,
+                  int Cout, cudaStream_t s);
+// dW[m][n][16] = sum coarse[pix][m] * fine[2*pix-1+tap][n]
+template <typename T>
+void wgrad_direct(const T* coarse, const T* fine, float* dW, int B, int cH, int cW, int Mc, int Nf, cudaStream_t s);
+// y[b][j] = sum_i zp[b][i] * W[f(j)][i] + bias[f(j)]  (fp32 master weights, NHWC-permuted output)
+template <typename T>
+void fc_direct(const T* zp, int Kp, const float* W, const float* bias, T* y, int B, int C0, int latent,
+               cudaStream_t s);
+// dW[f(j)][i] = sum_b dy[b][j] * zp[b][i]
+template <typename T>
+void fc_wgrad_direct(const T* dy, const T* zp, int Kp, float* dW, int B, int C0, int latent, cudaStream_t s);
+template <typename T>
+void fc_dz_direct(const T* dy, const float* W, float* dz, int B, int C0, int latent, cudaStream_t s);
+
+const char* kernels_last_error();
+int kernels_check(const char* what);  // cudaGetLastError -> 0 / -1 (message kept)
+
+}  // namespace sg

@@ -1,0 +1,994 @@
+// sg_model.cu — the Generator / Discriminator execution plans and the extern "C" boundary (include/siggan.h).
+//
+// Data layout in HBM
+//   activations : NHWC, bf16 (SG_PREC_BF16) or fp32 (SG_PREC_FP32); images (C = 1) are the caller's fp32 (B,1,S,S)
+//   parameters  : the caller's flat fp32 buffers in reference named_parameters() order (PyTorch layouts);
+//                 bf16 tensor-core packs [Cout][ky*4+kx][Cin] are rebuilt from them at the start of every
+//                 forward (3.9 M parameters: a few microseconds) so external optimizers / load_state_dict just work
+//   gradients   : flat fp32 buffers with the same offsets as the parameters
+//   workspace   : per-forward saved activations (caller-allocated so autograd owns their lifetime)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/siggan.h"
+#include "sg_conv_umma.cuh"
+#include "sg_kernels.cuh"
+
+using sg::bf16;
+
+static thread_local char t_err[768] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+#define SG_TRY(expr)                 \
+    do {                             \
+        int rc_ = (expr);            \
+        if (rc_ != 0) return rc_;    \
+    } while (0)
+#define SG_UMMA(expr)                                                  \
+    do {                                                               \
+        if ((expr) != 0) return fail("%s", sg::umma_last_error());     \
+    } while (0)
+#define SG_KCHECK(what)                                                   \
+    do {                                                                  \
+        if (sg::kernels_check(what) != 0) return fail("%s", sg::kernels_last_error()); \
+    } while (0)
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct TensorInfo {
+    std::string name;
+    long long offset;
+    int shape[4];
+    long long numel() const {
+        long long n = 1;
+        for (int i = 0; i < 4; ++i)
+            if (shape[i] > 0) n *= shape[i];
+        return n;
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);  // implicit device sync: in-flight users are done before the old block goes away
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Optional per-operation device timing (CUDA events on the launch stream) with the algorithmic work of each op.
+struct ProfRec {
+    std::string name;
+    double flops, bytes;
+    cudaEvent_t a, b;
+};
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+struct ProfScope {
+    Profiler* p;
+    cudaStream_t s;
+    size_t idx = 0;
+    ProfScope(Profiler* prof, cudaStream_t stream, const char* name, double flops, double bytes) : p(prof), s(stream) {
+        if (!p->on) return;
+        ProfRec r{name, flops, bytes, p->get(), p->get()};
+        cudaEventRecord(r.a, s);
+        idx = p->recs.size();
+        p->recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (p->on) cudaEventRecord(p->recs[idx].b, s);
+    }
+};
+#define PROF(name, flops, bytes) ProfScope prof_scope_(&c->prof, s, name, flops, bytes)
+
+struct BNInfo {
+    int C;
+    long long gamma_off, beta_off;  // into the flat G parameter buffer
+    long long mean_off, var_off;    // into the flat running-stat buffer
+};
+
+// Carved view of one Generator forward's saved state.
+struct GWs {
+    char* zp;
+    char* fc_y;
+    char* fc_a;
+    char* y[6];
+    char* a[6];
+    float* out;
+    float* mean[7];
+    float* rstd[7];
+    float* scale[7];
+    float* shift[7];
+    size_t bytes;
+};
+struct DWs {
+    char* a[6];
+    float* prob;
+    size_t bytes;
+};
+
+}  // namespace
+
+struct sg_ctx {
+    sg_config cfg;
+    int S, L, ND, Kp, es;  // image size, #upsample blocks, #downsample blocks, padded latent, activation element size
+    int gch[7], dch[7];
+    std::vector<TensorInfo> gt, dt;
+    long long g_count, d_count, g_stats;
+    BNInfo bn[7];
+    // tensor indices
+    int g_fc_w, g_fc_b, g_up_w[6], g_final_w, g_final_b;
+    int d_conv_w[6], d_conv_b[6], d_cls_w, d_cls_b;
+    // library-owned device memory
+    DevBuf packs;    // bf16 weight packs + permuted fp32 vectors
+    bf16 *fc_Wp, *g_packF[6], *g_packB[6], *d_packF[6], *d_packB[6];
+    float *fc_biasp, *cls_wp;
+    DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
+    float *dlogit, *k1, *k2, *k3;
+    int scratch_batch = 0;
+    Profiler prof;
+};
+
+namespace {
+
+void add_tensor(std::vector<TensorInfo>& v, long long& off, const std::string& name, int a, int b = 0, int c = 0,
+                int d = 0) {
+    TensorInfo t;
+    t.name = name;
+    t.offset = off;
+    t.shape[0] = a;
+    t.shape[1] = b;
+    t.shape[2] = c;
+    t.shape[3] = d;
+    off += t.numel();
+    v.push_back(t);
+}
+
+int g_spatial(const sg_ctx* c, int i) { return 8 << i; }        // output H=W of upsample block i
+int d_spatial(const sg_ctx* c, int i) { return c->S >> (i + 1); }  // output H=W of downsample block i
+
+GWs carve_g(const sg_ctx* c, void* base, int B) {
+    GWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    const size_t es = c->es;
+    const int F0 = c->gch[0] * 16;
+    w.zp = take(static_cast<size_t>(B) * c->Kp * es);
+    w.fc_y = take(static_cast<size_t>(B) * F0 * es);
+    w.fc_a = take(static_cast<size_t>(B) * F0 * es);
+    for (int i = 0; i < c->L; ++i) {
+        const size_t n = static_cast<size_t>(B) * g_spatial(c, i) * g_spatial(c, i) * c->gch[i + 1] * es;
+        w.y[i] = take(n);
+        w.a[i] = take(n);
+    }
+    w.out = reinterpret_cast<float*>(take(static_cast<size_t>(B) * c->S * c->S * 4));
+    for (int i = 0; i <= c->L; ++i) {
+        const size_t n = static_cast<size_t>(c->bn[i].C) * 4;
+        w.mean[i] = reinterpret_cast<float*>(take(n));
+        w.rstd[i] = reinterpret_cast<float*>(take(n));
+        w.scale[i] = reinterpret_cast<float*>(take(n));
+        w.shift[i] = reinterpret_cast<float*>(take(n));
+    }
+    w.bytes = off;
+    return w;
+}
+
+DWs carve_d(const sg_ctx* c, void* base, int B) {
+    DWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    for (int i = 0; i < c->ND; ++i)
+        w.a[i] = take(static_cast<size_t>(B) * d_spatial(c, i) * d_spatial(c, i) * c->dch[i + 1] * c->es);
+    w.prob = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 4));
+    w.bytes = off;
+    return w;
+}
+
+long long mask_offset(const sg_ctx* c, int batch, int layer) {
+    long long off = 0;
+    for (int i = 0; i < layer; ++i) off += static_cast<long long>(batch) * c->dch[i + 1];
+    return off;
+}
+
+int ensure_scratch(sg_ctx* c, int B) {
+    if (B <= c->scratch_batch) return 0;
+    const size_t lvl = static_cast<size_t>(B) * c->S * c->S * 32 * c->es;  // largest activation level
+    SG_TRY(c->bufA.ensure(lvl));
+    SG_TRY(c->bufB.ensure(lvl));
+    SG_TRY(c->dpre.ensure(static_cast<size_t>(B) * c->S * c->S * 4));
+    size_t wp = 0;
+    for (int i = 0; i < c->L; ++i) {
+        const int h = g_spatial(c, i) / 2;
+        const size_t n = sg::wgrad_partial_floats(B, h, h, c->gch[i], c->gch[i + 1]);
+        if (n > wp) wp = n;
+    }
+    for (int i = 1; i < c->ND; ++i) {
+        const int h = d_spatial(c, i);
+        const size_t n = sg::wgrad_partial_floats(B, h, h, c->dch[i + 1], c->dch[i]);
+        if (n > wp) wp = n;
+    }
+    {
+        const size_t n = sg::fc_wgrad_partial_floats(B, c->gch[0] * 16, c->Kp);
+        if (n > wp) wp = n;
+    }
+    SG_TRY(c->wpart.ensure(wp * 4));
+    SG_TRY(c->cpart.ensure(static_cast<size_t>(sg::kMaxChunks) * 2 * 2048 * 4));
+    SG_TRY(c->small.ensure((static_cast<size_t>(B) + 3 * 8192) * 4));
+    c->dlogit = static_cast<float*>(c->small.p);
+    c->k1 = c->dlogit + B;
+    c->k2 = c->k1 + 8192;
+    c->k3 = c->k2 + 8192;
+    c->scratch_batch = B;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packs
+// ------------------------------------------------------------------------------------------------
+int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
+    if (c->cfg.precision != SG_PREC_BF16) return 0;
+    PROF("g.pack", 0, 10.0 * c->g_count);
+    sg::pack_fc(params + c->gt[c->g_fc_w].offset, params + c->gt[c->g_fc_b].offset, c->fc_Wp, c->fc_biasp, c->gch[0],
+                c->cfg.latent_dim, c->Kp, s);
+    for (int i = 0; i < c->L; ++i)  // W (Cin, Cout, 4, 4): forward pack [Cout][16][Cin] = BA, dgrad pack [Cin][16][Cout] = AB
+        sg::pack_w16(params + c->gt[c->g_up_w[i]].offset, c->g_packB[i], c->g_packF[i], c->gch[i], c->gch[i + 1], s);
+    SG_KCHECK("pack_generator");
+    return 0;
+}
+int pack_discriminator(sg_ctx* c, const float* params, cudaStream_t s) {
+    PROF("d.pack", 0, 10.0 * c->d_count);
+    sg::pack_classifier(params + c->dt[c->d_cls_w].offset, c->cls_wp, c->dch[c->ND], s);
+    if (c->cfg.precision == SG_PREC_BF16) {
+        for (int i = 1; i < c->ND; ++i)  // W (Cout, Cin, 4, 4): forward pack [Cout][16][Cin] = AB, dgrad pack = BA
+            sg::pack_w16(params + c->dt[c->d_conv_w[i]].offset, c->d_packF[i], c->d_packB[i], c->dch[i + 1], c->dch[i],
+                         s);
+    }
+    SG_KCHECK("pack_discriminator");
+    return 0;
+}
+
+sg::ConvGemmArgs epi_args(void* out, int ldo) {
+    sg::ConvGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out = out;
+    a.ldo = ldo;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generator
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, int B, int train, void* ws_ptr,
+                float* out_image, uint8_t* out_u8, bool save, cudaStream_t s) {
+    constexpr bool kTC = std::is_same<T, bf16>::value;
+    GWs w = carve_g(c, ws_ptr, B);
+    const int F0 = c->gch[0] * 16;
+    const int latent = c->cfg.latent_dim;
+    const bool fused_eval = !train && !save;  // fold running-stat BN + ReLU into the producing GEMM's epilogue
+    SG_TRY(pack_generator(c, params, s));
+    const double es = c->es;
+    {
+        PROF("g.cast_z", 0, B * (4.0 * latent + es * c->Kp));
+        sg::cast_pad_z<T>(z, reinterpret_cast<T*>(w.zp), B, latent, c->Kp, s);
+    }
+    if (!train) {
+        PROF("g.bn_eval", 0, 0);
+        for (int i = 0; i <= c->L; ++i)
+            sg::bn_finalize(nullptr, 0, 1, c->bn[i].C, params + c->bn[i].gamma_off, params + c->bn[i].beta_off,
+                            stats + c->bn[i].mean_off, stats + c->bn[i].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 0,
+                            i == 0 ? c->gch[0] : 0, w.mean[i], w.rstd[i], w.scale[i], w.shift[i], s);
+    }
+    // ---- fc + BN1d + ReLU (gen…:124-128), output already NHWC (B,4,4,C0)
+    {
+        T* dst = reinterpret_cast<T*>(fused_eval ? w.fc_a : w.fc_y);
+        {
+        PROF("g.fc", 2.0 * B * latent * F0, es * B * (double)(F0 + c->Kp));
+        if (kTC) {
+            sg::ConvGemmArgs e = epi_args(dst, F0);
+            e.bias = c->fc_biasp;
+            if (fused_eval) {
+                e.scale = w.scale[0];
+                e.shift = w.shift[0];
+                e.act = sg::kActRelu;
+            }
+            SG_UMMA(sg::launch_conv_gemm(sg::kPlain, reinterpret_cast<const bf16*>(w.zp), c->fc_Wp, B, 1, 1, c->Kp, F0, e,
+                                         s));
+        } else {
+            sg::fc_direct<T>(reinterpret_cast<const T*>(w.zp), c->Kp, params + c->gt[c->g_fc_w].offset,
+                             params + c->gt[c->g_fc_b].offset, reinterpret_cast<T*>(w.fc_y), B, c->gch[0], latent, s);
+            dst = reinterpret_cast<T*>(w.fc_y);
+        }
+        }
+        if (!(kTC && fused_eval)) {
+            if (train) {
+                PROF("g.fc.bn_stats", 0, es * B * (double)F0);
+                const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.fc_y), nullptr, nullptr, nullptr,
+                                                     nullptr, B, F0, static_cast<float*>(c->cpart.p), s);
+                sg::bn_finalize(static_cast<float*>(c->cpart.p), chunks, B, F0, params + c->bn[0].gamma_off,
+                                params + c->bn[0].beta_off, stats + c->bn[0].mean_off, stats + c->bn[0].var_off,
+                                c->cfg.bn_momentum, c->cfg.bn_eps, 1, c->gch[0], w.mean[0], w.rstd[0], w.scale[0],
+                                w.shift[0], s);
+            }
+            PROF("g.fc.bn_apply", 0, 2.0 * es * B * (double)F0);
+            sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.fc_y), w.scale[0], w.shift[0],
+                                 reinterpret_cast<T*>(w.fc_a), B, F0, s);
+        }
+    }
+    // ---- upsample blocks: ConvT 4x4 s2 p1 (no bias) + BN2d + ReLU (gen…:46-60)
+    const char* in = w.fc_a;
+    for (int i = 0; i < c->L; ++i) {
+        const int ih = g_spatial(c, i) / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
+        const long rows = static_cast<long>(B) * 4 * ih * ih;
+        const bool fuse = kTC && fused_eval;
+        T* dst = reinterpret_cast<T*>(fuse ? w.a[i] : w.y[i]);
+        const std::string nm = "g.up" + std::to_string(i);
+        const double cflops = 2.0 * B * ih * ih * 16.0 * Cin * Cout;
+        {
+        PROF(nm.c_str(), cflops, es * ((double)B * ih * ih * Cin + (double)rows * Cout));
+        if (kTC) {
+            sg::ConvGemmArgs e = epi_args(dst, Cout);
+            if (fuse) {
+                e.scale = w.scale[i + 1];
+                e.shift = w.shift[i + 1];
+                e.act = sg::kActRelu;
+            }
+            SG_UMMA(sg::launch_conv_gemm(sg::kConvT, reinterpret_cast<const bf16*>(in), c->g_packF[i], B, ih, ih, Cin,
+                                         Cout, e, s));
+        } else {
+            sg::Epi e;
+            sg::convT_direct<T>(reinterpret_cast<const T*>(in), params + c->gt[c->g_up_w[i]].offset, 16,
+                                static_cast<long>(Cout) * 16, e, dst, B, ih, ih, Cin, Cout, s);
+        }
+        }
+        if (!fuse) {
+            if (train) {
+                PROF((nm + ".bn_stats").c_str(), 0, es * (double)rows * Cout);
+                const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.y[i]), nullptr, nullptr, nullptr,
+                                                     nullptr, rows, Cout, static_cast<float*>(c->cpart.p), s);
+                sg::bn_finalize(static_cast<float*>(c->cpart.p), chunks, rows, Cout, params + c->bn[i + 1].gamma_off,
+                                params + c->bn[i + 1].beta_off, stats + c->bn[i + 1].mean_off,
+                                stats + c->bn[i + 1].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 1, 0, w.mean[i + 1],
+                                w.rstd[i + 1], w.scale[i + 1], w.shift[i + 1], s);
+            }
+            PROF((nm + ".bn_apply").c_str(), 0, 2.0 * es * (double)rows * Cout);
+            sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.y[i]), w.scale[i + 1], w.shift[i + 1],
+                                 reinterpret_cast<T*>(w.a[i]), rows, Cout, s);
+        }
+        in = w.a[i];
+    }
+    // ---- Conv3x3 + tanh (gen…:153-163)
+    float* out = save ? w.out : out_image;
+    {
+    PROF("g.final", 2.0 * B * c->S * c->S * 9.0 * c->gch[c->L], (double)B * c->S * c->S * (es * c->gch[c->L] + 4.0));
+    sg::final_conv_tanh<T>(reinterpret_cast<const T*>(in), params + c->gt[c->g_final_w].offset,
+                           params + c->gt[c->g_final_b].offset, out, out_u8, B, c->S, c->gch[c->L], s);
+    }
+    if (save && out_image) {
+        cudaError_t e = cudaMemcpyAsync(out_image, w.out, static_cast<size_t>(B) * c->S * c->S * 4,
+                                        cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail("g_forward: copy of the image failed: %s", cudaGetErrorString(e));
+    }
+    SG_KCHECK("g_forward");
+    return 0;
+}
+
+template <typename T>
+int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float* grad_image, int B, int train,
+                 float* grads, float* dz, cudaStream_t s) {
+    constexpr bool kTC = std::is_same<T, bf16>::value;
+    GWs w = carve_g(c, const_cast<void*>(ws_ptr), B);
+    float* cpart = static_cast<float*>(c->cpart.p);
+    float* wpart = static_cast<float*>(c->wpart.p);
+    char* cur = static_cast<char*>(c->bufA.p);
+    char* nxt = static_cast<char*>(c->bufB.p);
+    const int L = c->L;
+    const double es = c->es;
+    {
+    PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L], (double)B * c->S * c->S * (12.0 + 3.0 * es * c->gch[L]));
+    sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.a[L - 1]),
+                          params + c->gt[c->g_final_w].offset, static_cast<float*>(c->dpre.p),
+                          reinterpret_cast<T*>(cur), grads + c->gt[c->g_final_w].offset,
+                          grads + c->gt[c->g_final_b].offset, cpart, B, c->S, c->gch[L], s);
+    }
+    for (int i = L - 1; i >= 0; --i) {
+        const int oh = g_spatial(c, i), ih = oh / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
+        const long rows = static_cast<long>(B) * oh * oh;
+        const BNInfo& bn = c->bn[i + 1];
+        const std::string nm = "g.up" + std::to_string(i);
+        const double cflops = 2.0 * B * ih * ih * 16.0 * Cin * Cout;
+        // BatchNorm2d backward (cur holds relu'-masked d/d(bn output)); result dy overwrites cur
+        {
+        PROF((nm + ".bn_bwd_reduce").c_str(), 0, 2.0 * es * (double)rows * Cout);
+        const int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]),
+                                             w.mean[i + 1], w.rstd[i + 1], nullptr, rows, Cout, cpart, s);
+        sg::bn_bwd_finalize(cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], train, 0,
+                            grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+        }
+        {
+        PROF((nm + ".bn_bwd_apply").c_str(), 0, 3.0 * es * (double)rows * Cout);
+        sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]), w.mean[i + 1],
+                            w.rstd[i + 1], c->k1, c->k2, c->k3, reinterpret_cast<T*>(cur), rows, Cout, s);
+        }
+        const char* xin = i == 0 ? w.fc_a : w.a[i - 1];
+        float* dW = grads + c->gt[c->g_up_w[i]].offset;
+        if (kTC) {
+            {
+            PROF((nm + ".wgrad").c_str(), cflops, es * ((double)B * ih * ih * Cin + (double)rows * Cout));
+            SG_UMMA(sg::launch_wgrad(reinterpret_cast<const bf16*>(xin), reinterpret_cast<const bf16*>(cur), B, ih, ih,
+                                     Cin, Cout, wpart, c->wpart.cap / 4, dW, 0, s));
+            }
+            PROF((nm + ".dgrad").c_str(), cflops, es * (2.0 * B * ih * ih * Cin + (double)rows * Cout));
+            sg::ConvGemmArgs e = epi_args(nxt, Cin);
+            e.gate = reinterpret_cast<const bf16*>(xin);  // ReLU' of the previous block (slope 0)
+            e.slope = 0.f;
+            SG_UMMA(sg::launch_conv_gemm(sg::kConvS2, reinterpret_cast<const bf16*>(cur), c->g_packB[i], B, oh, oh, Cout,
+                                         Cin, e, s));
+        } else {
+            sg::wgrad_direct<T>(reinterpret_cast<const T*>(xin), reinterpret_cast<const T*>(cur), dW, B, ih, ih, Cin,
+                                Cout, s);
+            sg::Epi e;
+            e.gate = xin;
+            e.slope = 0.f;
+            sg::conv_s2_direct<T>(reinterpret_cast<const T*>(cur), params + c->gt[c->g_up_w[i]].offset,
+                                  static_cast<long>(Cout) * 16, 16, e, reinterpret_cast<T*>(nxt), B, oh, oh, Cout, Cin,
+                                  s);
+        }
+        char* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    // ---- fc: BatchNorm1d backward, weight / bias gradients
+    const int F0 = c->gch[0] * 16, latent = c->cfg.latent_dim;
+    const BNInfo& bn = c->bn[0];
+    PROF("g.fc.bwd", 2.0 * B * F0 * latent, 6.0 * es * B * (double)F0);
+    int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.fc_y), w.mean[0],
+                                   w.rstd[0], nullptr, B, F0, cpart, s);
+    sg::bn_bwd_finalize(cpart, chunks, B, F0, params + bn.gamma_off, w.rstd[0], train, c->gch[0], grads + bn.gamma_off,
+                        grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+    sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.fc_y), w.mean[0], w.rstd[0], c->k1,
+                        c->k2, c->k3, reinterpret_cast<T*>(cur), B, F0, s);
+    chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr, nullptr, B, F0, cpart, s);
+    sg::col_finalize(cpart, chunks, F0, c->gch[0], grads + c->gt[c->g_fc_b].offset, nullptr, s);
+    float* dWfc = grads + c->gt[c->g_fc_w].offset;
+    if (kTC) {
+        SG_UMMA(sg::launch_fc_wgrad(reinterpret_cast<const bf16*>(cur), reinterpret_cast<const bf16*>(w.zp), B, c->gch[0],
+                                    c->Kp, latent, wpart, c->wpart.cap / 4, dWfc, s));
+    } else {
+        sg::fc_wgrad_direct<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.zp), c->Kp, dWfc, B,
+                               c->gch[0], latent, s);
+    }
+    if (dz) sg::fc_dz_direct<T>(reinterpret_cast<const T*>(cur), params + c->gt[c->g_fc_w].offset, dz, B, c->gch[0], latent, s);
+    SG_KCHECK("g_backward");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Discriminator
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int d_forward_t(sg_ctx* c, const float* params, const float* x, int B, const float* masks, void* ws_ptr,
+                float* prob_out, float* feat_out, cudaStream_t s) {
+    constexpr bool kTC = std::is_same<T, bf16>::value;
+    DWs w = carve_d(c, ws_ptr, B);
+    const float slope = c->cfg.leaky_slope;
+    SG_TRY(pack_discriminator(c, params, s));
+    const double es = c->es;
+    {
+    const int o0 = c->S / 2;
+    PROF("d.c0", 2.0 * B * o0 * o0 * 16.0 * c->dch[1], (double)B * (4.0 * c->S * c->S + es * o0 * o0 * c->dch[1]));
+    sg::d_conv0<T>(x, params + c->dt[c->d_conv_w[0]].offset, params + c->dt[c->d_conv_b[0]].offset,
+                   masks ? masks + mask_offset(c, B, 0) : nullptr, slope, reinterpret_cast<T*>(w.a[0]), B, c->S,
+                   c->dch[1], s);
+    }
+    for (int i = 1; i < c->ND; ++i) {
+        const int ih = d_spatial(c, i - 1), Cin = c->dch[i], Cout = c->dch[i + 1];
+        const std::string nm = "d.c" + std::to_string(i);
+        PROF(nm.c_str(), 2.0 * B * (ih / 2) * (ih / 2) * 16.0 * Cin * Cout,
+             es * B * ((double)ih * ih * Cin + (double)(ih / 2) * (ih / 2) * Cout));
+        const float* mk = masks ? masks + mask_offset(c, B, i) : nullptr;
+        const float* bias = params + c->dt[c->d_conv_b[i]].offset;
+        if (kTC) {
+            sg::ConvGemmArgs e = epi_args(w.a[i], Cout);
+            e.bias = bias;
+            e.act = sg::kActLeaky;
+            e.slope = slope;
+            e.mask = mk;
+            e.ldmask = Cout;
+            SG_UMMA(sg::launch_conv_gemm(sg::kConvS2, reinterpret_cast<const bf16*>(w.a[i - 1]), c->d_packF[i], B, ih, ih,
+                                         Cin, Cout, e, s));
+        } else {
+            sg::Epi e;
+            e.bias = bias;
+            e.act = 2;
+            e.slope = slope;
+            e.mask = mk;
+            e.ldmask = Cout;
+            sg::conv_s2_direct<T>(reinterpret_cast<const T*>(w.a[i - 1]), params + c->dt[c->d_conv_w[i]].offset,
+                                  static_cast<long>(Cin) * 16, 16, e, reinterpret_cast<T*>(w.a[i]), B, ih, ih, Cin, Cout,
+                                  s);
+        }
+    }
+    const int Cl = c->dch[c->ND];
+    PROF("d.cls", 2.0 * B * Cl * 16, es * B * Cl * 16.0);
+    sg::classifier_sigmoid<T>(reinterpret_cast<const T*>(w.a[c->ND - 1]), c->cls_wp, params + c->dt[c->d_cls_b].offset,
+                              w.prob, B, Cl * 16, s);
+    if (prob_out) {
+        cudaError_t e = cudaMemcpyAsync(prob_out, w.prob, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail("d_forward: copy of probabilities failed: %s", cudaGetErrorString(e));
+    }
+    if (feat_out) sg::features_nchw<T>(reinterpret_cast<const T*>(w.a[c->ND - 1]), feat_out, B, Cl, s);
+    SG_KCHECK("d_forward");
+    return 0;
+}
+
+// dlogit: d(loss)/d(logit) per sample (already includes sigmoid').
+template <typename T>
+int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_ptr, const float* masks,
+                 const float* dlogit, int B, float* grads, float* dx, cudaStream_t s) {
+    constexpr bool kTC = std::is_same<T, bf16>::value;
+    DWs w = carve_d(c, const_cast<void*>(ws_ptr), B);
+    const float slope = c->cfg.leaky_slope;
+    float* cpart = static_cast<float*>(c->cpart.p);
+    float* wpart = static_cast<float*>(c->wpart.p);
+    char* cur = static_cast<char*>(c->bufA.p);
+    char* nxt = static_cast<char*>(c->bufB.p);
+    const int last = c->ND - 1, Cl = c->dch[c->ND];
+    const double es = c->es;
+    {
+    PROF("d.cls_bwd", 4.0 * B * Cl * 16, 3.0 * es * B * Cl * 16.0);
+    if (grads) {
+        const int chunks = sg::col_reduce<T>(2, reinterpret_cast<const T*>(w.a[last]), nullptr, nullptr, nullptr, dlogit,
+                                             B, Cl * 16, cpart, s);
+        sg::col_finalize(cpart, chunks, Cl * 16, Cl, grads + c->dt[c->d_cls_w].offset, nullptr, s);
+        sg::sum_vector(dlogit, B, grads + c->dt[c->d_cls_b].offset, s);
+    }
+    sg::classifier_bwd_dy<T>(dlogit, c->cls_wp, masks ? masks + mask_offset(c, B, last) : nullptr,
+                             reinterpret_cast<const T*>(w.a[last]), slope, reinterpret_cast<T*>(cur), B, Cl, s);
+    }
+    for (int i = last; i >= 1; --i) {
+        const int oh = d_spatial(c, i), Cin = c->dch[i], Cout = c->dch[i + 1];
+        const long rows = static_cast<long>(B) * oh * oh;
+        const std::string nm = "d.c" + std::to_string(i);
+        const double cflops = 2.0 * (double)rows * 16.0 * Cin * Cout;
+        if (grads) {
+            float* dW = grads + c->dt[c->d_conv_w[i]].offset;
+            {
+            PROF((nm + ".wgrad").c_str(), cflops, es * ((double)rows * Cout + 4.0 * rows * Cin));
+            if (kTC)
+                SG_UMMA(sg::launch_wgrad(reinterpret_cast<const bf16*>(cur), reinterpret_cast<const bf16*>(w.a[i - 1]), B,
+                                         oh, oh, Cout, Cin, wpart, c->wpart.cap / 4, dW, 0, s));
+            else
+                sg::wgrad_direct<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.a[i - 1]), dW, B, oh,
+                                    oh, Cout, Cin, s);
+            }
+            PROF((nm + ".dbias").c_str(), 0, es * (double)rows * Cout);
+            const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr, nullptr,
+                                                 rows, Cout, cpart, s);
+            sg::col_finalize(cpart, chunks, Cout, 0, grads + c->dt[c->d_conv_b[i]].offset, nullptr, s);
+        }
+        // data gradient = transposed conv of dy, gated by the previous block's LeakyReLU' and dropout mask
+        const float* mk = masks ? masks + mask_offset(c, B, i - 1) : nullptr;
+        PROF((nm + ".dgrad").c_str(), cflops, es * ((double)rows * Cout + 8.0 * rows * Cin));
+        if (kTC) {
+            sg::ConvGemmArgs e = epi_args(nxt, Cin);
+            e.gate = reinterpret_cast<const bf16*>(w.a[i - 1]);
+            e.slope = slope;
+            e.mask = mk;
+            e.ldmask = Cin;
+            SG_UMMA(sg::launch_conv_gemm(sg::kConvT, reinterpret_cast<const bf16*>(cur), c->d_packB[i], B, oh, oh, Cout,
+                                         Cin, e, s));
+        } else {
+            sg::Epi e;
+            e.gate = w.a[i - 1];
+            e.slope = slope;
+            e.mask = mk;
+            e.ldmask = Cin;
+            sg::convT_direct<T>(reinterpret_cast<const T*>(cur), params + c->dt[c->d_conv_w[i]].offset, 16,
+                                static_cast<long>(Cin) * 16, e, reinterpret_cast<T*>(nxt), B, oh, oh, Cout, Cin, s);
+        }
+        char* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    const int o0 = c->S / 2;
+    if (grads) {
+        PROF("d.c0.wgrad", 2.0 * B * o0 * o0 * 16.0 * c->dch[1], (double)B * (4.0 * c->S * c->S + es * o0 * o0 * c->dch[1]));
+        sg::d_conv0_wgrad<T>(x, reinterpret_cast<const T*>(cur), grads + c->dt[c->d_conv_w[0]].offset, cpart, B, c->S,
+                             c->dch[1], s);
+    }
+    if (dx) {
+        PROF("d.c0.dgrad", 2.0 * B * o0 * o0 * 16.0 * c->dch[1], (double)B * (4.0 * c->S * c->S + es * o0 * o0 * c->dch[1]));
+        sg::d_conv0_dgrad<T>(reinterpret_cast<const T*>(cur), params + c->dt[c->d_conv_w[0]].offset, dx, B, c->S,
+                             c->dch[1], s);
+    }
+    SG_KCHECK("d_backward");
+    return 0;
+}
+
+#define DISPATCH_T(ctx, fn, ...) \
+    ((ctx)->cfg.precision == SG_PREC_BF16 ? fn<bf16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+unsigned long long sg_launch_count(void) { return sg::g_launches; }
+
+int sg_profile_enable(sg_ctx* c, int on) {
+    if (!c) return fail("sg_profile_enable: null ctx");
+    for (ProfRec& r : c->prof.recs) {
+        c->prof.pool.push_back(r.a);
+        c->prof.pool.push_back(r.b);
+    }
+    c->prof.recs.clear();
+    c->prof.on = on != 0;
+    return 0;
+}
+
+// Writes one line per recorded op: "name\tmilliseconds\tflops\tbytes\n". Synchronises the device.
+long long sg_profile_dump(sg_ctx* c, char* buf, size_t cap) {
+    if (!c || !buf || cap == 0) return fail("sg_profile_dump: bad argument");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail("sg_profile_dump: %s", cudaGetErrorString(e));
+    size_t off = 0;
+    buf[0] = 0;
+    for (const ProfRec& r : c->prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        int n = snprintf(buf + off, cap - off, "%s\t%.6f\t%.6e\t%.6e\n", r.name.c_str(), ms, r.flops, r.bytes);
+        if (n < 0 || static_cast<size_t>(n) >= cap - off) break;
+        off += n;
+    }
+    return static_cast<long long>(off);
+}
+const char* sg_last_error(void) { return t_err; }
+
+int sg_create(const sg_config* cfg, sg_ctx** out) {
+    if (!cfg || !out) return fail("sg_create: null argument");
+    if (cfg->image_size != 64 && cfg->image_size != 128)
+        return fail("sg_create: image_size must be 64 or 128, got %d", cfg->image_size);
+    if (cfg->latent_dim < 1 || cfg->latent_dim > 512) return fail("sg_create: latent_dim %d unsupported", cfg->latent_dim);
+    if (cfg->precision != SG_PREC_BF16 && cfg->precision != SG_PREC_FP32) return fail("sg_create: bad precision");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        cudaGetLastError();
+        return fail("sg_create: no CUDA device (this library has no CPU path)");
+    }
+    sg_ctx* c = new sg_ctx();
+    c->cfg = *cfg;
+    c->S = cfg->image_size;
+    c->es = cfg->precision == SG_PREC_BF16 ? 2 : 4;
+    c->Kp = (cfg->latent_dim + 63) / 64 * 64;
+    if (c->S == 64) {
+        const int g[] = {256, 128, 64, 32, 32}, d[] = {1, 64, 128, 256, 512};
+        c->L = 4;
+        c->ND = 4;
+        memcpy(c->gch, g, sizeof(g));
+        memcpy(c->dch, d, sizeof(d));
+    } else {
+        const int g[] = {512, 256, 128, 64, 32, 32}, d[] = {1, 64, 128, 256, 512, 512};
+        c->L = 5;
+        c->ND = 5;
+        memcpy(c->gch, g, sizeof(g));
+        memcpy(c->dch, d, sizeof(d));
+    }
+    // ---- parameter tables in reference named_parameters() order (gen…:124-163, disc…:131-207)
+    long long off = 0, soff = 0;
+    const int F0 = c->gch[0] * 16;
+    c->g_fc_w = (int)c->gt.size();
+    add_tensor(c->gt, off, "fc.0.weight", F0, cfg->latent_dim);
+    c->g_fc_b = (int)c->gt.size();
+    add_tensor(c->gt, off, "fc.0.bias", F0);
+    c->bn[0].C = F0;
+    c->bn[0].gamma_off = off;
+    add_tensor(c->gt, off, "fc.1.weight", F0);
+    c->bn[0].beta_off = off;
+    add_tensor(c->gt, off, "fc.1.bias", F0);
+    c->bn[0].mean_off = soff;
+    c->bn[0].var_off = soff + F0;
+    soff += 2 * F0;
+    for (int i = 0; i < c->L; ++i) {
+        const std::string p = "upsample_blocks." + std::to_string(i) + ".block.";
+        c->g_up_w[i] = (int)c->gt.size();
+        add_tensor(c->gt, off, p + "0.weight", c->gch[i], c->gch[i + 1], 4, 4);
+        c->bn[i + 1].C = c->gch[i + 1];
+        c->bn[i + 1].gamma_off = off;
+        add_tensor(c->gt, off, p + "1.weight", c->gch[i + 1]);
+        c->bn[i + 1].beta_off = off;
+        add_tensor(c->gt, off, p + "1.bias", c->gch[i + 1]);
+        c->bn[i + 1].mean_off = soff;
+        c->bn[i + 1].var_off = soff + c->gch[i + 1];
+        soff += 2 * c->gch[i + 1];
+    }
+    c->g_final_w = (int)c->gt.size();
+    add_tensor(c->gt, off, "final_conv.0.weight", 1, c->gch[c->L], 3, 3);
+    c->g_final_b = (int)c->gt.size();
+    add_tensor(c->gt, off, "final_conv.0.bias", 1);
+    c->g_count = off;
+    c->g_stats = soff;
+    off = 0;
+    for (int i = 0; i < c->ND; ++i) {
+        const std::string p = "conv_blocks." + std::to_string(i) + ".block.0.";
+        c->d_conv_w[i] = (int)c->dt.size();
+        add_tensor(c->dt, off, p + "weight", c->dch[i + 1], c->dch[i], 4, 4);
+        c->d_conv_b[i] = (int)c->dt.size();
+        add_tensor(c->dt, off, p + "bias", c->dch[i + 1]);
+    }
+    c->d_cls_w = (int)c->dt.size();
+    add_tensor(c->dt, off, "classifier.0.weight", 1, c->dch[c->ND] * 16);
+    c->d_cls_b = (int)c->dt.size();
+    add_tensor(c->dt, off, "classifier.0.bias", 1);
+    c->d_count = off;
+    // ---- weight packs
+    size_t pbytes = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t o = pbytes;
+        pbytes += align_up(bytes);
+        return o;
+    };
+    size_t o_fcW = reserve((size_t)F0 * c->Kp * 2), o_fcb = reserve((size_t)F0 * 4);
+    size_t o_gF[6], o_gB[6], o_dF[6], o_dB[6];
+    for (int i = 0; i < c->L; ++i) {
+        o_gF[i] = reserve((size_t)c->gch[i] * c->gch[i + 1] * 32);
+        o_gB[i] = reserve((size_t)c->gch[i] * c->gch[i + 1] * 32);
+    }
+    for (int i = 1; i < c->ND; ++i) {
+        o_dF[i] = reserve((size_t)c->dch[i] * c->dch[i + 1] * 32);
+        o_dB[i] = reserve((size_t)c->dch[i] * c->dch[i + 1] * 32);
+    }
+    size_t o_cls = reserve((size_t)c->dch[c->ND] * 16 * 4);
+    if (c->packs.ensure(pbytes) != 0) {
+        delete c;
+        return -1;
+    }
+    char* pb = static_cast<char*>(c->packs.p);
+    c->fc_Wp = reinterpret_cast<bf16*>(pb + o_fcW);
+    c->fc_biasp = reinterpret_cast<float*>(pb + o_fcb);
+    for (int i = 0; i < c->L; ++i) {
+        c->g_packF[i] = reinterpret_cast<bf16*>(pb + o_gF[i]);
+        c->g_packB[i] = reinterpret_cast<bf16*>(pb + o_gB[i]);
+    }
+    for (int i = 1; i < c->ND; ++i) {
+        c->d_packF[i] = reinterpret_cast<bf16*>(pb + o_dF[i]);
+        c->d_packB[i] = reinterpret_cast<bf16*>(pb + o_dB[i]);
+    }
+    c->cls_wp = reinterpret_cast<float*>(pb + o_cls);
+    *out = c;
+    return 0;
+}
+
+void sg_destroy(sg_ctx* c) {
+    if (!c) return;
+    DevBuf* bufs[] = {&c->packs, &c->bufA, &c->bufB, &c->dpre, &c->wpart, &c->cpart, &c->small,
+                      &c->g_ws,  &c->d_ws, &c->x2,   &c->masks2, &c->dximg, &c->gws_tmp};
+    for (DevBuf* b : bufs) b->release();
+    delete c;
+}
+
+int sg_num_tensors(const sg_ctx* c, int net) { return (int)(net == SG_NET_G ? c->gt.size() : c->dt.size()); }
+int sg_tensor_info(const sg_ctx* c, int net, int index, const char** name, long long* offset, int shape[4]) {
+    const std::vector<TensorInfo>& v = net == SG_NET_G ? c->gt : c->dt;
+    if (index < 0 || index >= (int)v.size()) return fail("sg_tensor_info: index %d out of range", index);
+    if (name) *name = v[index].name.c_str();
+    if (offset) *offset = v[index].offset;
+    if (shape) memcpy(shape, v[index].shape, sizeof(int) * 4);
+    return 0;
+}
+long long sg_param_count(const sg_ctx* c, int net) { return net == SG_NET_G ? c->g_count : c->d_count; }
+long long sg_g_stat_count(const sg_ctx* c) { return c->g_stats; }
+int sg_g_num_bn(const sg_ctx* c) { return c->L + 1; }
+int sg_g_bn_info(const sg_ctx* c, int index, long long* mean_offset, long long* var_offset, int* channels) {
+    if (index < 0 || index > c->L) return fail("sg_g_bn_info: index %d out of range", index);
+    *mean_offset = c->bn[index].mean_off;
+    *var_offset = c->bn[index].var_off;
+    *channels = c->bn[index].C;
+    return 0;
+}
+size_t sg_g_workspace_bytes(const sg_ctx* c, int batch) { return carve_g(c, nullptr, batch).bytes; }
+size_t sg_d_workspace_bytes(const sg_ctx* c, int batch) { return carve_d(c, nullptr, batch).bytes; }
+long long sg_d_mask_count(const sg_ctx* c, int batch) { return mask_offset(c, batch, c->ND); }
+long long sg_d_feature_count(const sg_ctx* c) { return (long long)c->dch[c->ND] * 16; }
+
+int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, int batch, int bn_batch_stats, void* ws,
+                 float* out_image, uint8_t* out_u8, void* stream) {
+    if (!c || !params || !stats || !z || batch < 1) return fail("sg_g_forward: bad argument");
+    if (!ws && !out_image && !out_u8) return fail("sg_g_forward: no output requested");
+    if (bn_batch_stats && batch < 2)
+        return fail("sg_g_forward: training-mode BatchNorm needs more than 1 value per channel (batch=%d)", batch);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    bool save = ws != nullptr;
+    if (!ws) {
+        SG_TRY(c->gws_tmp.ensure(sg_g_workspace_bytes(c, batch)));
+        ws = c->gws_tmp.p;
+        if (!out_image) {  // u8-only sampling still needs somewhere to put the fp32 image
+            SG_TRY(c->dximg.ensure((size_t)batch * c->S * c->S * 4));
+            out_image = static_cast<float*>(c->dximg.p);
+        }
+    }
+    return DISPATCH_T(c, g_forward_t, c, params, stats, z, batch, bn_batch_stats, ws, out_image, out_u8, save, s);
+}
+
+int sg_g_backward(sg_ctx* c, const float* params, const void* ws, const float* grad_image, int batch,
+                  int bn_batch_stats, float* grads_out, float* dz_out, void* stream) {
+    if (!c || !params || !ws || !grad_image || !grads_out || batch < 1) return fail("sg_g_backward: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    return DISPATCH_T(c, g_backward_t, c, params, ws, grad_image, batch, bn_batch_stats, grads_out, dz_out, s);
+}
+
+int sg_d_forward(sg_ctx* c, const float* params, const float* x, int batch, const float* masks, void* ws,
+                 float* prob_out, float* features_out, void* stream) {
+    if (!c || !params || !x || batch < 1) return fail("sg_d_forward: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    if (!ws) {
+        SG_TRY(c->d_ws.ensure(sg_d_workspace_bytes(c, batch)));
+        ws = c->d_ws.p;
+    }
+    return DISPATCH_T(c, d_forward_t, c, params, x, batch, masks, ws, prob_out, features_out, s);
+}
+
+int sg_d_backward(sg_ctx* c, const float* params, const float* x, const void* ws, const float* masks,
+                  const float* grad_prob, int batch, float* grads_out, float* dx_out, void* stream) {
+    if (!c || !params || !x || !ws || !grad_prob || batch < 1) return fail("sg_d_backward: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    DWs w = carve_d(c, const_cast<void*>(ws), batch);
+    sg::sigmoid_bwd(w.prob, grad_prob, c->dlogit, batch, s);
+    return DISPATCH_T(c, d_backward_t, c, params, x, ws, masks, c->dlogit, batch, grads_out, dx_out, s);
+}
+
+int sg_dropout_masks(sg_ctx* c, uint64_t seed, uint64_t offset, int batch, float p, float* masks_out, void* stream) {
+    if (!c || !masks_out || batch < 1 || !(p >= 0.f && p < 1.f)) return fail("sg_dropout_masks: bad argument");
+    sg::dropout_masks(seed, offset, sg_d_mask_count(c, batch), p, masks_out, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_dropout_masks");
+    return 0;
+}
+
+int sg_bce_forward(const float* prob, const float* target, int n, float* loss_out, void* stream) {
+    if (!prob || !target || !loss_out || n < 1) return fail("sg_bce_forward: bad argument");
+    sg::bce_forward(prob, target, n, loss_out, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_bce_forward");
+    return 0;
+}
+int sg_bce_backward(const float* prob, const float* target, int n, const float* grad_loss, float* dprob_out,
+                    void* stream) {
+    if (!prob || !target || !grad_loss || !dprob_out || n < 1) return fail("sg_bce_backward: bad argument");
+    sg::bce_backward(prob, target, n, grad_loss, dprob_out, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_bce_backward");
+    return 0;
+}
+
+int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                 float beta1, float beta2, float eps, long long step, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail("sg_adam_step: bad argument");
+    sg::adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_adam_step");
+    return 0;
+}
+
+int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
+                  int B, float* d_grads, float* g_grads, float* metrics, int phase, void* stream) {
+    if (!c || !st || !metrics || B < 2) return fail("sg_train_step: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, 2 * B));
+    const size_t img = (size_t)B * c->S * c->S;
+    SG_TRY(c->x2.ensure(2 * img * 4));
+    SG_TRY(c->d_ws.ensure(sg_d_workspace_bytes(c, 2 * B)));
+    SG_TRY(c->g_ws.ensure(sg_g_workspace_bytes(c, B)));
+    SG_TRY(c->gws_tmp.ensure(sg_g_workspace_bytes(c, B)));
+    SG_TRY(c->dximg.ensure(img * 4));
+    float* x2 = static_cast<float*>(c->x2.p);
+    const bool dropout = st->dropout_p > 0.f;
+    if (phase == 0 || phase == 1) {
+        if (!real || !noise_d || !d_grads) return fail("sg_train_step: D phase needs real, noise_d and d_grads");
+        // ---- D step (train…:281-337): D.train(), G.eval(); one 2B batch [real | G(noise)] since D has no batch coupling
+        cudaError_t e = cudaMemcpyAsync(x2, real, img * 4, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail("sg_train_step: copy of real batch failed: %s", cudaGetErrorString(e));
+        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, noise_d, B, 0, c->gws_tmp.p, x2 + img,
+                          nullptr, false, s));
+        const float* masks = nullptr;
+        if (dropout) {
+            SG_TRY(c->masks2.ensure((size_t)sg_d_mask_count(c, 2 * B) * 4));
+            float* m2 = static_cast<float*>(c->masks2.p);
+            if (st->masks_real && st->masks_fake) {
+                for (int i = 0; i < c->ND; ++i) {
+                    const size_t n = (size_t)B * c->dch[i + 1];
+                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i), st->masks_real + mask_offset(c, B, i), n * 4,
+                                    cudaMemcpyDeviceToDevice, s);
+                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i) + n, st->masks_fake + mask_offset(c, B, i), n * 4,
+                                    cudaMemcpyDeviceToDevice, s);
+                }
+            } else {
+                sg::dropout_masks(st->seed, st->offset, sg_d_mask_count(c, 2 * B), st->dropout_p, m2, s);
+            }
+            masks = m2;
+        }
+        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s));
+        DWs w = carve_d(c, c->d_ws.p, 2 * B);
+        sg::d_loss_metrics(w.prob, B, st->label_smoothing, metrics, c->dlogit, s);
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s));
+    }
+    if (phase == 0 || phase == 2) {
+        if (!d_grads) return fail("sg_train_step: D update needs d_grads");
+        PROF("adam.d", 0, 28.0 * c->d_count);
+        sg::adam_step(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->d_lr, st->beta1, st->beta2,
+                      st->eps, st->d_step + 1, s);
+    }
+    if (phase == 0 || phase == 3) {
+        if (!noise_g || !g_grads) return fail("sg_train_step: G phase needs noise_g and g_grads");
+        // ---- G step (train…:339-376): G.train() (batch-stat BN), D.eval() (no dropout), labels = 1
+        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, noise_g, B, 1, c->g_ws.p, x2, nullptr,
+                          true, s));
+        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, B, nullptr, c->d_ws.p, nullptr, nullptr, s));
+        DWs w = carve_d(c, c->d_ws.p, B);
+        sg::g_loss_metrics(w.prob, B, metrics, c->dlogit, s);
+        float* dximg = static_cast<float*>(c->dximg.p);
+        // weight gradients of D are not needed here (the reference's autograd computes and discards them)
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, nullptr, c->dlogit, B, nullptr, dximg, s));
+        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, dximg, B, 1, g_grads, nullptr, s));
+    }
+    if (phase == 0 || phase == 4) {
+        if (!g_grads) return fail("sg_train_step: G update needs g_grads");
+        PROF("adam.g", 0, 28.0 * c->g_count);
+        sg::adam_step(st->g_params, g_grads, st->g_exp_avg, st->g_exp_avg_sq, c->g_count, st->g_lr, st->beta1, st->beta2,
+                      st->eps, st->g_step + 1, s);
+    }
+    SG_KCHECK("sg_train_step");
+    return 0;
+}
+
+}  // extern "C"
