@@ -275,18 +275,26 @@ class FlatParams:
         for p, v in zip(self.params, cache[1]):
             p.grad = v
 
+    def fresh_grad(self) -> torch.Tensor:
+        """A new flat gradient buffer for one autograd backward call. Autograd may keep (steal) views of it as
+        `.grad`, or hold them in its input buffers while a second backward of the same network runs, so a buffer
+        handed to autograd is never reused."""
+        return torch.empty_like(self.flat)
+
     def flat_grad_if_contiguous(self) -> Optional[torch.Tensor]:
-        """If every p.grad is the matching view of one staging buffer, return that buffer (zero-copy)."""
+        """If every p.grad is the matching view of ONE flat buffer (what our backward hands to autograd), return a
+        flat view over it (zero-copy); otherwise None."""
         g0 = self.params[0].grad
-        if g0 is None:
+        if g0 is None or g0.dtype != torch.float32 or g0.device != self.flat.device:
             return None
-        for buf in self._gbuf:
-            if buf is None:
-                continue
-            base = buf.data_ptr()
-            if g0.data_ptr() != base + 4 * self.layout[0][0]:
-                continue
-            if all(p.grad is not None and p.grad.data_ptr() == base + 4 * off and p.grad.is_contiguous()
-                   for p, (off, _, _) in zip(self.params, self.layout)):
-                return buf
-        return None
+        total = self.flat.numel()
+        base_off = g0.storage_offset() - self.layout[0][0]
+        storage = g0.untyped_storage()
+        if base_off < 0 or storage.nbytes() < 4 * (base_off + total):
+            return None
+        base_ptr = storage.data_ptr() + 4 * base_off
+        for p, (off, _, _) in zip(self.params, self.layout):
+            g = p.grad
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != base_ptr + 4 * off:
+                return None
+        return g0.as_strided((total,), (1,), base_off)

@@ -59,6 +59,35 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// All spatial sizes / channel counts on this path are powers of two: index math uses shifts and masks
+// (64-bit div/mod per element was the dominant cost of the first version of these kernels).
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
+
+// Raw 8-element loads (no conversion) used to issue a whole neighbourhood of loads back to back.
+struct Raw8f { float4 a, b; };
+__device__ __forceinline__ Raw8f ldraw8(const float* p) {
+    Raw8f r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+}
+__device__ __forceinline__ uint4 ldraw8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const Raw8f& r, float (&f)[8]) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+    f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+template <typename T> struct RawOf;
+template <> struct RawOf<float> { using type = Raw8f; };
+template <> struct RawOf<bf16> { using type = uint4; };
+
 static inline int blocks_for(long n, int threads, int cap = 148 * 16) {
     long b = (n + threads - 1) / threads;
     if (b > cap) b = cap;
@@ -280,7 +309,7 @@ __global__ void bn_apply_relu_kernel(const T* __restrict__ y, const float* __res
                                      const float* __restrict__ shift, T* __restrict__ a, long n8, int C) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>((i * 8) % C);
+        const int c0 = static_cast<int>((i * 8) & (C - 1));
         float v[8];
         load8(y + i * 8, v);
 #pragma unroll
@@ -331,7 +360,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ d, const T* __restrict
                                     long n8, int C) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>((i * 8) % C);
+        const int c0 = static_cast<int>((i * 8) & (C - 1));
         float dv[8], yv[8];
         load8(d + i * 8, dv);
         load8(y + i * 8, yv);
@@ -377,53 +406,74 @@ void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* o
 // ------------------------------------------------------------------------------------------------
 // Generator tail: Conv3x3 (C -> 1) + tanh, and its backward
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// All three kernels give each pixel to C/8 adjacent lanes (one 8-channel slice each) and keep that slice's
+// 9x8 filter taps (or 9x8 gradient accumulators) in registers, so the inner loops are 16-byte activation
+// loads + FMAs with no shared-memory traffic. A warp covers 32/(C/8) consecutive pixels.
+template <typename T, int C>
 __global__ void __launch_bounds__(256)
 final_conv_tanh_kernel(const T* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
-                       float* __restrict__ out, uint8_t* __restrict__ out_u8, int B, int S, int C) {
-    extern __shared__ float wsm[];  // [C*9]
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) wsm[i] = w[i];
-    __syncthreads();
-    const long total = static_cast<long>(B) * S * S;
+                       float* __restrict__ out, uint8_t* __restrict__ out_u8, int B, int S) {
+    constexpr int G = C / 8;
+    const int g = threadIdx.x % G;
+    float wr[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
     const float b0 = bias[0];
-    for (long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; pix < total;
-         pix += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(pix % S);
-        const int yy = static_cast<int>((pix / S) % S);
-        const long n = pix / (static_cast<long>(S) * S);
-        float acc = b0;
+    const long total = static_cast<long>(B) * S * S;   // multiple of 32/G, so whole warps stay in the loop together
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
+    const int sh = ilog2(S);
+    for (long pix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; pix < total; pix += stride) {
+        const int x = static_cast<int>(pix) & (S - 1);
+        const int yy = static_cast<int>(pix >> sh) & (S - 1);
+        float acc = 0.f;
+        typename RawOf<T>::type raw[9];
+        bool ok[9];
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = yy + ky - 1;
-            if (iy < 0 || iy >= S) continue;
+            const int cy = min(max(iy, 0), S - 1);
+#pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = x + kx - 1;
-                if (ix < 0 || ix >= S) continue;
-                const T* p = a + ((n * S + iy) * S + ix) * C;
-                const int tap = ky * 3 + kx;
-                for (int c8 = 0; c8 < C; c8 += 8) {
-                    float v[8];
-                    load8(p + c8, v);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wsm[(c8 + j) * 9 + tap], acc);
-                }
+                const int cx = min(max(ix, 0), S - 1);
+                ok[ky * 3 + kx] = (iy == cy) && (ix == cx);
+                raw[ky * 3 + kx] = ldraw8(a + (pix + static_cast<long>(cy - yy) * S + (cx - x)) * C + g * 8);
             }
         }
-        const float t = tanhf(acc);
-        out[pix] = t;
-        if (out_u8) {
-            float q = (t + 1.f) * 127.5f;
-            q = fminf(fmaxf(q, 0.f), 255.f);
-            out_u8[pix] = static_cast<uint8_t>(q);  // numpy astype(uint8) truncates (utils/inference.py:129)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float v[8];
+            unpack8(raw[t], v);
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part = fmaf(v[j], wr[t][j], part);
+            acc += ok[t] ? part : 0.f;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0) {
+            const float t = tanhf(acc + b0);
+            out[pix] = t;
+            if (out_u8) {
+                float q = (t + 1.f) * 127.5f;
+                q = fminf(fmaxf(q, 0.f), 255.f);
+                out_u8[pix] = static_cast<uint8_t>(q);  // numpy astype(uint8) truncates (utils/inference.py:129)
+            }
         }
     }
 }
 template <typename T>
 void final_conv_tanh(const T* a, const float* w, const float* bias, float* out, uint8_t* out_u8, int B, int S, int C,
                      cudaStream_t s) {
-    const long total = static_cast<long>(B) * S * S;
+    if (C != 32) {
+        snprintf(k_err, sizeof(k_err), "final_conv_tanh: C=%d unsupported (reference uses 32)", C);
+        return;
+    }
+    const long threads = static_cast<long>(B) * S * S * (C / 8);
     note_launch();
-    final_conv_tanh_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, C * 9 * sizeof(float), s>>>(a, w, bias, out,
-                                                                                                  out_u8, B, S, C);
+    final_conv_tanh_kernel<T, 32><<<blocks_for(threads, 256, 148 * 8), 256, 0, s>>>(a, w, bias, out, out_u8, B, S);
 }
 template void final_conv_tanh<float>(const float*, const float*, const float*, float*, uint8_t*, int, int, int,
                                      cudaStream_t);
@@ -440,71 +490,118 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dout, const float* __r
 }
 
 // dbn[n,y,x,c] = [a>0] * sum_{ky,kx} dpre[n, y+1-ky, x+1-kx] * w[c][ky][kx]
-template <typename T>
+template <typename T, int C>
 __global__ void __launch_bounds__(256)
 final_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, const T* __restrict__ a,
-                   T* __restrict__ dbn, int B, int S, int C) {
-    extern __shared__ float wsm[];  // [9][C]
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) wsm[(i % 9) * C + i / 9] = w[i];
-    __syncthreads();
-    const int g = C / 8;
-    const long total = static_cast<long>(B) * S * S * g;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % g) * 8;
-        const long pix = i / g;
-        const int x = static_cast<int>(pix % S);
-        const int yy = static_cast<int>((pix / S) % S);
-        const long n = pix / (static_cast<long>(S) * S);
+                   T* __restrict__ dbn, int B, int S) {
+    constexpr int G = C / 8;
+    const int g = threadIdx.x % G;
+    float wr[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
+    const long total = static_cast<long>(B) * S * S;
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
+    const int sh = ilog2(S);
+    for (long pix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; pix < total; pix += stride) {
+        const int x = static_cast<int>(pix) & (S - 1);
+        const int yy = static_cast<int>(pix >> sh) & (S - 1);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const typename RawOf<T>::type araw = ldraw8(a + pix * C + g * 8);
+        float dv[9];
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int sy = yy + 1 - ky;
-            if (sy < 0 || sy >= S) continue;
+            const int cy = min(max(sy, 0), S - 1);
+#pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int sx = x + 1 - kx;
-                if (sx < 0 || sx >= S) continue;
-                const float d = dpre[(n * S + sy) * S + sx];
-                const float* ww = wsm + (ky * 3 + kx) * C + c0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, ww[j], acc[j]);
+                const int cx = min(max(sx, 0), S - 1);
+                const float d = __ldg(dpre + pix + static_cast<long>(cy - yy) * S + (cx - x));
+                dv[ky * 3 + kx] = (sy == cy && sx == cx) ? d : 0.f;
             }
         }
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[t], wr[t][j], acc[j]);
         float av[8];
-        load8(a + pix * C + c0, av);
+        unpack8(araw, av);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = av[j] > 0.f ? acc[j] : 0.f;
-        store8(dbn + pix * C + c0, acc);
+        store8(dbn + pix * C + g * 8, acc);
     }
 }
 
-// partial[chunk][C*9 + 1]: thread (tap, c) accumulates sum dpre[pix] * a[pix + tap offset][c]; slot C*9 = sum dpre
-template <typename T>
-__global__ void final_wgrad_kernel(const float* __restrict__ dpre, const T* __restrict__ a, float* __restrict__ partial,
-                                   int B, int S, int C, long pix_per_chunk) {
-    const int c = threadIdx.x % C;
-    const int tap = threadIdx.x / C;  // blockDim = 9*C
-    const int ky = tap / 3, kx = tap % 3;
+// dW[c][ky][kx] = sum_pix dpre[pix] * a[pix + (ky-1, kx-1)][c]; written as a scatter from each activation pixel q:
+// acc[tap][c] += a[q][c] * dpre[q - (ky-1, kx-1)]. partial[block][C*9 + 1] (last slot: sum of dpre = dbias).
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+final_wgrad_kernel(const float* __restrict__ dpre, const T* __restrict__ a, float* __restrict__ partial, int B, int S) {
+    constexpr int G = C / 8;
+    __shared__ float sm[8][C * 9 + 1];
+    const int g = threadIdx.x % G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+    float dsum = 0.f;
     const long total = static_cast<long>(B) * S * S;
-    const long p0 = blockIdx.x * pix_per_chunk;
-    long p1 = p0 + pix_per_chunk;
-    if (p1 > total) p1 = total;
-    float acc = 0.f, dsum = 0.f;
-    for (long pix = p0; pix < p1; ++pix) {
-        const float d = dpre[pix];
-        const int x = static_cast<int>(pix % S);
-        const int yy = static_cast<int>((pix / S) % S);
-        const int iy = yy + ky - 1, ix = x + kx - 1;
-        dsum += d;
-        if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
-            const long q = pix + static_cast<long>(ky - 1) * S + (kx - 1);
-            acc = fmaf(d, to_f(a[q * C + c]), acc);
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
+    const int sh = ilog2(S);
+    for (long q = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; q < total; q += stride) {
+        const int x = static_cast<int>(q) & (S - 1);
+        const int yy = static_cast<int>(q >> sh) & (S - 1);
+        const typename RawOf<T>::type araw = ldraw8(a + q * C + g * 8);
+        float dv[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int py = yy - (ky - 1);
+            const int cy = min(max(py, 0), S - 1);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int px = x - (kx - 1);
+                const int cx = min(max(px, 0), S - 1);
+                const float d = __ldg(dpre + q + static_cast<long>(cy - yy) * S + (cx - x));
+                dv[ky * 3 + kx] = (py == cy && px == cx) ? d : 0.f;
+            }
         }
+        float v[8];
+        unpack8(araw, v);
+        if (g == 0) dsum += dv[4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(dv[t], v[j], acc[t][j]);
     }
-    float* out = partial + static_cast<long>(blockIdx.x) * (C * 9 + 1);
-    out[c * 9 + tap] = acc;
-    if (threadIdx.x == 0) out[C * 9] = dsum;
+    // lanes with equal g hold partial sums of the same outputs: fold them (xor over the pixel bits of the lane id)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], o);
+#pragma unroll
+    for (int o = 16; o >= G; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane < G) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm[warp][(g * 8 + j) * 9 + t] = acc[t][j];
+        if (g == 0) sm[warp][C * 9] = dsum;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += sm[wv][i];
+        partial[static_cast<long>(blockIdx.x) * (C * 9 + 1) + i] = s;
+    }
 }
 __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunks, int n, float* __restrict__ out_a,
                                     int na, float* __restrict__ out_b) {
@@ -521,21 +618,18 @@ __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunk
 template <typename T>
 void final_conv_bwd(const float* dout, const float* out, const T* a, const float* w, float* dpre, T* dbn, float* dW,
                     float* dbias, float* partial, int B, int S, int C, cudaStream_t s) {
+    if (C != 32) {
+        snprintf(k_err, sizeof(k_err), "final_conv_bwd: C=%d unsupported (reference uses 32)", C);
+        return;
+    }
     const long total = static_cast<long>(B) * S * S;
-    note_launch();
+    note_launch(4);
     tanh_bwd_kernel<<<blocks_for(total, 256), 256, 0, s>>>(dout, out, dpre, total);
-    note_launch();
-    final_dgrad_kernel<T><<<blocks_for(total * (C / 8), 256, 148 * 32), 256, C * 9 * sizeof(float), s>>>(dpre, w, a, dbn,
-                                                                                                        B, S, C);
-    long chunks = (total + 1023) / 1024;
-    if (chunks > kMaxChunks) chunks = kMaxChunks;
-    const long ppc = (total + chunks - 1) / chunks;
-    chunks = (total + ppc - 1) / ppc;
-    note_launch();
-    final_wgrad_kernel<T><<<static_cast<unsigned>(chunks), 9 * C, 0, s>>>(dpre, a, partial, B, S, C, ppc);
+    final_dgrad_kernel<T, 32><<<blocks_for(total * 4, 256, 148 * 8), 256, 0, s>>>(dpre, w, a, dbn, B, S);
+    const int chunks = blocks_for(total * 4, 256, kMaxChunks);
+    final_wgrad_kernel<T, 32><<<chunks, 256, 0, s>>>(dpre, a, partial, B, S);
     const int n = C * 9 + 1;
-    note_launch();
-    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, static_cast<int>(chunks), n, dW, C * 9, dbias);
+    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, dW, C * 9, dbias);
 }
 template void final_conv_bwd<float>(const float*, const float*, const float*, const float*, float*, float*, float*,
                                     float*, float*, int, int, int, cudaStream_t);
@@ -545,6 +639,8 @@ template void final_conv_bwd<bf16>(const float*, const float*, const bf16*, cons
 // ------------------------------------------------------------------------------------------------
 // Discriminator head: Conv 4x4 s2 p1 from the 1-channel image, forward / wgrad / dgrad
 // ------------------------------------------------------------------------------------------------
+// Forward: a thread computes 4 consecutive output pixels x 8 channels from a 4x10 window of the image held in
+// registers; the 16x8 filter slice is read from shared memory once per 4 pixels (1 LDS.128 per 16 FMAs).
 template <typename T>
 __global__ void __launch_bounds__(256)
 d_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
@@ -553,47 +649,68 @@ d_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i % 16) * C + i / 16] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[16 * C + i] = bias[i];
     __syncthreads();
-    const int O = S / 2, g = C / 8;
-    const long total = static_cast<long>(B) * O * O * g;
+    const int O = S / 2, g = C / 8, Q = O / 4;  // Q pixel-quads per output row
+    const int lg = ilog2(g), lq = ilog2(Q), lo = ilog2(O);
+    const long total = static_cast<long>(B) * O * Q * g;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % g) * 8;
-        const long pix = i / g;
-        const int ox = static_cast<int>(pix % O);
-        const int oy = static_cast<int>((pix / O) % O);
-        const long n = pix / (static_cast<long>(O) * O);
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = wsm[16 * C + c0 + j];
+        const int c0 = (static_cast<int>(i) & (g - 1)) * 8;
+        const long quad = i >> lg;
+        const int ox0 = (static_cast<int>(quad) & (Q - 1)) * 4;
+        const int oy = static_cast<int>(quad >> lq) & (O - 1);
+        const long n = quad >> (lq + lo);
+        float xv[4][10];
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky) {
             const int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy >= S) continue;
+            const bool yok = iy >= 0 && iy < S;
+            const float* row = x + (n * S + (yok ? iy : 0)) * S;
 #pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-                const int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix >= S) continue;
-                const float xv = __ldg(x + (n * S + iy) * S + ix);
-                const float* ww = wsm + (ky * 4 + kx) * C + c0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ww[j], acc[j]);
+            for (int k = 0; k < 10; ++k) {
+                const int ix = 2 * ox0 - 1 + k;
+                xv[ky][k] = (yok && ix >= 0 && ix < S) ? __ldg(row + ix) : 0.f;
             }
         }
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float v = acc[j] > 0.f ? acc[j] : acc[j] * slope;
-            if (mask) v *= mask[n * C + c0 + j];
-            acc[j] = v;
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = wsm[16 * C + c0 + j];
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 4 + kx) * C + c0);
+                const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 4 + kx) * C + c0 + 4);
+                const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float xvv = xv[ky][2 * p + kx];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xvv, ww[j], acc[p][j]);
+                }
+            }
+        float mk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mk[j] = mask ? mask[n * C + c0 + j] : 1.f;
+        const long pix0 = (n * O + oy) * O + ox0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = acc[p][j] > 0.f ? acc[p][j] : acc[p][j] * slope;
+                acc[p][j] = v * mk[j];
+            }
+            store8(a + (pix0 + p) * C + c0, acc[p]);
         }
-        store8(a + pix * C + c0, acc);
     }
 }
 template <typename T>
 void d_conv0(const float* x, const float* w, const float* bias, const float* mask, float slope, T* a, int B, int S,
              int C, cudaStream_t s) {
-    const long total = static_cast<long>(B) * (S / 2) * (S / 2) * (C / 8);
+    const long total = static_cast<long>(B) * (S / 2) * (S / 8) * (C / 8);
     note_launch();
-    d_conv0_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, 17 * C * sizeof(float), s>>>(x, w, bias, mask, slope, a,
+    d_conv0_kernel<T><<<blocks_for(total, 256, 148 * 16), 256, 17 * C * sizeof(float), s>>>(x, w, bias, mask, slope, a,
                                                                                            B, S, C);
 }
 template void d_conv0<float>(const float*, const float*, const float*, const float*, float, float*, int, int, int,
@@ -601,97 +718,184 @@ template void d_conv0<float>(const float*, const float*, const float*, const flo
 template void d_conv0<bf16>(const float*, const float*, const float*, const float*, float, bf16*, int, int, int,
                             cudaStream_t);
 
-// partial[chunk][C*16 + C]: dW[c][ky][kx] and dbias[c]. blockDim = 4*C: thread (ky = t / C, c = t % C) keeps 4 kx taps.
+// Weight gradient: 16 lanes per output pixel = 8 channel slices x 2 filter-row halves; each lane keeps its
+// 8 channels x (2 ky x 4 kx) accumulators (+ the bias gradient) in registers while striding over pixels.
+// partial[block][C*16 + C] with C == 64.
 template <typename T>
-__global__ void d_conv0_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ partial,
-                                     int B, int S, int C, long pix_per_chunk) {
-    const int c = threadIdx.x % C;
-    const int ky = threadIdx.x / C;
+__global__ void __launch_bounds__(256)
+d_conv0_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ partial, int B, int S) {
+    constexpr int C = 64;
+    __shared__ float sm[8][C * 17];
+    const int sub = threadIdx.x & 15;
+    const int c0 = (sub & 7) * 8, half = sub >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int O = S / 2;
-    const long total = static_cast<long>(B) * O * O;
-    const long p0 = blockIdx.x * pix_per_chunk;
-    long p1 = p0 + pix_per_chunk;
-    if (p1 > total) p1 = total;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
-    for (long pix = p0; pix < p1; ++pix) {
-        const int ox = static_cast<int>(pix % O);
-        const int oy = static_cast<int>((pix / O) % O);
-        const long n = pix / (static_cast<long>(O) * O);
-        const float d = to_f(dy[pix * C + c]);
-        bsum += d;
-        const int iy = 2 * oy - 1 + ky;
-        if (iy < 0 || iy >= S) continue;
-        const float* row = x + (n * S + iy) * S;
+    float acc[2][4][8], bacc[8];
 #pragma unroll
-        for (int kx = 0; kx < 4; ++kx) {
-            const int ix = 2 * ox - 1 + kx;
-            if (ix >= 0 && ix < S) acc[kx] = fmaf(d, __ldg(row + ix), acc[kx]);
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][k][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+    const long total = static_cast<long>(B) * O * O;  // multiple of 2: both pixel slots of a warp stay in the loop
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x / 16;
+    const int lo = ilog2(O);
+    for (long pix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / 16; pix < total; pix += stride) {
+        const int ox = static_cast<int>(pix) & (O - 1);
+        const int oy = static_cast<int>(pix >> lo) & (O - 1);
+        const long n = pix >> (2 * lo);
+        const typename RawOf<T>::type draw = ldraw8(dy + pix * C + c0);
+        float xv[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int iy = 2 * oy - 1 + half * 2 + r;
+            const int cy = min(max(iy, 0), S - 1);
+            const float* row = x + (n * S + cy) * S;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                const int cx = min(max(ix, 0), S - 1);
+                const float v = __ldg(row + cx);
+                xv[r][kx] = (iy == cy && ix == cx) ? v : 0.f;
+            }
+        }
+        float d[8];
+        unpack8(draw, d);
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bacc[j] += d[j];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[r][kx][j] = fmaf(d[j], xv[r][kx], acc[r][kx][j]);
+    }
+    // the two pixel slots of a warp (lane and lane^16) hold the same outputs
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][k][j] += __shfl_xor_sync(0xffffffffu, acc[r][k][j], 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bacc[j] += __shfl_xor_sync(0xffffffffu, bacc[j], 16);
+    if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sm[warp][(c0 + j) * 16 + (half * 2 + r) * 4 + k] = acc[r][k][j];
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm[warp][C * 16 + c0 + j] = bacc[j];
         }
     }
-    float* out = partial + static_cast<long>(blockIdx.x) * (C * 17);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 17; i += blockDim.x) {
+        float s = 0.f;
 #pragma unroll
-    for (int kx = 0; kx < 4; ++kx) out[c * 16 + ky * 4 + kx] = acc[kx];
-    if (ky == 0) out[C * 16 + c] = bsum;
+        for (int wv = 0; wv < 8; ++wv) s += sm[wv][i];
+        partial[static_cast<long>(blockIdx.x) * (C * 17) + i] = s;
+    }
 }
 template <typename T>
 void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s) {
+    if (C != 64) {
+        snprintf(k_err, sizeof(k_err), "d_conv0_wgrad: C=%d unsupported (reference uses 64)", C);
+        return;
+    }
     const long total = static_cast<long>(B) * (S / 2) * (S / 2);
-    long chunks = (total + 255) / 256;
-    if (chunks > kMaxChunks) chunks = kMaxChunks;
-    const long ppc = (total + chunks - 1) / chunks;
-    chunks = (total + ppc - 1) / ppc;
-    note_launch();
-    d_conv0_wgrad_kernel<T><<<static_cast<unsigned>(chunks), 4 * C, 0, s>>>(x, dy, partial, B, S, C, ppc);
+    const int chunks = blocks_for(total * 16, 256, kMaxChunks);
+    note_launch(2);
+    d_conv0_wgrad_kernel<T><<<chunks, 256, 0, s>>>(x, dy, partial, B, S);
     const int n = C * 17;
     // dW (C*16 floats) is immediately followed by dbias (C floats) in the flat gradient buffer
-    note_launch();
-    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, static_cast<int>(chunks), n, dW, n, nullptr);
+    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, dW, n, nullptr);
 }
 template void d_conv0_wgrad<float>(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 template void d_conv0_wgrad<bf16>(const float*, const bf16*, float*, float*, int, int, int, cudaStream_t);
 
-// dx[n,iy,ix] = sum over (oy,ky): 2oy-1+ky = iy, same for x, and channels: dy[n,oy,ox,c] * w[c][ky][kx]
+// Image gradient: dx[n,iy,ix] = sum over the 2x2 output pixels that see (iy,ix) and all channels of
+// dy[n,oy,ox,c] * w[c][ky][kx]. blockIdx.y selects the (iy&1, ix&1) parity class so every thread of a block uses
+// the same 4 filter taps; 4 lanes per pixel hold 16 channels x 4 taps of weights in registers.
 template <typename T>
 __global__ void __launch_bounds__(256)
-d_conv0_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S,
-                     int C) {
-    extern __shared__ float wsm[];  // [16][C]
-    for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i % 16) * C + i / 16] = w[i];
-    __syncthreads();
+d_conv0_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S) {
+    constexpr int C = 64;
+    const int py = blockIdx.y >> 1, px = blockIdx.y & 1;
+    const int q = threadIdx.x & 3;
     const int O = S / 2;
-    const long total = static_cast<long>(B) * S * S;
-    for (long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; pix < total;
-         pix += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int ix = static_cast<int>(pix % S);
-        const int iy = static_cast<int>((pix / S) % S);
-        const long n = pix / (static_cast<long>(S) * S);
-        float acc = 0.f;
-        for (int ty = 0; ty < 2; ++ty) {
-            const int ky = ((iy + 1) & 1) + 2 * ty;
-            const int oy = (iy + 1 - ky) >> 1;
-            if (oy < 0 || oy >= O || (iy + 1 - ky) < 0) continue;
-            for (int tx = 0; tx < 2; ++tx) {
-                const int kx = ((ix + 1) & 1) + 2 * tx;
-                const int ox = (ix + 1 - kx) >> 1;
-                if (ox < 0 || ox >= O || (ix + 1 - kx) < 0) continue;
-                const T* p = dy + ((n * O + oy) * O + ox) * C;
-                const float* ww = wsm + (ky * 4 + kx) * C;
-                for (int c8 = 0; c8 < C; c8 += 8) {
-                    float v[8];
-                    load8(p + c8, v);
+    float wr[2][2][16];
+    int kyv[2], kxv[2];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], ww[c8 + j], acc);
-                }
+    for (int t = 0; t < 2; ++t) {
+        kyv[t] = ((py + 1) & 1) + 2 * t;
+        kxv[t] = ((px + 1) & 1) + 2 * t;
+    }
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) wr[ty][tx][j] = w[(q * 16 + j) * 16 + kyv[ty] * 4 + kxv[tx]];
+    const long total = static_cast<long>(B) * O * O;  // pixels of this parity class
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x / 4;
+    const int lo = ilog2(O);
+    for (long i = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / 4; i < total; i += stride) {
+        const int xh = static_cast<int>(i) & (O - 1);
+        const int yh = static_cast<int>(i >> lo) & (O - 1);
+        const long n = i >> (2 * lo);
+        const int iy = 2 * yh + py, ix = 2 * xh + px;
+        float acc = 0.f;
+        typename RawOf<T>::type raw[2][2][2];
+        bool ok[2][2];
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty) {
+            const int oy = (iy + 1 - kyv[ty]) >> 1;   // arithmetic shift: -1 for the out-of-range row above the image
+            const int cy = min(max(oy, 0), O - 1);
+#pragma unroll
+            for (int tx = 0; tx < 2; ++tx) {
+                const int ox = (ix + 1 - kxv[tx]) >> 1;
+                const int cx = min(max(ox, 0), O - 1);
+                ok[ty][tx] = (oy == cy) && (ox == cx);
+                const T* p = dy + ((n * O + cy) * O + cx) * C + q * 16;
+                raw[ty][tx][0] = ldraw8(p);
+                raw[ty][tx][1] = ldraw8(p + 8);
             }
         }
-        dx[pix] = acc;
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 2; ++tx) {
+                float v[8], part = 0.f;
+                unpack8(raw[ty][tx][0], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part = fmaf(v[j], wr[ty][tx][j], part);
+                unpack8(raw[ty][tx][1], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part = fmaf(v[j], wr[ty][tx][8 + j], part);
+                acc += ok[ty][tx] ? part : 0.f;
+            }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (q == 0) dx[(n * S + iy) * S + ix] = acc;
     }
 }
 template <typename T>
 void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s) {
-    const long total = static_cast<long>(B) * S * S;
+    if (C != 64) {
+        snprintf(k_err, sizeof(k_err), "d_conv0_dgrad: C=%d unsupported (reference uses 64)", C);
+        return;
+    }
+    const long threads = static_cast<long>(B) * (S / 2) * (S / 2) * 4;
+    dim3 grid(blocks_for(threads, 256, 148 * 4), 4);
     note_launch();
-    d_conv0_dgrad_kernel<T><<<blocks_for(total, 256, 148 * 32), 256, 16 * C * sizeof(float), s>>>(dy, w, dx, B, S, C);
+    d_conv0_dgrad_kernel<T><<<grid, 256, 0, s>>>(dy, w, dx, B, S);
 }
 template void d_conv0_dgrad<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
 template void d_conv0_dgrad<bf16>(const bf16*, const float*, float*, int, int, int, cudaStream_t);
@@ -770,9 +974,9 @@ __global__ void classifier_bwd_dy_kernel(const float* __restrict__ dlogit, const
     const long n8 = static_cast<long>(B) * F / 8;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int j0 = static_cast<int>((i * 8) % F);
-        const long b = (i * 8) / F;
-        const int c0 = j0 % C;
+        const int j0 = static_cast<int>((i * 8) & (F - 1));
+        const long b = (i * 8) >> ilog2(F);
+        const int c0 = j0 & (C - 1);
         const float dl = dlogit[b];
         float av[8], w[8];
         load8(a + i * 8, av);

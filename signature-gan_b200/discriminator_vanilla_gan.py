@@ -65,7 +65,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             raise RuntimeError("Discriminator backward without saved activations")
         grad_prob = grad_prob.contiguous().float()
         dev = grad_prob.device
-        gflat = fp.grad_staging() if ctx.w_needs_grad else None
+        gflat = fp.fresh_grad() if ctx.w_needs_grad else None
         dx = torch.empty_like(ctx.x) if ctx.x_needs_grad else None
         L.check(sctx.lib.sg_d_backward(sctx.handle, L.ptr(fp.flat), L.ptr(ctx.x), L.ptr(ctx.ws), L.ptr(ctx.masks),
                                        L.ptr(grad_prob), ctx.B, L.ptr(gflat), L.ptr(dx), L.current_stream(dev)),

@@ -60,7 +60,7 @@ class _GeneratorFn(torch.autograd.Function):
         if ctx.ws is None:
             raise RuntimeError("Generator backward without saved activations")
         grad_out = grad_out.contiguous().float()
-        gflat = fp.grad_staging()
+        gflat = fp.fresh_grad()
         dz = torch.empty(ctx.B, gen.latent_dim, dtype=torch.float32, device=grad_out.device) if ctx.z_needs_grad else None
         L.check(sctx.lib.sg_g_backward(sctx.handle, L.ptr(fp.flat), L.ptr(ctx.ws), L.ptr(grad_out), ctx.B, ctx.train,
                                        L.ptr(gflat), L.ptr(dz), L.current_stream(grad_out.device)), "sg_g_backward")
