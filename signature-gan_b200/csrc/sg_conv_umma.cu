@@ -84,19 +84,33 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 }
 
 // ----------------------------------------------------------------------------
-// Forward / dgrad implicit GEMM
+// Forward / dgrad implicit GEMM — persistent, warp-specialised
+//
+// One CTA per SM loops over 128 x BN output tiles (static round-robin schedule). Three pipelines:
+//   smem ring   : TMA producer (warp 0)  -> full/empty mbarriers  -> MMA issuer (warp 1)
+//   TMEM ring   : two BN-column accumulators; MMA issuer -> tfull/tempty mbarriers -> epilogue warps
+//   tile loop   : every role walks the same tile sequence, so no scheduler traffic is needed
+// The epilogue of tile j therefore overlaps the main loop of tile j+1, and the ~2.7k-cycle CTA prologue
+// (barrier init, TMEM allocation, descriptor prefetch) is paid once per launch instead of once per tile.
+// Tile order: the tiles that read the same A rows (other output-channel tiles, other ConvT phases) are
+// adjacent in the schedule so that they run at the same time on neighbouring SMs and share A through L2.
 // ----------------------------------------------------------------------------
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN, int BK>
 struct ConvCfg {
     static constexpr int kABytes = kTileM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // Keep two CTAs per SM resident when the tile allows it so one CTA's epilogue overlaps another's mainloop.
-    static constexpr int kStages = (BN == 256) ? 4 : (kStageBytes >= 32768 ? 3 : 4);
-    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    // Thin tiles (BN <= 64) are epilogue/latency-bound rather than MMA-bound: run two persistent CTAs per SM.
+    static constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;
+    static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 98 : 196) * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;          // double-buffered accumulator
+    static constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
+    static constexpr int kActiveEpiWarps = BN >= 64 ? 8 : 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
     static constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of one swizzle atom
@@ -109,27 +123,54 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 32 floats of a per-column vector (uniform across the warp): 8 broadcast 128-bit loads.
+__device__ __forceinline__ void load_vec32(const float* p, float (&v)[32]) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(q + j);
+        v[4 * j] = t.x;
+        v[4 * j + 1] = t.y;
+        v[4 * j + 2] = t.z;
+        v[4 * j + 3] = t.w;
+    }
+}
+
+struct TileCoord {
+    int tile_m, tile_n, phase;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int phases) {
+    TileCoord c;
+    c.tile_n = t % n_tiles;
+    const int r = t / n_tiles;
+    c.phase = r % phases;
+    c.tile_m = r / phases;
+    return c;
+}
+
 template <int BN, int BK>
-__global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
+__global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     using Cfg = ConvCfg<BN, BK>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready for the epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained, MMA may overwrite
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x;
-    const int tile_n = blockIdx.y;
-    const int phase = blockIdx.z;
     const int mode = args.mode;
     const int cc_n = args.Cin / BK;
     const int taps = (mode == kConvS2) ? 16 : (mode == kConvT ? 4 : 1);
+    const int phases = (mode == kConvT) ? 4 : 1;
     const int num_k = taps * cc_n;
     const int R = args.GH * args.GW;
+    const int n_tiles = args.N_total / BN;
+    const int m_tiles = (args.M_total + kTileM - 1) / kTileM;
+    const int total_tiles = m_tiles * n_tiles * phases;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.amap[0]);
@@ -138,7 +179,10 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], Cfg::kActiveEpiWarps);
+        }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -150,40 +194,45 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
-            int n0 = 0, y0 = 0;
-            if (mode != kPlain) {
-                if (R >= kTileM) {
-                    const int tpi = R / kTileM;
-                    n0 = tile_m / tpi;
-                    y0 = (tile_m % tpi) * (kTileM / args.GW);
-                } else {
-                    n0 = tile_m * (kTileM / R);
-                }
-            }
-            const int py = phase >> 1, px = phase & 1;
-            for (int it = 0; it < num_k; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* sa = smem + s * Cfg::kStageBytes;
-                uint8_t* sb = sa + Cfg::kABytes;
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                if (mode == kPlain) {
-                    tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tile_m * kTileM);
-                    tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tile_n * BN);
-                } else {
-                    const int tap = it / cc_n, cc = it - tap * cc_n;
-                    if (mode == kConvS2) {
-                        const int ky = tap >> 2, kx = tap & 3;
-                        const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
-                        const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
-                        tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
-                        tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tile_n * BN);
+            uint32_t g = 0;  // running stage counter across tiles
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, n_tiles, phases);
+                int n0 = 0, y0 = 0;
+                if (mode != kPlain) {
+                    if (R >= kTileM) {
+                        const int tpi = R / kTileM;
+                        n0 = tc.tile_m / tpi;
+                        y0 = (tc.tile_m % tpi) * (kTileM / args.GW);
                     } else {
-                        const int ty = tap >> 1, tx = tap & 1;
-                        const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                        tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
-                        tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK, tile_n * BN);
+                        n0 = tc.tile_m * (kTileM / R);
+                    }
+                }
+                const int py = tc.phase >> 1, px = tc.phase & 1;
+                for (int it = 0; it < num_k; ++it, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kABytes;
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    if (mode == kPlain) {
+                        tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tc.tile_m * kTileM);
+                        tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
+                    } else {
+                        const int tap = it / cc_n, cc = it - tap * cc_n;
+                        if (mode == kConvS2) {
+                            const int ky = tap >> 2, kx = tap & 3;
+                            const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
+                            const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+                            tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
+                            tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
+                        } else {
+                            const int ty = tap >> 1, tx = tap & 1;
+                            const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                            tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
+                            tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK,
+                                        tc.tile_n * BN);
+                        }
                     }
                 }
             }
@@ -192,97 +241,148 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
-            for (int it = 0; it < num_k; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t g = 0;
+            int j = 0;  // local tile counter
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+                const int acc = j & 1;
+                mbar_wait(&tempty_bar[acc], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                const uint32_t b_addr = a_addr + Cfg::kABytes;
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int it = 0; it < num_k; ++it, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                    const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                    umma_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                        const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit(&tfull_bar[acc]);
             }
-            umma_commit(accum_bar);
         }
-    } else {
+    } else if (warp - 2 < Cfg::kActiveEpiWarps) {
         // ---------------- Epilogue: TMEM -> registers -> global ----------------
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which half of the tile's columns
         const int r = q * 32 + lane;
-        const long gm = static_cast<long>(tile_m) * kTileM + r;
-        const bool row_ok = gm < args.M_total;
-        long opix = gm;
-        int img = 0;
-        if (mode != kPlain) {
-            img = static_cast<int>(gm / R);
-            if (mode == kConvT) {
-                const int rem = static_cast<int>(gm - static_cast<long>(img) * R);
-                const int yh = rem / args.GW, xh = rem - yh * args.GW;
-                opix = (static_cast<long>(img) * 2 * args.GH + 2 * yh + (phase >> 1)) * (2 * args.GW) + 2 * xh +
-                       (phase & 1);
+        const bool vec_ok = (((args.bias ? reinterpret_cast<uintptr_t>(args.bias) : 0) |
+                              (args.scale ? reinterpret_cast<uintptr_t>(args.scale) : 0) |
+                              (args.shift ? reinterpret_cast<uintptr_t>(args.shift) : 0) |
+                              (args.mask ? reinterpret_cast<uintptr_t>(args.mask) : 0)) & 15) == 0 &&
+                            (args.ldmask % 4 == 0);
+        int j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            const TileCoord tc = decode_tile(t, n_tiles, phases);
+            const int acc = j & 1;
+            const long gm = static_cast<long>(tc.tile_m) * kTileM + r;
+            const bool row_ok = gm < args.M_total;
+            long opix = gm;
+            int img = 0;
+            if (mode != kPlain) {
+                img = static_cast<int>(gm / R);
+                if (mode == kConvT) {
+                    const int rem = static_cast<int>(gm - static_cast<long>(img) * R);
+                    const int yh = rem / args.GW, xh = rem - yh * args.GW;
+                    opix = (static_cast<long>(img) * 2 * args.GH + 2 * yh + (tc.phase >> 1)) * (2 * args.GW) + 2 * xh +
+                           (tc.phase & 1);
+                }
             }
-        }
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+            mbar_wait(&tfull_bar[acc], (j >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            const int n_base = tile_n * BN + c0;
-            if (row_ok && n_base < args.N_total) {
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (args.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + n_base + j);
+            for (int c0 = half * Cfg::kColsPerWarp; c0 < (half + 1) * Cfg::kColsPerWarp; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 >= (half + 1) * Cfg::kColsPerWarp) {
+                    // last chunk of this warp is in registers: hand the accumulator back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-                if (args.scale) {
+                const int n_base = tc.tile_n * BN + c0;
+                if (row_ok) {
+                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        f[j] = fmaf(f[j], __ldg(args.scale + n_base + j), __ldg(args.shift + n_base + j));
-                }
-                if (args.act == kActRelu) {
+                    for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]);
+                    if (args.bias) {
+                        float b[32];
+                        if (vec_ok) {
+                            load_vec32(args.bias + n_base, b);
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                } else if (args.act == kActLeaky) {
+                            for (int jj = 0; jj < 32; ++jj) b[jj] = __ldg(args.bias + n_base + jj);
+                        }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * args.slope;
-                }
-                if (args.mask) {
-                    const float* mk = args.mask + static_cast<long>(img) * args.ldmask + n_base;
+                        for (int jj = 0; jj < 32; ++jj) f[jj] += b[jj];
+                    }
+                    if (args.scale) {
+                        float sc[32], sh[32];
+                        if (vec_ok) {
+                            load_vec32(args.scale + n_base, sc);
+                            load_vec32(args.shift + n_base, sh);
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] *= __ldg(mk + j);
-                }
-                if (args.gate) {
-                    const uint4* g = reinterpret_cast<const uint4*>(args.gate + opix * args.ldo + n_base);
+                            for (int jj = 0; jj < 32; ++jj) {
+                                sc[jj] = __ldg(args.scale + n_base + jj);
+                                sh[jj] = __ldg(args.shift + n_base + jj);
+                            }
+                        }
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const uint4 u = __ldg(g + j4);
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = fmaf(f[jj], sc[jj], sh[jj]);
+                    }
+                    if (args.act == kActRelu) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            f[j4 * 8 + t * 2] *= bf16_lo(w[t]) > 0.f ? 1.f : args.slope;
-                            f[j4 * 8 + t * 2 + 1] *= bf16_hi(w[t]) > 0.f ? 1.f : args.slope;
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+                    } else if (args.act == kActLeaky) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
+                    }
+                    if (args.mask) {
+                        const float* mk = args.mask + static_cast<long>(img) * args.ldmask + n_base;
+                        float m[32];
+                        if (vec_ok) {
+                            load_vec32(mk, m);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) m[jj] = __ldg(mk + jj);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) f[jj] *= m[jj];
+                    }
+                    if (args.gate) {
+                        const uint4* gp = reinterpret_cast<const uint4*>(args.gate + opix * args.ldo + n_base);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint4 u = __ldg(gp + j4);
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt) {
+                                f[j4 * 8 + tt * 2] *= bf16_lo(w[tt]) > 0.f ? 1.f : args.slope;
+                                f[j4 * 8 + tt * 2 + 1] *= bf16_hi(w[tt]) > 0.f ? 1.f : args.slope;
+                            }
                         }
                     }
-                }
-                if (args.out_fp32) {
-                    float4* o = reinterpret_cast<float4*>(static_cast<float*>(args.out) + opix * args.ldo + n_base);
+                    if (args.out_fp32) {
+                        float4* o = reinterpret_cast<float4*>(static_cast<float*>(args.out) + opix * args.ldo + n_base);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-                    uint4* o =
-                        reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + opix * args.ldo + n_base);
+                        for (int jj = 0; jj < 8; ++jj)
+                            o[jj] = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
+                    } else {
+                        uint4* o =
+                            reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + opix * args.ldo + n_base);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        o[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        for (int jj = 0; jj < 4; ++jj)
+                            o[jj] = make_uint4(pack_bf16(f[8 * jj], f[8 * jj + 1]), pack_bf16(f[8 * jj + 2], f[8 * jj + 3]),
+                                               pack_bf16(f[8 * jj + 4], f[8 * jj + 5]),
+                                               pack_bf16(f[8 * jj + 6], f[8 * jj + 7]));
+                    }
                 }
             }
         }
@@ -292,8 +392,18 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN, int BK>
-static int launch_cfg(const ConvGemmArgs& a, dim3 grid, cudaStream_t stream) {
+static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, BK>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -302,6 +412,8 @@ static int launch_cfg(const ConvGemmArgs& a, dim3 grid, cudaStream_t stream) {
         if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(conv_umma<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
         attr_set = true;
     }
+    const int slots = sm_count() * Cfg::kCtasPerSm;
+    const int grid = total_tiles < slots ? total_tiles : slots;
     note_launch();
     conv_umma_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
@@ -347,9 +459,9 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
         }
     }
     if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN)) return -1;
-    dim3 grid((a.M_total + kTileM - 1) / kTileM, Cout / BN, mode == kConvT ? 4 : 1);
+    const int total_tiles = ((a.M_total + kTileM - 1) / kTileM) * (Cout / BN) * (mode == kConvT ? 4 : 1);
 #define SG_DISPATCH(bn, bk) \
-    if (BN == bn && BK == bk) return launch_cfg<bn, bk>(a, grid, stream);
+    if (BN == bn && BK == bk) return launch_cfg<bn, bk>(a, total_tiles, stream);
     SG_DISPATCH(256, 64)
     SG_DISPATCH(128, 64)
     SG_DISPATCH(64, 64)
@@ -367,6 +479,7 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
 // Both operands are "MN-major" (the contraction runs over rows of NHWC tensors).
 // ----------------------------------------------------------------------------
 constexpr int kWgK = 64;  // pixels per pipeline stage
+constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 
 template <int BN>
 struct WgCfg {
@@ -380,7 +493,7 @@ struct WgCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) wgrad_umma_kernel(const __grid_constant__ WgradArgs args) {
+__global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_constant__ WgradArgs args) {
     using Cfg = WgCfg<BN>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -557,7 +670,7 @@ static int launch_wg(const WgradArgs& a, dim3 grid, cudaStream_t stream) {
         attr_set = true;
     }
     note_launch();
-    wgrad_umma_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
+    wgrad_umma_kernel<BN><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("wgrad_umma<%d> launch: %s", BN, cudaGetErrorString(e));
     return 0;

@@ -346,6 +346,12 @@ int main(int argc, char** argv) {
     RUN(test_conv("convT 4x16x16x64->32", sg::kConvT, 4, 16, 16, 64, 32, true));
     RUN(test_conv("convT 2x32x32x32->32 (thin)", sg::kConvT, 2, 32, 32, 32, 32, true));
     RUN(test_conv("convT 3x8x8x512->256", sg::kConvT, 3, 8, 8, 512, 256, false));
+    // more tiles than SMs: every persistent CTA walks several tiles and both TMEM accumulators wrap
+    RUN(test_conv("convS2 48x64x64x32->32 (384 tiles)", sg::kConvS2, 48, 64, 64, 32, 32, true));
+    RUN(test_conv("convT 24x32x32x32->32 (768 tiles)", sg::kConvT, 24, 32, 32, 32, 32, true));
+    RUN(test_conv("convS2 1280x8x8x64->128 (160 t)", sg::kConvS2, 1280, 8, 8, 64, 128, true));
+    RUN(test_conv("convT 700x4x4x64->64 (352 tiles)", sg::kConvT, 700, 4, 4, 64, 64, true));
+    RUN(test_conv("plain 40000x64x256 (626 tiles)", sg::kPlain, 40000, 1, 1, 64, 256, true));
     RUN(test_wgrad("wgrad 8x16x16 128|64", 8, 16, 16, 128, 64));
     RUN(test_wgrad("wgrad 16x4x4 512|256", 16, 4, 4, 512, 256));
     RUN(test_wgrad("wgrad 8x8x8 256|128", 8, 8, 8, 256, 128));
