@@ -66,6 +66,18 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs epi /* only epilogue fields read */, cudaStream_t stream);
 
+// Phase-fused transposed convolution for the thin, wide-grid layers (input grid width 16/32/64, Cout 32 or 64):
+// one CTA computes all four output parities of a 128-input-pixel tile, loading each input row block (with a
+// one-row halo) once per horizontal shift instead of once per filter tap; the 16 tap weight blocks stay resident
+// in shared memory when they fit (Cout = 32), else they are streamed through their own ring. Optionally emits
+// per-CTA partial sums (sum, sum of squares per channel) of the raw output for BatchNorm: `stats_partial` holds
+// [convt4_max_chunks()][2][Cout] floats, *stats_chunks receives the number of rows written.
+bool convt4_supported(int inH, int inW, int Cin, int Cout);
+int convt4_max_chunks();
+int launch_convt4(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW, int Cin, int Cout,
+                  ConvGemmArgs epi /* only epilogue fields read */, float* stats_partial, int* stats_chunks,
+                  cudaStream_t stream);
+
 // dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
 // `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.
 int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,

@@ -259,7 +259,9 @@ static int test_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
     return bad;
 }
 
+static bool want(const char* name);
 static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout) {
+    if (!want(name)) return;
     bf16 *x, *w, *out;
     const size_t xn = (size_t)N * H * W * Cin, wn = (size_t)Cout * 16 * Cin;
     const size_t on = mode == sg::kConvS2 ? (size_t)N * H / 2 * W / 2 * Cout : (size_t)N * H * 2 * W * 2 * Cout;
@@ -294,6 +296,7 @@ static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, 
 }
 
 static void perf_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
+    if (!want(name)) return;
     bf16 *c, *f;
     const size_t cn = (size_t)N * cH * cW * Mc, fn = (size_t)N * 4 * cH * cW * Nf;
     CK(cudaMalloc(&c, cn * 2));
@@ -325,8 +328,13 @@ static void perf_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) 
     cudaFree(dW);
 }
 
+static const char* g_filter = nullptr;
+static bool want(const char* name) { return !g_filter || strstr(name, g_filter); }
+
 int main(int argc, char** argv) {
-    int only = argc > 2 ? atoi(argv[2]) : -1;
+    const bool perfonly = argc > 1 && !strcmp(argv[1], "perfonly");  // perfonly [name-substring]: skip the checks
+    if (perfonly && argc > 2) g_filter = argv[2];
+    int only = (!perfonly && argc > 2) ? atoi(argv[2]) : (perfonly ? 1 << 30 : -1);
     int fails = 0, t = 0;
 #define RUN(expr)                          \
     do {                                   \
@@ -359,7 +367,7 @@ int main(int argc, char** argv) {
     RUN(test_wgrad("wgrad 3x16x16 64|32 (thin)", 3, 16, 16, 64, 32));
     RUN(test_wgrad("wgrad 5x4x4 256|128 (tail)", 5, 4, 4, 256, 128));
     printf("harness: %d failing tests\n", fails);
-    if (argc > 1 && !strcmp(argv[1], "perf") && fails == 0) {
+    if (argc > 1 && (!strcmp(argv[1], "perf") || perfonly) && fails == 0) {
         const int B = 4096;
         perf_conv("D c1 64->128 @32x32", sg::kConvS2, B, 32, 32, 64, 128);
         perf_conv("D c2 128->256 @16x16", sg::kConvS2, B, 16, 16, 128, 256);
