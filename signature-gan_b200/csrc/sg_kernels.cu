@@ -1,5 +1,6 @@
 // sg_kernels.cu — CUDA-core kernels of the siggan hot path (see sg_kernels.cuh).
 #include "sg_kernels.cuh"
+#include "sg_elem.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -16,83 +17,6 @@ int kernels_check(const char* what) {
         return -1;
     }
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// element access helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_f(float v) { return v; }
-__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
-template <typename T>
-__device__ __forceinline__ T from_f(float v);
-template <>
-__device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
-
-__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0];
-    const float4 b = reinterpret_cast<const float4*>(p)[1];
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-}
-__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
-}
-__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// All spatial sizes / channel counts on this path are powers of two: index math uses shifts and masks
-// (64-bit div/mod per element was the dominant cost of the first version of these kernels).
-__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
-
-// Raw 8-element loads (no conversion) used to issue a whole neighbourhood of loads back to back.
-struct Raw8f { float4 a, b; };
-__device__ __forceinline__ Raw8f ldraw8(const float* p) {
-    Raw8f r;
-    r.a = __ldg(reinterpret_cast<const float4*>(p));
-    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    return r;
-}
-__device__ __forceinline__ uint4 ldraw8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ void unpack8(const Raw8f& r, float (&f)[8]) {
-    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
-    f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
-}
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-}
-template <typename T> struct RawOf;
-template <> struct RawOf<float> { using type = Raw8f; };
-template <> struct RawOf<bf16> { using type = uint4; };
-
-static inline int blocks_for(long n, int threads, int cap = 148 * 16) {
-    long b = (n + threads - 1) / threads;
-    if (b > cap) b = cap;
-    if (b < 1) b = 1;
-    return static_cast<int>(b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,7 +252,8 @@ template void bn_apply_relu<bf16>(const bf16*, const float*, const float*, bf16*
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, long rows, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
-                                       int batch_stats, int perm_c0, float* __restrict__ dgamma,
+                                       const float* __restrict__ raw_mean, int batch_stats, int perm_c0,
+                                       float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
                                        float* __restrict__ k3) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,6 +264,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ch
         s0 += partial[static_cast<long>(k) * 2 * C + j];
         s1 += partial[static_cast<long>(k) * 2 * C + C + j];
     }
+    // raw mode: the second partial is sum d*y; sum d*xhat = rstd * (sum d*y - mean * sum d)
+    if (raw_mean) s1 = static_cast<double>(rstd[j]) * (s1 - static_cast<double>(raw_mean[j]) * s0);
     dbeta[p] = static_cast<float>(s0);
     dgamma[p] = static_cast<float>(s1);
     k1[j] = gamma[p] * rstd[j];
@@ -346,11 +273,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ch
     k3[j] = batch_stats ? static_cast<float>(s1 / rows) : 0.f;
 }
 void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* rstd,
-                     int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
-                     cudaStream_t s) {
+                     const float* raw_mean, int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1,
+                     float* k2, float* k3, cudaStream_t s) {
     note_launch();
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, rstd, batch_stats, perm_c0,
-                                                          dgamma, dbeta, k1, k2, k3);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, rstd, raw_mean, batch_stats,
+                                                          perm_c0, dgamma, dbeta, k1, k2, k3);
 }
 
 template <typename T>
@@ -404,205 +331,8 @@ void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* o
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generator tail: Conv3x3 (C -> 1) + tanh, and its backward
+// partial[chunks][n] -> out_a[0..na) and out_b[0..n-na) (deterministic, double accumulation)
 // ------------------------------------------------------------------------------------------------
-// All three kernels give each pixel to C/8 adjacent lanes (one 8-channel slice each) and keep that slice's
-// 9x8 filter taps (or 9x8 gradient accumulators) in registers, so the inner loops are 16-byte activation
-// loads + FMAs with no shared-memory traffic. A warp covers 32/(C/8) consecutive pixels.
-template <typename T, int C>
-__global__ void __launch_bounds__(256)
-final_conv_tanh_kernel(const T* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
-                       float* __restrict__ out, uint8_t* __restrict__ out_u8, int B, int S) {
-    constexpr int G = C / 8;
-    const int g = threadIdx.x % G;
-    float wr[9][8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
-    const float b0 = bias[0];
-    const long total = static_cast<long>(B) * S * S;   // multiple of 32/G, so whole warps stay in the loop together
-    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
-    const int sh = ilog2(S);
-    for (long pix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; pix < total; pix += stride) {
-        const int x = static_cast<int>(pix) & (S - 1);
-        const int yy = static_cast<int>(pix >> sh) & (S - 1);
-        float acc = 0.f;
-        typename RawOf<T>::type raw[9];
-        bool ok[9];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = yy + ky - 1;
-            const int cy = min(max(iy, 0), S - 1);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = x + kx - 1;
-                const int cx = min(max(ix, 0), S - 1);
-                ok[ky * 3 + kx] = (iy == cy) && (ix == cx);
-                raw[ky * 3 + kx] = ldraw8(a + (pix + static_cast<long>(cy - yy) * S + (cx - x)) * C + g * 8);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            float v[8];
-            unpack8(raw[t], v);
-            float part = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) part = fmaf(v[j], wr[t][j], part);
-            acc += ok[t] ? part : 0.f;
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (g == 0) {
-            const float t = tanhf(acc + b0);
-            out[pix] = t;
-            if (out_u8) {
-                float q = (t + 1.f) * 127.5f;
-                q = fminf(fmaxf(q, 0.f), 255.f);
-                out_u8[pix] = static_cast<uint8_t>(q);  // numpy astype(uint8) truncates (utils/inference.py:129)
-            }
-        }
-    }
-}
-template <typename T>
-void final_conv_tanh(const T* a, const float* w, const float* bias, float* out, uint8_t* out_u8, int B, int S, int C,
-                     cudaStream_t s) {
-    if (C != 32) {
-        snprintf(k_err, sizeof(k_err), "final_conv_tanh: C=%d unsupported (reference uses 32)", C);
-        return;
-    }
-    const long threads = static_cast<long>(B) * S * S * (C / 8);
-    note_launch();
-    final_conv_tanh_kernel<T, 32><<<blocks_for(threads, 256, 148 * 8), 256, 0, s>>>(a, w, bias, out, out_u8, B, S);
-}
-template void final_conv_tanh<float>(const float*, const float*, const float*, float*, uint8_t*, int, int, int,
-                                     cudaStream_t);
-template void final_conv_tanh<bf16>(const bf16*, const float*, const float*, float*, uint8_t*, int, int, int,
-                                    cudaStream_t);
-
-__global__ void tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
-                                float* __restrict__ dpre, long n) {
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const float o = out[i];
-        dpre[i] = dout[i] * (1.f - o * o);
-    }
-}
-
-// dbn[n,y,x,c] = [a>0] * sum_{ky,kx} dpre[n, y+1-ky, x+1-kx] * w[c][ky][kx]
-template <typename T, int C>
-__global__ void __launch_bounds__(256)
-final_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, const T* __restrict__ a,
-                   T* __restrict__ dbn, int B, int S) {
-    constexpr int G = C / 8;
-    const int g = threadIdx.x % G;
-    float wr[9][8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
-    const long total = static_cast<long>(B) * S * S;
-    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
-    const int sh = ilog2(S);
-    for (long pix = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; pix < total; pix += stride) {
-        const int x = static_cast<int>(pix) & (S - 1);
-        const int yy = static_cast<int>(pix >> sh) & (S - 1);
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        const typename RawOf<T>::type araw = ldraw8(a + pix * C + g * 8);
-        float dv[9];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int sy = yy + 1 - ky;
-            const int cy = min(max(sy, 0), S - 1);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int sx = x + 1 - kx;
-                const int cx = min(max(sx, 0), S - 1);
-                const float d = __ldg(dpre + pix + static_cast<long>(cy - yy) * S + (cx - x));
-                dv[ky * 3 + kx] = (sy == cy && sx == cx) ? d : 0.f;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[t], wr[t][j], acc[j]);
-        float av[8];
-        unpack8(araw, av);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = av[j] > 0.f ? acc[j] : 0.f;
-        store8(dbn + pix * C + g * 8, acc);
-    }
-}
-
-// dW[c][ky][kx] = sum_pix dpre[pix] * a[pix + (ky-1, kx-1)][c]; written as a scatter from each activation pixel q:
-// acc[tap][c] += a[q][c] * dpre[q - (ky-1, kx-1)]. partial[block][C*9 + 1] (last slot: sum of dpre = dbias).
-template <typename T, int C>
-__global__ void __launch_bounds__(256)
-final_wgrad_kernel(const float* __restrict__ dpre, const T* __restrict__ a, float* __restrict__ partial, int B, int S) {
-    constexpr int G = C / 8;
-    __shared__ float sm[8][C * 9 + 1];
-    const int g = threadIdx.x % G;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc[9][8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-    float dsum = 0.f;
-    const long total = static_cast<long>(B) * S * S;
-    const long stride = static_cast<long>(gridDim.x) * blockDim.x / G;
-    const int sh = ilog2(S);
-    for (long q = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / G; q < total; q += stride) {
-        const int x = static_cast<int>(q) & (S - 1);
-        const int yy = static_cast<int>(q >> sh) & (S - 1);
-        const typename RawOf<T>::type araw = ldraw8(a + q * C + g * 8);
-        float dv[9];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int py = yy - (ky - 1);
-            const int cy = min(max(py, 0), S - 1);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int px = x - (kx - 1);
-                const int cx = min(max(px, 0), S - 1);
-                const float d = __ldg(dpre + q + static_cast<long>(cy - yy) * S + (cx - x));
-                dv[ky * 3 + kx] = (py == cy && px == cx) ? d : 0.f;
-            }
-        }
-        float v[8];
-        unpack8(araw, v);
-        if (g == 0) dsum += dv[4];
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(dv[t], v[j], acc[t][j]);
-    }
-    // lanes with equal g hold partial sums of the same outputs: fold them (xor over the pixel bits of the lane id)
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int o = 16; o >= G; o >>= 1) acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], o);
-#pragma unroll
-    for (int o = 16; o >= G; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    if (lane < G) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sm[warp][(g * 8 + j) * 9 + t] = acc[t][j];
-        if (g == 0) sm[warp][C * 9] = dsum;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) {
-        float s = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) s += sm[wv][i];
-        partial[static_cast<long>(blockIdx.x) * (C * 9 + 1) + i] = s;
-    }
-}
 __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunks, int n, float* __restrict__ out_a,
                                     int na, float* __restrict__ out_b) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,26 +345,10 @@ __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunk
         out_b[j - na] = static_cast<float>(s);
 }
 
-template <typename T>
-void final_conv_bwd(const float* dout, const float* out, const T* a, const float* w, float* dpre, T* dbn, float* dW,
-                    float* dbias, float* partial, int B, int S, int C, cudaStream_t s) {
-    if (C != 32) {
-        snprintf(k_err, sizeof(k_err), "final_conv_bwd: C=%d unsupported (reference uses 32)", C);
-        return;
-    }
-    const long total = static_cast<long>(B) * S * S;
-    note_launch(4);
-    tanh_bwd_kernel<<<blocks_for(total, 256), 256, 0, s>>>(dout, out, dpre, total);
-    final_dgrad_kernel<T, 32><<<blocks_for(total * 4, 256, 148 * 8), 256, 0, s>>>(dpre, w, a, dbn, B, S);
-    const int chunks = blocks_for(total * 4, 256, kMaxChunks);
-    final_wgrad_kernel<T, 32><<<chunks, 256, 0, s>>>(dpre, a, partial, B, S);
-    const int n = C * 9 + 1;
-    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, dW, C * 9, dbias);
+void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na, float* out_b, cudaStream_t s) {
+    note_launch();
+    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, out_a, na, out_b);
 }
-template void final_conv_bwd<float>(const float*, const float*, const float*, const float*, float*, float*, float*,
-                                    float*, float*, int, int, int, cudaStream_t);
-template void final_conv_bwd<bf16>(const float*, const float*, const bf16*, const float*, float*, bf16*, float*, float*,
-                                   float*, int, int, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // Discriminator head: Conv 4x4 s2 p1 from the 1-channel image, forward / wgrad / dgrad
@@ -811,11 +525,11 @@ void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B
     }
     const long total = static_cast<long>(B) * (S / 2) * (S / 2);
     const int chunks = blocks_for(total * 16, 256, kMaxChunks);
-    note_launch(2);
+    note_launch();
     d_conv0_wgrad_kernel<T><<<chunks, 256, 0, s>>>(x, dy, partial, B, S);
     const int n = C * 17;
     // dW (C*16 floats) is immediately followed by dbias (C floats) in the flat gradient buffer
-    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, dW, n, nullptr);
+    vec_finalize(partial, chunks, n, dW, n, nullptr, s);
 }
 template void d_conv0_wgrad<float>(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 template void d_conv0_wgrad<bf16>(const float*, const bf16*, float*, float*, int, int, int, cudaStream_t);

@@ -57,23 +57,30 @@ void bn_finalize(const float* partial, int chunks, long rows, int C, const float
 template <typename T>
 void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, cudaStream_t s);
 // BatchNorm backward bookkeeping: dgamma/dbeta (parameter order) and the per-channel coefficients.
+// raw_mean != null: the second partial is sum d*y (not d*xhat) and is converted here with mean/rstd.
 void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* rstd,
-                     int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
-                     cudaStream_t s);
+                     const float* raw_mean, int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1,
+                     float* k2, float* k3, cudaStream_t s);
 template <typename T>
 void bn_bwd_apply(const T* d, const T* y, const float* mean, const float* rstd, const float* k1, const float* k2,
                   const float* k3, T* dy, long rows, int C, cudaStream_t s);
 // Generic: out0[pidx] = sum_chunks p0, out1[pidx] = sum_chunks p1 (null = skip); accumulate adds into out.
 void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* out0, float* out1, cudaStream_t s);
 
-// Conv3x3(C->1) + bias + tanh (gen…:153-163). out fp32 (B,1,S,S); out_u8 optional.
+// Conv3x3(32->1) + bias + tanh (gen…:153-163) over the last NHWC level (sg_gfinal.cu). With scale/shift non-null `in`
+// is the PRE-BatchNorm convolution output and relu(in*scale+shift) is applied while loading, so the normalised
+// activation of the last upsample block is never written to HBM. out fp32 (B,1,S,S); out_u8 optional.
 template <typename T>
-void final_conv_tanh(const T* a, const float* w, const float* bias, float* out, uint8_t* out_u8, int B, int S, int C,
-                     cudaStream_t s);
-// Backward of the above: dpre = dout*(1-out^2) (scratch fp32), dbn = relu'(a) * convT3x3(dpre), dW, dbias.
+void final_conv_tanh(const T* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
+                     uint8_t* out_u8, int B, int S, int C, cudaStream_t s);
+// Backward of the above in one pass over y: dbn = relu'(a) * convT3x3(dout*(1-out^2)), dW, dbias, plus the
+// BatchNorm-backward partial sums of the last block, part_bn[chunk][2][C] = (sum dbn, sum dbn*y) (raw form, see
+// bn_bwd_finalize). part_w must hold chunks*(C*9+1) floats. Returns the number of chunks (<= kMaxChunks).
 template <typename T>
-void final_conv_bwd(const float* dout, const float* out, const T* a, const float* w, float* dpre, T* dbn, float* dW,
-                    float* dbias, float* partial, int B, int S, int C, cudaStream_t s);
+int final_conv_bwd(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
+                   const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S, int C,
+                   cudaStream_t s);
+void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na, float* out_b, cudaStream_t s);
 
 // ---- discriminator side ----------------------------------------------------------------------
 // Conv 4x4 s2 p1, 1 -> C channels (disc…:134-139) with bias + LeakyReLU + dropout mask.

@@ -398,17 +398,21 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
                                 stats + c->bn[i + 1].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 1, 0, w.mean[i + 1],
                                 w.rstd[i + 1], w.scale[i + 1], w.shift[i + 1], s);
             }
-            PROF((nm + ".bn_apply").c_str(), 0, 2.0 * es * (double)rows * Cout);
-            sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.y[i]), w.scale[i + 1], w.shift[i + 1],
-                                 reinterpret_cast<T*>(w.a[i]), rows, Cout, s);
+            if (i < c->L - 1) {  // the last level is normalised on the fly inside final_conv_tanh
+                PROF((nm + ".bn_apply").c_str(), 0, 2.0 * es * (double)rows * Cout);
+                sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.y[i]), w.scale[i + 1], w.shift[i + 1],
+                                     reinterpret_cast<T*>(w.a[i]), rows, Cout, s);
+            }
         }
-        in = w.a[i];
+        in = (fuse || i < c->L - 1) ? w.a[i] : w.y[i];
     }
     // ---- Conv3x3 + tanh (gen…:153-163)
     float* out = save ? w.out : out_image;
     {
     PROF("g.final", 2.0 * B * c->S * c->S * 9.0 * c->gch[c->L], (double)B * c->S * c->S * (es * c->gch[c->L] + 4.0));
-    sg::final_conv_tanh<T>(reinterpret_cast<const T*>(in), params + c->gt[c->g_final_w].offset,
+    const bool affine = !(kTC && fused_eval);
+    sg::final_conv_tanh<T>(reinterpret_cast<const T*>(in), affine ? w.scale[c->L] : nullptr,
+                           affine ? w.shift[c->L] : nullptr, params + c->gt[c->g_final_w].offset,
                            params + c->gt[c->g_final_b].offset, out, out_u8, B, c->S, c->gch[c->L], s);
     }
     if (save && out_image) {
@@ -431,12 +435,16 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
     char* nxt = static_cast<char*>(c->bufB.p);
     const int L = c->L;
     const double es = c->es;
+    // One pass over the last block's pre-BatchNorm output: d/d(bn output), final-conv dW/dbias, and the
+    // BatchNorm-backward reductions of the last block (so that block needs no separate reduction pass below).
+    float* part_bn = cpart + static_cast<size_t>(sg::kMaxChunks) * (9 * c->gch[L] + 1);
+    int last_chunks = 0;
     {
-    PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L], (double)B * c->S * c->S * (12.0 + 3.0 * es * c->gch[L]));
-    sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.a[L - 1]),
-                          params + c->gt[c->g_final_w].offset, static_cast<float*>(c->dpre.p),
-                          reinterpret_cast<T*>(cur), grads + c->gt[c->g_final_w].offset,
-                          grads + c->gt[c->g_final_b].offset, cpart, B, c->S, c->gch[L], s);
+    PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L], (double)B * c->S * c->S * (8.0 + 2.0 * es * c->gch[L]));
+    last_chunks = sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.y[L - 1]), w.scale[L], w.shift[L],
+                                        params + c->gt[c->g_final_w].offset, reinterpret_cast<T*>(cur),
+                                        grads + c->gt[c->g_final_w].offset, grads + c->gt[c->g_final_b].offset, cpart,
+                                        part_bn, B, c->S, c->gch[L], s);
     }
     for (int i = L - 1; i >= 0; --i) {
         const int oh = g_spatial(c, i), ih = oh / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
@@ -445,12 +453,15 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
         const std::string nm = "g.up" + std::to_string(i);
         const double cflops = 2.0 * B * ih * ih * 16.0 * Cin * Cout;
         // BatchNorm2d backward (cur holds relu'-masked d/d(bn output)); result dy overwrites cur
-        {
-        PROF((nm + ".bn_bwd_reduce").c_str(), 0, 2.0 * es * (double)rows * Cout);
-        const int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]),
-                                             w.mean[i + 1], w.rstd[i + 1], nullptr, rows, Cout, cpart, s);
-        sg::bn_bwd_finalize(cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], train, 0,
-                            grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+        if (i == L - 1) {
+            sg::bn_bwd_finalize(part_bn, last_chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], w.mean[i + 1],
+                                train, 0, grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+        } else {
+            PROF((nm + ".bn_bwd_reduce").c_str(), 0, 2.0 * es * (double)rows * Cout);
+            const int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]),
+                                                 w.mean[i + 1], w.rstd[i + 1], nullptr, rows, Cout, cpart, s);
+            sg::bn_bwd_finalize(cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], nullptr, train, 0,
+                                grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
         }
         {
         PROF((nm + ".bn_bwd_apply").c_str(), 0, 3.0 * es * (double)rows * Cout);
@@ -491,8 +502,8 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
     PROF("g.fc.bwd", 2.0 * B * F0 * latent, 6.0 * es * B * (double)F0);
     int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.fc_y), w.mean[0],
                                    w.rstd[0], nullptr, B, F0, cpart, s);
-    sg::bn_bwd_finalize(cpart, chunks, B, F0, params + bn.gamma_off, w.rstd[0], train, c->gch[0], grads + bn.gamma_off,
-                        grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+    sg::bn_bwd_finalize(cpart, chunks, B, F0, params + bn.gamma_off, w.rstd[0], nullptr, train, c->gch[0],
+                        grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
     sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.fc_y), w.mean[0], w.rstd[0], c->k1,
                         c->k2, c->k3, reinterpret_cast<T*>(cur), B, F0, s);
     chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr, nullptr, B, F0, cpart, s);
