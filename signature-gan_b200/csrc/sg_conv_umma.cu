@@ -98,20 +98,25 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiStageBytes = 32 * 64;           // per epilogue warp: 32 rows x 32 bf16 columns, swizzled
 
-template <int BN, int BK>
+// kPair (transposed convolution, BN <= 128): one schedule unit = both horizontal output parities (px = 0, 1) of a
+// (128-input-pixel tile, py) pair, accumulated side by side in TMEM, so that the epilogue of a row writes the two
+// horizontally adjacent output pixels — a contiguous run — instead of every other pixel.
+template <int BN, int BK, bool kPair>
 struct ConvCfg {
     static constexpr int kABytes = kTileM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // Thin tiles (BN <= 64) are epilogue/latency-bound rather than MMA-bound: run two persistent CTAs per SM.
-    static constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;
-    static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 98 : 196) * 1024) / kStageBytes;
+    static constexpr int kAccCols = kPair ? 2 * BN : BN;                  // columns of one accumulator buffer
+    static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // double-buffered accumulator
+    // Thin tiles are epilogue/latency-bound rather than MMA-bound: run two persistent CTAs per SM.
+    static constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;   // (2 x kTmemCols <= 512 holds for BN <= 64, paired or not)
+    static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 92 : 196) * 1024) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;          // double-buffered accumulator
-    static constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
-    static constexpr int kActiveEpiWarps = BN >= 64 ? 8 : 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kColsPerWarp = kAccCols >= 64 ? kAccCols / 2 : kAccCols;
+    static constexpr int kActiveEpiWarps = kAccCols >= 64 ? 8 : 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
     static constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of one swizzle atom
 };
@@ -121,19 +126,6 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// 32 floats of a per-column vector (uniform across the warp): 8 broadcast 128-bit loads.
-__device__ __forceinline__ void load_vec32(const float* p, float (&v)[32]) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(q + j);
-        v[4 * j] = t.x;
-        v[4 * j + 1] = t.y;
-        v[4 * j + 2] = t.z;
-        v[4 * j + 3] = t.w;
-    }
 }
 
 struct TileCoord {
@@ -148,13 +140,32 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int phases)
     return c;
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
-    using Cfg = ConvCfg<BN, BK>;
+// 8 floats of a per-column vector (uniform across the warp, so these are broadcast loads that hit L1).
+__device__ __forceinline__ void load_vec8(const float* p, bool vec_ok, float (&v)[8]) {
+    if (vec_ok) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
+    }
+}
+
+// Epilogue staging buffer of one warp: 32 rows x 64 bytes; 16-byte piece k of row r lives at piece k ^ ((r >> 1) & 3),
+// which makes both the row-per-lane and the 4-lanes-per-row access patterns bank-conflict free.
+__device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 64 + ((k ^ ((row >> 1) & 3)) << 4); }
+
+template <int BN, int BK, bool kPair>
+__global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK, kPair>::kCtasPerSm)
+conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
+    using Cfg = ConvCfg<BN, BK, kPair>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready for the epilogue
     uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained, MMA may overwrite
@@ -165,7 +176,9 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_um
     const int mode = args.mode;
     const int cc_n = args.Cin / BK;
     const int taps = (mode == kConvS2) ? 16 : (mode == kConvT ? 4 : 1);
-    const int phases = (mode == kConvT) ? 4 : 1;
+    // schedule units per (tile_m, tile_n): 4 parity phases, or 2 vertical parities when px is paired in the unit
+    const int phases = (mode == kConvT) ? (kPair ? 2 : 4) : 1;
+    constexpr int kSub = kPair ? 2 : 1;  // accumulations per unit
     const int num_k = taps * cc_n;
     const int R = args.GH * args.GW;
     const int n_tiles = args.N_total / BN;
@@ -207,31 +220,34 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_um
                         n0 = tc.tile_m * (kTileM / R);
                     }
                 }
-                const int py = tc.phase >> 1, px = tc.phase & 1;
-                for (int it = 0; it < num_k; ++it, ++g) {
-                    const int s = g % STAGES;
-                    const uint32_t ph = (g / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + s * Cfg::kStageBytes;
-                    uint8_t* sb = sa + Cfg::kABytes;
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                    if (mode == kPlain) {
-                        tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tc.tile_m * kTileM);
-                        tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
-                    } else {
-                        const int tap = it / cc_n, cc = it - tap * cc_n;
-                        if (mode == kConvS2) {
-                            const int ky = tap >> 2, kx = tap & 3;
-                            const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
-                            const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
-                            tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
+#pragma unroll 1
+                for (int sub = 0; sub < kSub; ++sub) {
+                    const int py = kPair ? tc.phase : (tc.phase >> 1), px = kPair ? sub : (tc.phase & 1);
+                    for (int it = 0; it < num_k; ++it, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* sa = smem + s * Cfg::kStageBytes;
+                        uint8_t* sb = sa + Cfg::kABytes;
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                        if (mode == kPlain) {
+                            tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tc.tile_m * kTileM);
                             tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
                         } else {
-                            const int ty = tap >> 1, tx = tap & 1;
-                            const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                            tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
-                            tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK,
-                                        tc.tile_n * BN);
+                            const int tap = it / cc_n, cc = it - tap * cc_n;
+                            if (mode == kConvS2) {
+                                const int ky = tap >> 2, kx = tap & 3;
+                                const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
+                                const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+                                tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
+                                tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
+                            } else {
+                                const int ty = tap >> 1, tx = tap & 1;
+                                const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                                tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
+                                tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK,
+                                            tc.tile_n * BN);
+                            }
                         }
                     }
                 }
@@ -247,58 +263,80 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_um
                 const int acc = j & 1;
                 mbar_wait(&tempty_bar[acc], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int it = 0; it < num_k; ++it, ++g) {
-                    const int s = g % STAGES;
-                    const uint32_t ph = (g / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll 1
+                for (int sub = 0; sub < kSub; ++sub) {
+                    const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols + sub * BN;
+                    for (int it = 0; it < num_k; ++it, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                        const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                        const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                        umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                            const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                            umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0);
+                        }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&tfull_bar[acc]);
             }
         }
     } else if (warp - 2 < Cfg::kActiveEpiWarps) {
-        // ---------------- Epilogue: TMEM -> registers -> global ----------------
+        // ---------------- Epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced global ----------------
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which half of the tile's columns
-        const int r = q * 32 + lane;
+        const int half = (warp - 2) >> 2;             // which half of the unit's accumulator columns
+        uint8_t* stage = epi_smem + (warp - 2) * kEpiStageBytes;
+        const uint32_t stage_u32 = smem_u32(stage);
         const bool vec_ok = (((args.bias ? reinterpret_cast<uintptr_t>(args.bias) : 0) |
                               (args.scale ? reinterpret_cast<uintptr_t>(args.scale) : 0) |
                               (args.shift ? reinterpret_cast<uintptr_t>(args.shift) : 0) |
                               (args.mask ? reinterpret_cast<uintptr_t>(args.mask) : 0)) & 15) == 0 &&
                             (args.ldmask % 4 == 0);
+        const int lgR = 31 - __clz(R), lgW = 31 - __clz(args.GW);
+        const int wr_row = lane >> 2, wr_k = lane & 3;  // write-back role: 4 lanes per row, 16 bytes each
+        __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
         int j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
             const TileCoord tc = decode_tile(t, n_tiles, phases);
             const int acc = j & 1;
-            const long gm = static_cast<long>(tc.tile_m) * kTileM + r;
-            const bool row_ok = gm < args.M_total;
-            long opix = gm;
-            int img = 0;
+            const int row0 = tc.tile_m * kTileM + q * 32;   // first GEMM row of this warp
+            const int gm = row0 + lane;
+            // output row (pixel index) of this lane's GEMM row; for paired units: of its px = 0 pixel
+            int orow = gm, img = 0;
             if (mode != kPlain) {
-                img = static_cast<int>(gm / R);
+                img = gm >> lgR;
                 if (mode == kConvT) {
-                    const int rem = static_cast<int>(gm - static_cast<long>(img) * R);
-                    const int yh = rem / args.GW, xh = rem - yh * args.GW;
-                    opix = (static_cast<long>(img) * 2 * args.GH + 2 * yh + (tc.phase >> 1)) * (2 * args.GW) + 2 * xh +
-                           (tc.phase & 1);
+                    const int rem = gm & (R - 1);
+                    const int yh = rem >> lgW, xh = rem & (args.GW - 1);
+                    const int py = kPair ? tc.phase : (tc.phase >> 1), px = kPair ? 0 : (tc.phase & 1);
+                    orow = ((img * 2 * args.GH + 2 * yh + py) * 2 * args.GW) + 2 * xh + px;
                 }
             }
             mbar_wait(&tfull_bar[acc], (j >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = half * Cfg::kColsPerWarp; c0 < (half + 1) * Cfg::kColsPerWarp; c0 += 32) {
+                const int sub = kPair ? c0 / BN : 0;
+                const int n_base = tc.tile_n * BN + (kPair ? c0 - sub * BN : c0);
+                // ---- gate (saved activation at the output position): coalesced load, transposed through smem
+                uint4 gq[4];
+                if (args.gate) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = i * 8 + wr_row;
+                        const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
+                        gq[i] = make_uint4(0, 0, 0, 0);
+                        if (row0 + r < args.M_total)
+                            gq[i] = __ldg(reinterpret_cast<const uint4*>(args.gate + static_cast<size_t>(o) * args.ldo +
+                                                                         n_base + wr_k * 8));
+                    }
+                }
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols + c0, v);
                 tmem_ld_wait();
                 if (c0 + 32 >= (half + 1) * Cfg::kColsPerWarp) {
                     // last chunk of this warp is in registers: hand the accumulator back to the MMA issuer
@@ -306,86 +344,75 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK>::kCtasPerSm) conv_um
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-                const int n_base = tc.tile_n * BN + c0;
-                if (row_ok) {
-                    float f[32];
+                if (args.gate) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]);
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(stage + epi_off(i * 8 + wr_row, wr_k)) = gq[i];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gq[i] = *reinterpret_cast<const uint4*>(stage + epi_off(lane, i));
+                    __syncwarp();
+                }
+                uint4 packed[4];
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    float f[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) f[jj] = __uint_as_float(v[g8 * 8 + jj]);
+                    const int n8 = n_base + g8 * 8;
                     if (args.bias) {
-                        float b[32];
-                        if (vec_ok) {
-                            load_vec32(args.bias + n_base, b);
-                        } else {
+                        float b[8];
+                        load_vec8(args.bias + n8, vec_ok, b);
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) b[jj] = __ldg(args.bias + n_base + jj);
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] += b[jj];
+                        for (int jj = 0; jj < 8; ++jj) f[jj] += b[jj];
                     }
                     if (args.scale) {
-                        float sc[32], sh[32];
-                        if (vec_ok) {
-                            load_vec32(args.scale + n_base, sc);
-                            load_vec32(args.shift + n_base, sh);
-                        } else {
+                        float sc[8], sh[8];
+                        load_vec8(args.scale + n8, vec_ok, sc);
+                        load_vec8(args.shift + n8, vec_ok, sh);
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) {
-                                sc[jj] = __ldg(args.scale + n_base + jj);
-                                sh[jj] = __ldg(args.shift + n_base + jj);
-                            }
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] = fmaf(f[jj], sc[jj], sh[jj]);
+                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc[jj], sh[jj]);
                     }
                     if (args.act == kActRelu) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
                     } else if (args.act == kActLeaky) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
+                        for (int jj = 0; jj < 8; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
                     }
                     if (args.mask) {
-                        const float* mk = args.mask + static_cast<long>(img) * args.ldmask + n_base;
-                        float m[32];
-                        if (vec_ok) {
-                            load_vec32(mk, m);
-                        } else {
+                        float m[8];
+                        const int mi = gm < args.M_total ? img : 0;
+                        load_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m);
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) m[jj] = __ldg(mk + jj);
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] *= m[jj];
+                        for (int jj = 0; jj < 8; ++jj) f[jj] *= m[jj];
                     }
                     if (args.gate) {
-                        const uint4* gp = reinterpret_cast<const uint4*>(args.gate + opix * args.ldo + n_base);
+                        const uint32_t w4[4] = {gq[g8].x, gq[g8].y, gq[g8].z, gq[g8].w};
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const uint4 u = __ldg(gp + j4);
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int tt = 0; tt < 4; ++tt) {
-                                f[j4 * 8 + tt * 2] *= bf16_lo(w[tt]) > 0.f ? 1.f : args.slope;
-                                f[j4 * 8 + tt * 2 + 1] *= bf16_hi(w[tt]) > 0.f ? 1.f : args.slope;
-                            }
+                        for (int tt = 0; tt < 4; ++tt) {
+                            f[tt * 2] *= bf16_lo(w4[tt]) > 0.f ? 1.f : args.slope;
+                            f[tt * 2 + 1] *= bf16_hi(w4[tt]) > 0.f ? 1.f : args.slope;
                         }
                     }
-                    if (args.out_fp32) {
-                        float4* o = reinterpret_cast<float4*>(static_cast<float*>(args.out) + opix * args.ldo + n_base);
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            o[jj] = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
-                    } else {
-                        uint4* o =
-                            reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + opix * args.ldo + n_base);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            o[jj] = make_uint4(pack_bf16(f[8 * jj], f[8 * jj + 1]), pack_bf16(f[8 * jj + 2], f[8 * jj + 3]),
-                                               pack_bf16(f[8 * jj + 4], f[8 * jj + 5]),
-                                               pack_bf16(f[8 * jj + 6], f[8 * jj + 7]));
-                    }
+                    packed[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                            pack_bf16(f[6], f[7]));
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + epi_off(lane, i)) = packed[i];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + wr_row;
+                    const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
+                    const uint4 d = *reinterpret_cast<const uint4*>(stage + epi_off(r, wr_k));
+                    if (row0 + r < args.M_total)
+                        *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n_base + wr_k * 8) = d;
+                }
+                __syncwarp();
             }
         }
+        (void)stage_u32;
     }
     tc_fence_before();
     __syncthreads();
@@ -402,20 +429,20 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool kPair>
 static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, BK>;
+    using Cfg = ConvCfg<BN, BK, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, kPair>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(conv_umma<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
         attr_set = true;
     }
     const int slots = sm_count() * Cfg::kCtasPerSm;
     const int grid = total_tiles < slots ? total_tiles : slots;
     note_launch();
-    conv_umma_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
+    conv_umma_kernel<BN, BK, kPair><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("conv_umma<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
     return 0;
@@ -459,9 +486,12 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
         }
     }
     if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN)) return -1;
-    const int total_tiles = ((a.M_total + kTileM - 1) / kTileM) * (Cout / BN) * (mode == kConvT ? 4 : 1);
-#define SG_DISPATCH(bn, bk) \
-    if (BN == bn && BK == bk) return launch_cfg<bn, bk>(a, total_tiles, stream);
+    const bool pair = mode == kConvT && BN <= 128;
+    const int total_tiles = ((a.M_total + kTileM - 1) / kTileM) * (Cout / BN) * (mode == kConvT ? (pair ? 2 : 4) : 1);
+#define SG_DISPATCH(bn, bk)                                                   \
+    if (BN == bn && BK == bk)                                                 \
+        return pair ? launch_cfg<bn, bk, (bn <= 128)>(a, total_tiles, stream) \
+                    : launch_cfg<bn, bk, false>(a, total_tiles, stream);
     SG_DISPATCH(256, 64)
     SG_DISPATCH(128, 64)
     SG_DISPATCH(64, 64)
@@ -639,6 +669,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
+void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream) {
+    const long total = static_cast<long>(M) * N * 16;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    note_launch();
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, S, M, N, accumulate);
+}
+
+// sg_wgrad_thin.cu
+bool wgrad_thin_supported(int cH, int cW, int Mc, int Nf);
+int wgrad_thin_ctas(int nimg, int cH, int cW);
+int launch_wgrad_thin(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
+                      float* partial, float* dW, int accumulate, cudaStream_t stream);
+
 static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16) {
     // Aim for ~2 waves of 148 SMs, at least 8 K-tiles per CTA.
     const int base = m_tiles * n_tiles * taps;
@@ -653,6 +697,7 @@ static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16) {
 static int wgrad_bn(int Nf) { return Nf >= 256 ? 256 : (Nf >= 128 ? 128 : 64); }
 
 size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf) {
+    if (wgrad_thin_supported(cH, cW, Mc, Nf)) return static_cast<size_t>(wgrad_thin_ctas(nimg, cH, cW)) * 16 * Mc * Nf;
     const int k_tiles = (nimg * cH * cW + kWgK - 1) / kWgK;
     const int BN = wgrad_bn(Nf);
     const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN);
@@ -680,6 +725,12 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
                  float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream) {
     if (!is_pow2(cH) || !is_pow2(cW) || cW > kWgK) SG_FAIL("wgrad: coarse grid %dx%d unsupported", cH, cW);
     if (Mc % 8 != 0 || Nf % 8 != 0) SG_FAIL("wgrad: channels must be multiples of 8 (Mc=%d Nf=%d)", Mc, Nf);
+    if (wgrad_thin_supported(cH, cW, Mc, Nf)) {  // thin layers: every pixel row staged once, mma.sync + ldmatrix
+        if (wgrad_partial_floats(nimg, cH, cW, Mc, Nf) > partial_floats) SG_FAIL("wgrad: partial workspace too small");
+        if (launch_wgrad_thin(coarse, fine, nimg, cH, cW, Mc, Nf, partial, dW, accumulate, stream))
+            SG_FAIL("wgrad_thin launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.GH = cH;
@@ -708,11 +759,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     else
         rc = launch_wg<64>(a, grid, stream);
     if (rc) return rc;
-    const long total = static_cast<long>(Mc) * Nf * 16;
-    int blocks = static_cast<int>((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    note_launch();
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, a.splits, Mc, Nf, accumulate);
+    wgrad_reduce(partial, dW, a.splits, Mc, Nf, accumulate, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("wgrad_reduce launch: %s", cudaGetErrorString(e));
     return 0;

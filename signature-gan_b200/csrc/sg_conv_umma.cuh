@@ -29,9 +29,8 @@ struct ConvGemmArgs {
     int N_total;  // output channels
     int Cin;      // channels per tap (K = taps*Cin)
     // epilogue: v = acc (+bias[n]) ; (v = v*scale[n]+shift[n]) ; act ; (*mask[img][n]) ; (*gate')
-    void* out;  // bf16 (or fp32 when out_fp32) rows of `ldo` elements
+    void* out;  // bf16 rows of `ldo` elements
     int ldo;
-    int out_fp32;
     const float* bias;
     const float* scale;
     const float* shift;
@@ -40,7 +39,6 @@ struct ConvGemmArgs {
     const float* mask;  // [nimg][ldmask] dropout keep-scale, or null
     int ldmask;
     const __nv_bfloat16* gate;  // saved activation at the output position: v *= (g>0 ? 1 : slope)
-    float* colsum;              // optional [2][N_total]: per-column sum / sum of squares of v (atomic)
 };
 
 struct WgradArgs {
@@ -65,18 +63,6 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 // modes and 1 for kPlain. For kConvT all four phases are launched (grid.z = 4).
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs epi /* only epilogue fields read */, cudaStream_t stream);
-
-// Phase-fused transposed convolution for the thin, wide-grid layers (input grid width 16/32/64, Cout 32 or 64):
-// one CTA computes all four output parities of a 128-input-pixel tile, loading each input row block (with a
-// one-row halo) once per horizontal shift instead of once per filter tap; the 16 tap weight blocks stay resident
-// in shared memory when they fit (Cout = 32), else they are streamed through their own ring. Optionally emits
-// per-CTA partial sums (sum, sum of squares per channel) of the raw output for BatchNorm: `stats_partial` holds
-// [convt4_max_chunks()][2][Cout] floats, *stats_chunks receives the number of rows written.
-bool convt4_supported(int inH, int inW, int Cin, int Cout);
-int convt4_max_chunks();
-int launch_convt4(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW, int Cin, int Cout,
-                  ConvGemmArgs epi /* only epilogue fields read */, float* stats_partial, int* stats_chunks,
-                  cudaStream_t stream);
 
 // dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
 // `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.
