@@ -1,0 +1,288 @@
+// sg_dconv0.cu — the Discriminator's first block, Conv 4x4 s2 p1 from the 1-channel image to 64 channels
+// (disc…:134-139), forward / weight gradient / image gradient, bf16 tensor-core mode.
+//
+// K = 16 taps x 1 channel: one k-step of a 16x8x16 MMA. All three passes are HBM-bound (16 KB of image against
+// 128 KB of bf16 activations per 64x64 image; 2.1 MFLOP), but on the CUDA cores their 1 MFMA per image costs more
+// issue slots than the memory system needs time, so the contraction runs on warp-level mma.sync with fragments built
+// straight from global memory — the im2col gather of a 1-channel image is two floats per fragment register:
+//   forward : A = im2col(x) [16 pixels x 16 taps] from scalar loads, B = w [16 taps x 8 channels] in registers;
+//             bias + LeakyReLU + Dropout2d mask in the accumulator registers; tile transposed through swizzled
+//             shared memory and written as one contiguous 2 KB run (16 pixels x 64 channels, NHWC).
+//   wgrad   : dW[c][tap] = sum_pix dy[pix][c] * im2col(x)[pix][tap]. A = dy^T: the pixel-pair packing the fragment
+//             layout wants is done with PRMT on 16-byte loads (rows of the MMA are a permutation of the channels,
+//             undone when the partials are written); an extra all-ones B block yields the bias gradient.
+//   dgrad   : T[pix][tap] = sum_c dy[pix][c] * w[c][tap] per band of output rows into shared memory (k permuted so
+//             that A fragments are plain 16-byte loads), then dx = col2im(T): 4 reads per image pixel.
+#include "sg_elem.cuh"
+#include "sg_kernels.cuh"
+#include "sg_mma.cuh"
+
+namespace sg {
+namespace {
+
+constexpr int kC0 = 64;  // output channels of the first block (disc…:134)
+
+__global__ void __launch_bounds__(256)
+dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ mask, float slope, bf16* __restrict__ a, int B, int S) {
+    __shared__ __align__(16) uint8_t stage_all[8][2048];  // per warp: 16 pixels x 128 bytes, chunk-swizzled
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, t4 = lane & 3;
+    uint8_t* stage = stage_all[warp];
+    const int O = S / 2, lgO = ilog2(O), tpr = O / 16;
+    uint32_t bw[8][2];
+    float bs[8][2];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        const float* wp = w + (nb * 8 + gid) * 16 + 2 * t4;
+        bw[nb][0] = pack2_bf16(wp[0], wp[1]);
+        bw[nb][1] = pack2_bf16(wp[8], wp[9]);
+        bs[nb][0] = bias[nb * 8 + 2 * t4];
+        bs[nb][1] = bias[nb * 8 + 2 * t4 + 1];
+    }
+    const int ky0 = t4 >> 1, kxo = 2 * (t4 & 1);
+    const long total = static_cast<long>(B) * O * tpr;
+    for (long tile = static_cast<long>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<long>(gridDim.x) * 8) {
+        const int ox0 = static_cast<int>(tile % tpr) * 16;
+        const long r = tile / tpr;
+        const int oy = static_cast<int>(r) & (O - 1);
+        const long n = r >> lgO;
+        const float* xi = x + n * S * S;
+        uint32_t af[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int iy = 2 * oy - 1 + ky0 + 2 * h;
+            const bool yok = iy >= 0 && iy < S;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int ix = 2 * (ox0 + gid + 8 * rr) - 1 + kxo;
+                const float v0 = (yok && ix >= 0) ? __ldg(xi + iy * S + ix) : 0.f;
+                const float v1 = (yok && ix + 1 < S) ? __ldg(xi + iy * S + ix + 1) : 0.f;
+                af[h * 2 + rr] = pack2_bf16(v0, v1);
+            }
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+            mma_bf16(acc[nb], af, bw[nb][0], bw[nb][1]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            float m0 = 1.f, m1 = 1.f;
+            if (mask) {
+                const float2 mk = __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4));
+                m0 = mk.x;
+                m1 = mk.y;
+            }
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float t = acc[nb][e] + bs[nb][e & 1];
+                v[e] = (t > 0.f ? t : t * slope) * ((e & 1) ? m1 : m0);
+            }
+            const uint32_t off = static_cast<uint32_t>((nb ^ gid) << 4) + t4 * 4;   // (gid + 8) & 7 == gid
+            *reinterpret_cast<uint32_t*>(stage + gid * 128 + off) = pack2_bf16(v[0], v[1]);
+            *reinterpret_cast<uint32_t*>(stage + (gid + 8) * 128 + off) = pack2_bf16(v[2], v[3]);
+        }
+        __syncwarp();
+        bf16* dst = a + ((n * O + oy) * O + ox0) * kC0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = j * 4 + (lane >> 3), chunk = lane & 7;
+            const uint4 d = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+            *reinterpret_cast<uint4*>(dst + row * kC0 + chunk * 8) = d;
+        }
+        __syncwarp();
+    }
+}
+
+// partial[block][64*16 + 64]: dW in (c, tap) order followed by dbias.
+__global__ void __launch_bounds__(256)
+dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int B,
+                        int S) {
+    constexpr int NOUT = kC0 * 17;
+    __shared__ float red[8][NOUT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, t4 = lane & 3;
+    const int O = S / 2, lgO = ilog2(O), tpr = O / 16;
+    float acc[4][3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int nb = 0; nb < 3; ++nb) acc[i][nb][0] = acc[i][nb][1] = acc[i][nb][2] = acc[i][nb][3] = 0.f;
+    const uint32_t ones = gid == 0 ? 0x3F803F80u : 0u;  // B column 0 of the third block = 1.0: row sums = dbias
+    const int kx = gid & 3, kyb = gid >> 2;
+    const long total = static_cast<long>(B) * O * tpr;
+    for (long tile = static_cast<long>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<long>(gridDim.x) * 8) {
+        const int ox0 = static_cast<int>(tile % tpr) * 16;
+        const long r = tile / tpr;
+        const int oy = static_cast<int>(r) & (O - 1);
+        const long n = r >> lgO;
+        // dy: 8-channel chunk `gid` of pixels 2*t4, 2*t4+1, 2*t4+8, 2*t4+9 of the tile
+        const bf16* dp = dy + ((n * O + oy) * O + ox0) * kC0 + gid * 8;
+        const uint4 L0 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4) * kC0));
+        const uint4 L1 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 1) * kC0));
+        const uint4 L2 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 8) * kC0));
+        const uint4 L3 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 9) * kC0));
+        // im2col(x): taps gid (block 0) and 8 + gid (block 1) at the same four pixels
+        const float* xi = x + n * S * S;
+        uint32_t b[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int iy = 2 * oy - 1 + nb * 2 + kyb;
+            const bool yok = iy >= 0 && iy < S;
+            float v[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int px = 2 * t4 + (p & 1) + 8 * (p >> 1);
+                const int ix = 2 * (ox0 + px) - 1 + kx;
+                v[p] = (yok && ix >= 0 && ix < S) ? __ldg(xi + iy * S + ix) : 0.f;
+            }
+            b[nb][0] = pack2_bf16(v[0], v[1]);
+            b[nb][1] = pack2_bf16(v[2], v[3]);
+        }
+        const uint32_t l0[4] = {L0.x, L0.y, L0.z, L0.w}, l1[4] = {L1.x, L1.y, L1.z, L1.w};
+        const uint32_t l2[4] = {L2.x, L2.y, L2.z, L2.w}, l3[4] = {L3.x, L3.y, L3.z, L3.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // MMA row gid <-> channel 8*gid + 2*i (low halves), row gid + 8 <-> channel 8*gid + 2*i + 1 (high halves)
+            uint32_t af[4];
+            af[0] = __byte_perm(l0[i], l1[i], 0x5410);
+            af[1] = __byte_perm(l0[i], l1[i], 0x7632);
+            af[2] = __byte_perm(l2[i], l3[i], 0x5410);
+            af[3] = __byte_perm(l2[i], l3[i], 0x7632);
+            mma_bf16(acc[i][0], af, b[0][0], b[0][1]);
+            mma_bf16(acc[i][1], af, b[1][0], b[1][1]);
+            mma_bf16(acc[i][2], af, ones, ones);
+        }
+    }
+    float* rw = red[warp];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = 8 * gid + 2 * i;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int tap = nb * 8 + 2 * t4;
+            rw[c * 16 + tap] = acc[i][nb][0];
+            rw[c * 16 + tap + 1] = acc[i][nb][1];
+            rw[(c + 1) * 16 + tap] = acc[i][nb][2];
+            rw[(c + 1) * 16 + tap + 1] = acc[i][nb][3];
+        }
+        if (t4 == 0) {
+            rw[kC0 * 16 + c] = acc[i][2][0];
+            rw[kC0 * 16 + c + 1] = acc[i][2][2];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NOUT; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
+        partial[static_cast<long>(blockIdx.x) * NOUT + i] = s;
+    }
+}
+
+constexpr int kTPitch = 17;  // floats per pixel of the tap-sum tile (16 taps + 1: conflict-free col2im reads)
+
+__global__ void __launch_bounds__(256)
+dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S) {
+    extern __shared__ float T[];  // [(RB + 2)][O][kTPitch]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, t4 = lane & 3;
+    const int O = S / 2, tpr = O / 16, lgS = ilog2(S);
+    const int RB = 1024 / O;  // output rows per band (the whole 32x32 grid at 64x64)
+    const int bands = O / RB, units = B * bands;
+    // B fragments: k index 2*t4+e of step s <-> channel 8*t4 + 2*s + e; k index 8+2*t4+e <-> channel 32 + 8*t4 + 2*s + e
+    uint32_t bw[4][2][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int c = 8 * t4 + 2 * s, tap = nb * 8 + gid;
+            bw[s][nb][0] = pack2_bf16(w[c * 16 + tap], w[(c + 1) * 16 + tap]);
+            bw[s][nb][1] = pack2_bf16(w[(32 + c) * 16 + tap], w[(33 + c) * 16 + tap]);
+        }
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const long n = u / bands;
+        const int r0 = (u - static_cast<int>(n) * bands) * RB;
+        // ---- phase 1: T rows r0-1 .. r0+RB
+        const int ntile = (RB + 2) * tpr;
+        for (int tl = warp; tl < ntile; tl += 8) {
+            const int rr = tl / tpr, ox0 = (tl - rr * tpr) * 16;
+            const int oy = r0 - 1 + rr;
+            float acc[2][4];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+            if (oy >= 0 && oy < O) {
+                const bf16* dp = dy + ((n * O + oy) * O + ox0 + gid) * kC0 + t4 * 8;
+                const uint4 A0 = __ldg(reinterpret_cast<const uint4*>(dp));
+                const uint4 A1 = __ldg(reinterpret_cast<const uint4*>(dp + 32));
+                const uint4 A2 = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0));
+                const uint4 A3 = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0 + 32));
+                const uint32_t lo0[4] = {A0.x, A0.y, A0.z, A0.w}, hi0[4] = {A1.x, A1.y, A1.z, A1.w};
+                const uint32_t lo8[4] = {A2.x, A2.y, A2.z, A2.w}, hi8[4] = {A3.x, A3.y, A3.z, A3.w};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t af[4] = {lo0[s], lo8[s], hi0[s], hi8[s]};
+                    mma_bf16(acc[0], af, bw[s][0][0], bw[s][0][1]);
+                    mma_bf16(acc[1], af, bw[s][1][0], bw[s][1][1]);
+                }
+            }
+            float* t0 = T + (rr * O + ox0 + gid) * kTPitch + 2 * t4;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                t0[nb * 8] = acc[nb][0];
+                t0[nb * 8 + 1] = acc[nb][1];
+                t0[8 * kTPitch + nb * 8] = acc[nb][2];
+                t0[8 * kTPitch + nb * 8 + 1] = acc[nb][3];
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: dx rows 2*r0 .. 2*(r0+RB)-1; dx[iy][ix] = sum of the 2x2 (ky, kx) taps that reach it
+        const int npix = 2 * RB * S;
+        for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+            const int ix = i & (S - 1), iyl = i >> lgS, iy = 2 * r0 + iyl;
+            const int kya = (iy + 1) & 1, kxa = (ix + 1) & 1;
+            float s = 0.f;
+#pragma unroll
+            for (int ty = 0; ty < 2; ++ty) {
+                const int ky = kya + 2 * ty;
+                const int trow = ((iy + 1 - ky) >> 1) - (r0 - 1);   // 0 .. RB+1
+#pragma unroll
+                for (int tx = 0; tx < 2; ++tx) {
+                    const int kx = kxa + 2 * tx;
+                    const int ox = (ix + 1 - kx) >> 1;
+                    if (ox >= 0 && ox < O) s += T[(trow * O + ox) * kTPitch + ky * 4 + kx];
+                }
+            }
+            dx[(n * S + iy) * S + ix] = s;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+void dconv0_fwd_mma(const float* x, const float* w, const float* bias, const float* mask, float slope, bf16* a, int B,
+                    int S, cudaStream_t s) {
+    const long tiles = static_cast<long>(B) * (S / 2) * (S / 32);
+    note_launch();
+    dconv0_fwd_mma_kernel<<<blocks_for(tiles, 8, 148 * 8), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
+}
+int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s) {
+    const long tiles = static_cast<long>(B) * (S / 2) * (S / 32);
+    const int blocks = blocks_for(tiles, 8, 148 * 4);
+    note_launch();
+    dconv0_wgrad_mma_kernel<<<blocks, 256, 0, s>>>(x, dy, partial, B, S);
+    return blocks;
+}
+void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s) {
+    const int O = S / 2, RB = 1024 / O;
+    const int units = B * (O / RB);
+    const int smem = (RB + 2) * O * kTPitch * 4;
+    static bool ok = cudaFuncSetAttribute(dconv0_dgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) ==
+                     cudaSuccess;
+    (void)ok;
+    note_launch();
+    dconv0_dgrad_mma_kernel<<<units < 148 * 2 ? units : 148 * 2, 256, smem, s>>>(dy, w, dx, B, S);
+}
+
+}  // namespace sg

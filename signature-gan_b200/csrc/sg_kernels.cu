@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <type_traits>
 
 namespace sg {
 
@@ -422,6 +423,12 @@ d_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 template <typename T>
 void d_conv0(const float* x, const float* w, const float* bias, const float* mask, float slope, T* a, int B, int S,
              int C, cudaStream_t s) {
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (C == 64) {
+            dconv0_fwd_mma(x, w, bias, mask, slope, a, B, S, s);
+            return;
+        }
+    }
     const long total = static_cast<long>(B) * (S / 2) * (S / 8) * (C / 8);
     note_launch();
     d_conv0_kernel<T><<<blocks_for(total, 256, 148 * 16), 256, 17 * C * sizeof(float), s>>>(x, w, bias, mask, slope, a,
@@ -524,9 +531,13 @@ void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B
         return;
     }
     const long total = static_cast<long>(B) * (S / 2) * (S / 2);
-    const int chunks = blocks_for(total * 16, 256, kMaxChunks);
-    note_launch();
-    d_conv0_wgrad_kernel<T><<<chunks, 256, 0, s>>>(x, dy, partial, B, S);
+    int chunks = blocks_for(total * 16, 256, kMaxChunks);
+    if constexpr (std::is_same<T, bf16>::value) {
+        chunks = dconv0_wgrad_mma(x, dy, partial, B, S, s);
+    } else {
+        note_launch();
+        d_conv0_wgrad_kernel<T><<<chunks, 256, 0, s>>>(x, dy, partial, B, S);
+    }
     const int n = C * 17;
     // dW (C*16 floats) is immediately followed by dbias (C floats) in the flat gradient buffer
     vec_finalize(partial, chunks, n, dW, n, nullptr, s);
@@ -604,6 +615,10 @@ template <typename T>
 void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s) {
     if (C != 64) {
         snprintf(k_err, sizeof(k_err), "d_conv0_dgrad: C=%d unsupported (reference uses 64)", C);
+        return;
+    }
+    if constexpr (std::is_same<T, bf16>::value) {
+        dconv0_dgrad_mma(dy, w, dx, B, S, s);
         return;
     }
     const long threads = static_cast<long>(B) * (S / 2) * (S / 2) * 4;

@@ -91,6 +91,11 @@ template <typename T>
 void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s);
 template <typename T>
 void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s);
+// bf16 mode implementations of the three calls above (sg_dconv0.cu, warp-level mma.sync); C = 64 only.
+void dconv0_fwd_mma(const float* x, const float* w, const float* bias, const float* mask, float slope, bf16* a, int B,
+                    int S, cudaStream_t s);
+int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s);  // returns chunks
+void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s);
 // logit = <a, wp> + b ; prob = sigmoid(logit). a is [B][F] NHWC-flattened.
 template <typename T>
 void classifier_sigmoid(const T* a, const float* wp, const float* bias, float* prob, int B, int F, cudaStream_t s);

@@ -19,6 +19,7 @@
 // The kernel is HBM-bound by design: 64 KB + 256 KB per image for the 32 -> 32 block at 64x64.
 #include "sg_conv_umma.cuh"
 #include "sg_kernels.cuh"
+#include "sg_mma.cuh"
 #include "sg_umma.cuh"
 
 #include <cstdio>
@@ -49,19 +50,6 @@ struct WtCfg {
     static constexpr int kSlotBytes = kCoarseBytes + kFineBytesMax;
     static constexpr int kSmem = kWtSlots * kSlotBytes + 1024 /*zero rows*/ + 2 * kWtSlots * 8 + 1024 /*align*/;
 };
-
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-        "{%0, %1, %2, %3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 template <int MC>
 __device__ __forceinline__ void wt_issue(const WgradThinArgs& args, uint8_t* smem, uint64_t* full, uint64_t* empty,
