@@ -157,7 +157,10 @@ __device__ __forceinline__ void load_vec8(const float* p, bool vec_ok, float (&v
 // which makes both the row-per-lane and the 4-lanes-per-row access patterns bank-conflict free.
 __device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 64 + ((k ^ ((row >> 1) & 3)) << 4); }
 
-template <int BN, int BK, bool kPair>
+// kStats (paired transposed convolution only; there BN == N_total): the epilogue also accumulates per-channel sum and
+// sum of squares of the stored (bf16-rounded) outputs — the BatchNorm batch statistics of gen…:58 — and the CTA writes
+// one partial row stats_partial[blockIdx.x][2][BN], so that no separate pass over the convolution output is needed.
+template <int BN, int BK, bool kPair, bool kStats>
 __global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK, kPair>::kCtasPerSm)
 conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     using Cfg = ConvCfg<BN, BK, kPair>;
@@ -299,6 +302,12 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
         const int lgR = 31 - __clz(R), lgW = 31 - __clz(args.GW);
         const int wr_row = lane >> 2, wr_k = lane & 3;  // write-back role: 4 lanes per row, 16 bytes each
         __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
+        constexpr int NCH = Cfg::kColsPerWarp / 32;  // 32-column chunks per warp
+        float st_sum[kStats ? NCH : 1][8], st_sq[kStats ? NCH : 1][8];
+#pragma unroll
+        for (int ci = 0; ci < (kStats ? NCH : 1); ++ci)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) st_sum[ci][jj] = st_sq[ci][jj] = 0.f;
         int j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
             const TileCoord tc = decode_tile(t, n_tiles, phases);
@@ -318,8 +327,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
             }
             mbar_wait(&tfull_bar[acc], (j >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = half * Cfg::kColsPerWarp; c0 < (half + 1) * Cfg::kColsPerWarp; c0 += 32) {
+#pragma unroll(kStats ? NCH : 1)
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int c0 = half * Cfg::kColsPerWarp + ci * 32;
                 const int sub = kPair ? c0 / BN : 0;
                 const int n_base = tc.tile_n * BN + (kPair ? c0 - sub * BN : c0);
                 // ---- gate (saved activation at the output position): coalesced load, transposed through smem
@@ -406,16 +416,60 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                     const int r = i * 8 + wr_row;
                     const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
                     const uint4 d = *reinterpret_cast<const uint4*>(stage + epi_off(r, wr_k));
-                    if (row0 + r < args.M_total)
+                    if (row0 + r < args.M_total) {
                         *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n_base + wr_k * 8) = d;
+                        if (kStats) {
+                            const int cs = kStats ? ci : 0;
+                            const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt) {
+                                const float lo = bf16_lo(w4[tt]), hi = bf16_hi(w4[tt]);
+                                st_sum[cs][2 * tt] += lo;
+                                st_sq[cs][2 * tt] = fmaf(lo, lo, st_sq[cs][2 * tt]);
+                                st_sum[cs][2 * tt + 1] += hi;
+                                st_sq[cs][2 * tt + 1] = fmaf(hi, hi, st_sq[cs][2 * tt + 1]);
+                            }
+                        }
+                    }
                 }
                 __syncwarp();
             }
         }
         (void)stage_u32;
+        if (kStats) {
+            // lanes with equal wr_k hold partial sums of the same 8 channels; this warp's slot = [2][kColsPerWarp]
+            float* slot = reinterpret_cast<float*>(stage);
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    float a = st_sum[ci][jj], b = st_sq[ci][jj];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                    }
+                    if (lane < 4) {
+                        slot[ci * 32 + lane * 8 + jj] = a;
+                        slot[Cfg::kColsPerWarp + ci * 32 + lane * 8 + jj] = b;
+                    }
+                }
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kStats && warp >= 2) {
+        // paired units: every epilogue warp covered all BN channels (of one px); fold the 8 warps in a fixed order
+        const int e = (warp - 2) * 32 + lane;
+        if (e < 2 * BN) {
+            const int which = e / BN, ch = e - which * BN;
+            float tot = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < kEpiWarps; ++wi)
+                tot += reinterpret_cast<const float*>(epi_smem + wi * kEpiStageBytes)[which * Cfg::kColsPerWarp + ch];
+            args.stats_partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * BN + ch] = tot;
+        }
+    }
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
@@ -430,25 +484,39 @@ static int sm_count() {
 }
 
 template <int BN, int BK, bool kPair>
+static int conv_grid(int total_tiles) {
+    const int slots = sm_count() * ConvCfg<BN, BK, kPair>::kCtasPerSm;
+    return total_tiles < slots ? total_tiles : slots;
+}
+
+template <int BN, int BK, bool kPair, bool kStats = false>
 static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, BK, kPair>;
+    if (kPair && !kStats && a.stats_partial) return launch_cfg<BN, BK, kPair, kPair>(a, total_tiles, stream);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, kPair>,
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, kPair, kStats>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(conv_umma<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int slots = sm_count() * Cfg::kCtasPerSm;
-    const int grid = total_tiles < slots ? total_tiles : slots;
+    const int grid = conv_grid<BN, BK, kPair>(total_tiles);
     note_launch();
-    conv_umma_kernel<BN, BK, kPair><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
+    conv_umma_kernel<BN, BK, kPair, kStats><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("conv_umma<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
     return 0;
 }
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// Rows of stats_partial a kConvT launch will write (= its grid), or 0 when the configuration cannot fuse the statistics.
+int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
+    if (!(Cout == 32 || Cout == 64 || Cout == 128) || Cin % 32 != 0) return 0;
+    const int total_tiles = (nimg * inH * inW + kTileM - 1) / kTileM * 2;
+    const int slots = sm_count() * (Cout <= 64 ? 2 : 1);
+    return total_tiles < slots ? total_tiles : slots;
+}
 
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
@@ -487,6 +555,7 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
     }
     if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN)) return -1;
     const bool pair = mode == kConvT && BN <= 128;
+    if (a.stats_partial && !(pair && BN == Cout)) SG_FAIL("conv_gemm: fused statistics need a paired transposed convolution");
     const int total_tiles = ((a.M_total + kTileM - 1) / kTileM) * (Cout / BN) * (mode == kConvT ? (pair ? 2 : 4) : 1);
 #define SG_DISPATCH(bn, bk)                                                   \
     if (BN == bn && BK == bk)                                                 \

@@ -39,6 +39,7 @@ struct ConvGemmArgs {
     const float* mask;  // [nimg][ldmask] dropout keep-scale, or null
     int ldmask;
     const __nv_bfloat16* gate;  // saved activation at the output position: v *= (g>0 ? 1 : slope)
+    float* stats_partial;       // kConvT only, optional: [conv_gemm_stats_chunks()][2][N_total] per-CTA sum / sum of squares
 };
 
 struct WgradArgs {
@@ -63,6 +64,9 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 // modes and 1 for kPlain. For kConvT all four phases are launched (grid.z = 4).
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs epi /* only epilogue fields read */, cudaStream_t stream);
+
+// Number of partial rows a kConvT launch with `stats_partial` set writes, 0 if this shape cannot fuse the statistics.
+int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout);
 
 // dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
 // `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.

@@ -371,6 +371,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
         T* dst = reinterpret_cast<T*>(fuse ? w.a[i] : w.y[i]);
         const std::string nm = "g.up" + std::to_string(i);
         const double cflops = 2.0 * B * ih * ih * 16.0 * Cin * Cout;
+        int stat_chunks = 0;
         {
         PROF(nm.c_str(), cflops, es * ((double)B * ih * ih * Cin + (double)rows * Cout));
         if (kTC) {
@@ -379,6 +380,9 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
                 e.scale = w.scale[i + 1];
                 e.shift = w.shift[i + 1];
                 e.act = sg::kActRelu;
+            } else if (train) {
+                stat_chunks = sg::conv_gemm_stats_chunks(B, ih, ih, Cin, Cout);  // batch statistics from the epilogue
+                if (stat_chunks > 0) e.stats_partial = static_cast<float*>(c->cpart.p);
             }
             SG_UMMA(sg::launch_conv_gemm(sg::kConvT, reinterpret_cast<const bf16*>(in), c->g_packF[i], B, ih, ih, Cin,
                                          Cout, e, s));
@@ -390,9 +394,11 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
         }
         if (!fuse) {
             if (train) {
-                PROF((nm + ".bn_stats").c_str(), 0, es * (double)rows * Cout);
-                const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.y[i]), nullptr, nullptr, nullptr,
-                                                     nullptr, rows, Cout, static_cast<float*>(c->cpart.p), s);
+                PROF((nm + ".bn_stats").c_str(), 0, stat_chunks > 0 ? 0.0 : es * (double)rows * Cout);
+                const int chunks = stat_chunks > 0
+                                       ? stat_chunks
+                                       : sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.y[i]), nullptr, nullptr, nullptr,
+                                                           nullptr, rows, Cout, static_cast<float*>(c->cpart.p), s);
                 sg::bn_finalize(static_cast<float*>(c->cpart.p), chunks, rows, Cout, params + c->bn[i + 1].gamma_off,
                                 params + c->bn[i + 1].beta_off, stats + c->bn[i + 1].mean_off,
                                 stats + c->bn[i + 1].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 1, 0, w.mean[i + 1],
