@@ -510,8 +510,15 @@ static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t strea
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// sg_convt4.cu
+bool convt4_supported(int inH, int inW, int Cin, int Cout);
+int convt4_grid(int nimg, int inH, int inW);
+int launch_convt4(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW, int Cin, int Cout,
+                  __nv_bfloat16* out, const float* scale, const float* shift, float* stats_partial, cudaStream_t stream);
+
 // Rows of stats_partial a kConvT launch will write (= its grid), or 0 when the configuration cannot fuse the statistics.
 int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
+    if (convt4_supported(inH, inW, Cin, Cout)) return convt4_grid(nimg, inH, inW);
     if (!(Cout == 32 || Cout == 64 || Cout == 128) || Cin % 32 != 0) return 0;
     const int total_tiles = (nimg * inH * inW + kTileM - 1) / kTileM * 2;
     const int slots = sm_count() * (Cout <= 64 ? 2 : 1);
@@ -520,6 +527,14 @@ int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
 
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
+    if (mode == kConvT && convt4_supported(inH, inW, Cin, Cout) && !a.bias && !a.mask && !a.gate && a.ldo == Cout &&
+        (a.scale ? a.act == kActRelu : a.act == kActNone)) {
+        // thin wide-grid generator blocks: all four output parities per tile, halo-shared A, resident weights
+        if (launch_convt4(in, w_packed, nimg, inH, inW, Cin, Cout, static_cast<__nv_bfloat16*>(a.out), a.scale, a.shift,
+                          a.stats_partial, stream))
+            SG_FAIL("convt4 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     a.mode = mode;
     a.nimg = nimg;
     a.Cin = Cin;

@@ -360,6 +360,11 @@ int main(int argc, char** argv) {
     RUN(test_conv("convS2 1280x8x8x64->128 (160 t)", sg::kConvS2, 1280, 8, 8, 64, 128, true));
     RUN(test_conv("convT 700x4x4x64->64 (352 tiles)", sg::kConvT, 700, 4, 4, 64, 64, true));
     RUN(test_conv("plain 40000x64x256 (626 tiles)", sg::kPlain, 40000, 1, 1, 64, 256, true));
+    // phase-fused thin transposed convolutions (sg_convt4.cu): no bias/mask/gate epilogue
+    RUN(test_conv("convT4 6x32x32x32->32", sg::kConvT, 6, 32, 32, 32, 32, false));
+    RUN(test_conv("convT4 40x32x32x32->32 (320 t)", sg::kConvT, 40, 32, 32, 32, 32, false));
+    RUN(test_conv("convT4 5x16x16x64->32", sg::kConvT, 5, 16, 16, 64, 32, false));
+    RUN(test_conv("convT4 200x16x16x64->32 (400 t)", sg::kConvT, 200, 16, 16, 64, 32, false));
     RUN(test_wgrad("wgrad 8x16x16 128|64", 8, 16, 16, 128, 64));
     RUN(test_wgrad("wgrad 16x4x4 512|256", 16, 4, 4, 512, 256));
     RUN(test_wgrad("wgrad 8x8x8 256|128", 8, 8, 8, 256, 128));
