@@ -111,12 +111,18 @@ struct ConvCfg {
     static constexpr int kAccCols = kPair ? 2 * BN : BN;                  // columns of one accumulator buffer
     static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // double-buffered accumulator
     // Thin tiles are epilogue/latency-bound rather than MMA-bound: run two persistent CTAs per SM.
+    // Fat tiles (BN >= 128) run as clusters of two CTAs that work on M-adjacent tiles and share the weight tile: each
+    // CTA loads half of B and TMA-multicasts it to both, which removes a quarter to a third of the shared-memory
+    // fill traffic — the resource these kernels are bound by (L2 -> SM at ~64 B/clk against 128x256x64 MMA stages).
+    static constexpr int kCluster = BN >= 128 ? 2 : 1;
     static constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;   // (2 x kTmemCols <= 512 holds for BN <= 64, paired or not)
     static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 92 : 196) * 1024) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kColsPerWarp = kAccCols >= 64 ? kAccCols / 2 : kAccCols;
     static constexpr int kActiveEpiWarps = kAccCols >= 64 ? 8 : 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kTabEntries = 128;  // per-stage load table of the producer (<= 16 taps x 8 channel chunks)
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kTabEntries * 16 +
+                                      1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
     static constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of one swizzle atom
 };
@@ -168,7 +174,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
+    int4* tab = reinterpret_cast<int4*>(epi_smem + kEpiWarps * kEpiStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tab + Cfg::kTabEntries);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready for the epilogue
     uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained, MMA may overwrite
@@ -185,15 +192,20 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     const int num_k = taps * cc_n;
     const int R = args.GH * args.GW;
     const int n_tiles = args.N_total / BN;
-    const int m_tiles = (args.M_total + kTileM - 1) / kTileM;
+    constexpr int CL = Cfg::kCluster;
+    // schedule units are handed to clusters; CTA `rank` of a cluster takes M tile CL * unit.tile_m + rank (a tile
+    // index past the end is harmless: TMA zero-fills, the epilogue skips rows >= M_total)
+    const int m_tiles = ((args.M_total + kTileM - 1) / kTileM + CL - 1) / CL;
     const int total_tiles = m_tiles * n_tiles * phases;
+    const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int first_unit = blockIdx.x / CL, unit_step = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.amap[0]);
         tma_prefetch_desc(&args.bmap);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);   // every CTA of the cluster must have consumed the stage (multicast B)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -203,54 +215,87 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // The producer is ONE thread and its instruction stream is on the critical path of thin stages (a 128x128x64
+        // stage is 256 MMA cycles), so everything per-stage that can be tabulated is: entry e of the table holds, for
+        // the e-th K step of a unit, {A channel offset, packed(dx+1, dy+1, parity view), B k-offset}. Transposed
+        // convolutions keep one table section per output parity.
+        if (mode != kPlain) {
+            const int n_ent = (mode == kConvT ? 4 : 1) * num_k;
+            for (int e = lane; e < n_ent; e += 32) {
+                const int ph4 = e / num_k, it = e - ph4 * num_k;
+                const int tap = it / cc_n, cc = it - tap * cc_n;
+                int4 v;
+                v.x = cc * BK;
+                if (mode == kConvS2) {
+                    const int ky = tap >> 2, kx = tap & 3;
+                    const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
+                    const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+                    v.y = (dx + 1) | ((dy + 1) << 2) | ((yp * 2 + xp) << 4);
+                    v.z = it * BK;
+                } else {
+                    const int py = ph4 >> 1, px = ph4 & 1, ty = tap >> 1, tx = tap & 1;
+                    const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                    v.y = (px - tx + 1) | ((py - ty + 1) << 2);
+                    v.z = (ky * 4 + kx) * args.Cin + cc * BK;
+                }
+                v.w = 0;
+                tab[e] = v;
+            }
+        }
+        __syncwarp();
         if (lane == 0) {
             // ---------------- TMA producer ----------------
-            uint32_t g = 0;  // running stage counter across tiles
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(t, n_tiles, phases);
+            // B tile: whole (single CTA) or this CTA's half, multicast to both CTAs of the cluster
+            auto load_b = [&](uint8_t* sb, uint64_t* bar, int kc, int nc) {
+                if (CL == 1)
+                    tma_load_2d(sb, &args.bmap, bar, kc, nc);
+                else
+                    tma_load_2d_mc(sb + cta_rank * (Cfg::kBBytes / CL), &args.bmap, bar, kc, nc + cta_rank * (BN / CL),
+                                   static_cast<uint16_t>((1u << CL) - 1));
+            };
+            int s = 0;
+            uint32_t ph = 0;  // stage index / phase bit of the running stage counter
+            const int tpi = R >= kTileM ? R / kTileM : 1, bh = kTileM / args.GW, ipt = R >= kTileM ? 1 : kTileM / R;
+            for (int t = first_unit; t < total_tiles; t += unit_step) {
+                TileCoord tc = decode_tile(t, n_tiles, phases);
+                tc.tile_m = tc.tile_m * CL + cta_rank;
                 int n0 = 0, y0 = 0;
                 if (mode != kPlain) {
                     if (R >= kTileM) {
-                        const int tpi = R / kTileM;
                         n0 = tc.tile_m / tpi;
-                        y0 = (tc.tile_m % tpi) * (kTileM / args.GW);
+                        y0 = (tc.tile_m - n0 * tpi) * bh;
                     } else {
-                        n0 = tc.tile_m * (kTileM / R);
+                        n0 = tc.tile_m * ipt;
                     }
                 }
+                const int nb = tc.tile_n * BN;
 #pragma unroll 1
                 for (int sub = 0; sub < kSub; ++sub) {
-                    const int py = kPair ? tc.phase : (tc.phase >> 1), px = kPair ? sub : (tc.phase & 1);
-                    for (int it = 0; it < num_k; ++it, ++g) {
-                        const int s = g % STAGES;
-                        const uint32_t ph = (g / STAGES) & 1;
+                    const int ph4 = mode == kConvT ? (kPair ? tc.phase * 2 + sub : tc.phase) : 0;
+                    const int4* tp = tab + ph4 * num_k;
+#pragma unroll 1
+                    for (int it = 0; it < num_k; ++it) {
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         uint8_t* sa = smem + s * Cfg::kStageBytes;
                         uint8_t* sb = sa + Cfg::kABytes;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                         if (mode == kPlain) {
                             tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tc.tile_m * kTileM);
-                            tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
+                            load_b(sb, &full_bar[s], it * BK, nb);
                         } else {
-                            const int tap = it / cc_n, cc = it - tap * cc_n;
-                            if (mode == kConvS2) {
-                                const int ky = tap >> 2, kx = tap & 3;
-                                const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
-                                const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
-                                tma_load_4d(sa, &args.amap[yp * 2 + xp], &full_bar[s], cc * BK, dx, y0 + dy, n0);
-                                tma_load_2d(sb, &args.bmap, &full_bar[s], it * BK, tc.tile_n * BN);
-                            } else {
-                                const int ty = tap >> 1, tx = tap & 1;
-                                const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                                tma_load_4d(sa, &args.amap[0], &full_bar[s], cc * BK, px - tx, y0 + py - ty, n0);
-                                tma_load_2d(sb, &args.bmap, &full_bar[s], (ky * 4 + kx) * args.Cin + cc * BK,
-                                            tc.tile_n * BN);
-                            }
+                            const int4 e = tp[it];
+                            tma_load_4d(sa, &args.amap[(e.y >> 4) & 3], &full_bar[s], e.x, (e.y & 3) - 1,
+                                        y0 + ((e.y >> 2) & 3) - 1, n0);
+                            load_b(sb, &full_bar[s], e.z, nb);
+                        }
+                        if (++s == STAGES) {
+                            s = 0;
+                            ph ^= 1;
                         }
                     }
                 }
@@ -260,18 +305,18 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
-            uint32_t g = 0;
+            int s = 0;
+            uint32_t ph = 0;
             int j = 0;  // local tile counter
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
                 const int acc = j & 1;
                 mbar_wait(&tempty_bar[acc], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int sub = 0; sub < kSub; ++sub) {
                     const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols + sub * BN;
-                    for (int it = 0; it < num_k; ++it, ++g) {
-                        const int s = g % STAGES;
-                        const uint32_t ph = (g / STAGES) & 1;
+#pragma unroll 1
+                    for (int it = 0; it < num_k; ++it) {
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
@@ -282,7 +327,14 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                             const uint64_t db = make_smem_desc(b_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
                             umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0);
                         }
-                        umma_commit(&empty_bar[s]);
+                        if (CL == 1)
+                            umma_commit(&empty_bar[s]);
+                        else
+                            umma_commit_mc(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1));
+                        if (++s == STAGES) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
                 umma_commit(&tfull_bar[acc]);
@@ -309,8 +361,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) st_sum[ci][jj] = st_sq[ci][jj] = 0.f;
         int j = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
-            const TileCoord tc = decode_tile(t, n_tiles, phases);
+        for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
+            TileCoord tc = decode_tile(t, n_tiles, phases);
+            tc.tile_m = tc.tile_m * CL + cta_rank;
             const int acc = j & 1;
             const int row0 = tc.tile_m * kTileM + q * 32;   // first GEMM row of this warp
             const int gm = row0 + lane;
@@ -457,7 +510,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();  // (cluster: the peer may still multicast into / arrive on this CTA)
     if (kStats && warp >= 2) {
         // paired units: every epilogue warp covered all BN channels (of one px); fold the 8 warps in a fixed order
         const int e = (warp - 2) * 32 + lane;
@@ -483,10 +536,12 @@ static int sm_count() {
     return n;
 }
 
+// total_tiles counts schedule units (one per cluster); the grid is that many clusters, capped by the SM count.
 template <int BN, int BK, bool kPair>
 static int conv_grid(int total_tiles) {
-    const int slots = sm_count() * ConvCfg<BN, BK, kPair>::kCtasPerSm;
-    return total_tiles < slots ? total_tiles : slots;
+    using Cfg = ConvCfg<BN, BK, kPair>;
+    const int slots = sm_count() * Cfg::kCtasPerSm / Cfg::kCluster;
+    return (total_tiles < slots ? total_tiles : slots) * Cfg::kCluster;
 }
 
 template <int BN, int BK, bool kPair, bool kStats = false>
@@ -502,8 +557,21 @@ static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t strea
     }
     const int grid = conv_grid<BN, BK, kPair>(total_tiles);
     note_launch();
-    conv_umma_kernel<BN, BK, kPair, kStats><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = Cfg::kSmemBytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = Cfg::kCluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    lc.attrs = &attr;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, conv_umma_kernel<BN, BK, kPair, kStats>, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("conv_umma<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
     return 0;
 }
@@ -520,9 +588,10 @@ int launch_convt4(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int ni
 int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
     if (convt4_supported(inH, inW, Cin, Cout)) return convt4_grid(nimg, inH, inW);
     if (!(Cout == 32 || Cout == 64 || Cout == 128) || Cin % 32 != 0) return 0;
-    const int total_tiles = (nimg * inH * inW + kTileM - 1) / kTileM * 2;
-    const int slots = sm_count() * (Cout <= 64 ? 2 : 1);
-    return total_tiles < slots ? total_tiles : slots;
+    const int cl = Cout >= 128 ? 2 : 1;
+    const int units = (((nimg * inH * inW + kTileM - 1) / kTileM) + cl - 1) / cl * 2;
+    const int slots = sm_count() * (Cout <= 64 ? 2 : 1) / cl;
+    return (units < slots ? units : slots) * cl;
 }
 
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
@@ -568,10 +637,12 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
             if (make_map_nhwc(&a.amap[0], in, nimg, inH, inW, Cin, 1, 0, 0, BK, bw, bh, bn)) return -1;
         }
     }
-    if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN)) return -1;
+    const int cl = BN >= 128 ? 2 : 1;  // = ConvCfg::kCluster
+    if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN / cl)) return -1;
     const bool pair = mode == kConvT && BN <= 128;
     if (a.stats_partial && !(pair && BN == Cout)) SG_FAIL("conv_gemm: fused statistics need a paired transposed convolution");
-    const int total_tiles = ((a.M_total + kTileM - 1) / kTileM) * (Cout / BN) * (mode == kConvT ? (pair ? 2 : 4) : 1);
+    const int total_tiles = (((a.M_total + kTileM - 1) / kTileM + cl - 1) / cl) * (Cout / BN) *
+                            (mode == kConvT ? (pair ? 2 : 4) : 1);
 #define SG_DISPATCH(bn, bk)                                                   \
     if (BN == bn && BK == bk)                                                 \
         return pair ? launch_cfg<bn, bk, (bn <= 128)>(a, total_tiles, stream) \
@@ -622,8 +693,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
     const int tile_m = blockIdx.x;
     const int n_tiles = (args.Nf + BN - 1) / BN;
     const int taps = args.plain ? 1 : 16;
-    const int tap = blockIdx.y / n_tiles;
-    const int tile_n = blockIdx.y - tap * n_tiles;
+    // Narrow fine tensors (Nf < BN): the N dimension stacks tpc = BN/Nf filter taps, [tap][channel] — a 128 x 256 UMMA
+    // reads 96 B/clk of operands from shared memory where four 128 x 64 ones read 192 B/clk, the actual bound here.
+    const int tpc = args.tpc;                    // taps per CTA
+    const int apt = (BN / 64) / tpc;             // 64-channel atoms per tap
+    const int tap = (blockIdx.y / n_tiles) * tpc;  // first tap of this CTA
+    const int tile_n = blockIdx.y % n_tiles;
     const int split = blockIdx.z;
     const int kt_begin = static_cast<int>(static_cast<long>(args.k_tiles) * split / args.splits);
     const int kt_end = static_cast<int>(static_cast<long>(args.k_tiles) * (split + 1) / args.splits);
@@ -647,9 +722,18 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            const int ky = tap >> 2, kx = tap & 3;
-            const CUtensorMap* fm = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
-            const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+            // per 64-channel atom of B: tap -> parity view, shift and channel block (loop invariant)
+            const CUtensorMap* a_fm[BN / 64];
+            int a_dy[BN / 64], a_dx[BN / 64], a_ch[BN / 64];
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a) {
+                const int ta = tap + a / apt, cb = a % apt;
+                const int ky = ta >> 2, kx = ta & 3;
+                a_fm[a] = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
+                a_dy[a] = ((ky + 1) >> 1) - 1;
+                a_dx[a] = ((kx + 1) >> 1) - 1;
+                a_ch[a] = tile_n * BN + cb * 64;
+            }
             for (int it = 0; it < num_k; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -677,7 +761,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
                 } else {
 #pragma unroll
                     for (int a = 0; a < BN / 64; ++a)
-                        tma_load_4d(sb + a * Cfg::kAtomBytes, fm, &full_bar[s], tile_n * BN + a * 64, dx, y0 + dy, n0);
+                        tma_load_4d(sb + a * Cfg::kAtomBytes, a_fm[a], &full_bar[s], a_ch[a], a_dx[a], y0 + a_dy[a], n0);
                 }
             }
         }
@@ -709,9 +793,11 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        float* dst = args.partial + ((static_cast<size_t>(split) * taps + tap) * args.Mc + m) * args.Nf;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int atom = c0 >> 6;
+            const int ta = tap + atom / apt;
+            float* dst = args.partial + ((static_cast<size_t>(split) * taps + ta) * args.Mc + m) * args.Nf;
             uint32_t v[32];
             if (num_k > 0) {
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
@@ -720,7 +806,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0;
             }
-            const int n_base = tile_n * BN + c0;
+            const int n_base = tile_n * BN + (atom % apt) * 64 + (c0 & 63);
             if (m < args.Mc && n_base < args.Nf) {
                 float4* o = reinterpret_cast<float4*>(dst + n_base);
 #pragma unroll
@@ -778,13 +864,15 @@ static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16) {
     return s;
 }
 
-static int wgrad_bn(int Nf) { return Nf >= 256 ? 256 : (Nf >= 128 ? 128 : 64); }
+static int wgrad_bn(int Nf) { return Nf >= 64 ? 256 : 64; }
+static int fc_wgrad_bn(int Kp) { return Kp >= 256 ? 256 : (Kp >= 128 ? 128 : 64); }
+static int wgrad_tpc(int Nf) { return Nf == 64 ? 4 : (Nf == 128 ? 2 : 1); }  // filter taps stacked along N per CTA
 
 size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf) {
     if (wgrad_thin_supported(cH, cW, Mc, Nf)) return static_cast<size_t>(wgrad_thin_ctas(nimg, cH, cW)) * 16 * Mc * Nf;
     const int k_tiles = (nimg * cH * cW + kWgK - 1) / kWgK;
     const int BN = wgrad_bn(Nf);
-    const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN);
+    const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN, 16 / wgrad_tpc(Nf));
     return static_cast<size_t>(s) * 16 * Mc * Nf;
 }
 
@@ -826,7 +914,8 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     a.k_tiles = static_cast<int>((pix + kWgK - 1) / kWgK);
     const int BN = wgrad_bn(Nf);
     const int m_tiles = (Mc + 127) / 128, n_tiles = (Nf + BN - 1) / BN;
-    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles);
+    a.tpc = wgrad_tpc(Nf);
+    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 16 / a.tpc);
     a.partial = partial;
     if (static_cast<size_t>(a.splits) * 16 * Mc * Nf > partial_floats) SG_FAIL("wgrad: partial workspace too small");
     if (make_map_2d(&a.cmap, coarse, Mc, pix, Mc, 64, kWgK)) return -1;
@@ -834,7 +923,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     const uint32_t bw = cW, bh = R >= kWgK ? kWgK / cW : cH, bn = R >= kWgK ? 1 : kWgK / R;
     for (int p = 0; p < 4; ++p)
         if (make_map_nhwc(&a.fmap[p], fine, nimg, 2 * cH, 2 * cW, Nf, 2, p >> 1, p & 1, 64, bw, bh, bn)) return -1;
-    dim3 grid(m_tiles, 16 * n_tiles, a.splits);
+    dim3 grid(m_tiles, (16 / a.tpc) * n_tiles, a.splits);
     int rc;
     if (BN == 256)
         rc = launch_wg<256>(a, grid, stream);
@@ -866,7 +955,7 @@ __global__ void fc_wgrad_reduce_kernel(const float* __restrict__ partial, float*
 
 size_t fc_wgrad_partial_floats(int B, int F, int Kp) {
     const int k_tiles = (B + kWgK - 1) / kWgK;
-    const int BN = wgrad_bn(Kp);
+    const int BN = fc_wgrad_bn(Kp);
     const int s = wgrad_splits(k_tiles, (F + 127) / 128, (Kp + BN - 1) / BN, 1);
     return static_cast<size_t>(s) * F * Kp;
 }
@@ -877,13 +966,14 @@ int launch_fc_wgrad(const __nv_bfloat16* dy, const __nv_bfloat16* zp, int B, int
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.plain = 1;
+    a.tpc = 1;
     a.GH = 1;
     a.GW = kWgK;
     a.nimg = B;
     a.Mc = F;
     a.Nf = Kp;
     a.k_tiles = (B + kWgK - 1) / kWgK;
-    const int BN = wgrad_bn(Kp);
+    const int BN = fc_wgrad_bn(Kp);
     const int m_tiles = (F + 127) / 128, n_tiles = (Kp + BN - 1) / BN;
     a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 1);
     a.partial = partial;

@@ -50,6 +50,7 @@ struct WgradArgs {
     int k_tiles;          // ceil(nimg*GH*GW / 64)
     int splits;
     int plain;            // 1: no taps, fmap[0] is a 2-D [pixels][Nf] map (Generator fc weight gradient)
+    int tpc;              // filter taps stacked along N per CTA (1, 2 or 4)
     float* partial;  // [splits][16][Mc][Nf]
 };
 
