@@ -16,6 +16,8 @@
 #include "sg_umma.cuh"
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace sg {
 namespace {
@@ -394,9 +396,24 @@ bool set_smem(K kernel, int bytes) {
 
 }  // namespace
 
+// sg_gfinal_mma.cu
+void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
+                    uint8_t* out_u8, int B, int S, cudaStream_t s);
+int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
+                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, cudaStream_t s);
+
+// SIGGAN_GFINAL=stencil keeps the bf16 path on the streaming-stencil kernels (A/B comparison in the harness).
+static bool use_stencil_bf16() {
+    static const bool v = [] {
+        const char* e = getenv("SIGGAN_GFINAL");
+        return e && !strcmp(e, "stencil");
+    }();
+    return v;
+}
+
 template <typename T>
-void final_conv_tanh(const T* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
-                     uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
+void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift, const float* w, const float* bias,
+                             float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
     if (C != kFC || S % kStripW != 0) return;  // sg_create only admits 64 / 128 with 32 channels at the last level
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
@@ -412,15 +429,11 @@ void final_conv_tanh(const T* in, const float* scale, const float* shift, const 
         gfinal_fwd_kernel<T, false><<<grid, kThreadsG, Cfg::kSmem, s>>>(in, scale, shift, w, bias, out, out_u8, B, S);
     }
 }
-template void final_conv_tanh<float>(const float*, const float*, const float*, const float*, const float*, float*,
-                                     uint8_t*, int, int, int, cudaStream_t);
-template void final_conv_tanh<bf16>(const bf16*, const float*, const float*, const float*, const float*, float*,
-                                    uint8_t*, int, int, int, cudaStream_t);
 
 template <typename T>
-int final_conv_bwd(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
-                   const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S, int C,
-                   cudaStream_t s) {
+int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
+                           const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
+                           int C, cudaStream_t s) {
     if (C != kFC || S % kStripW != 0) return 0;
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
@@ -432,9 +445,46 @@ int final_conv_bwd(const float* dout, const float* out, const T* y, const float*
     vec_finalize(part_w, grid, 9 * kFC + 1, dW, 9 * kFC, dbias, s);
     return grid;
 }
-template int final_conv_bwd<float>(const float*, const float*, const float*, const float*, const float*, const float*,
-                                   float*, float*, float*, float*, float*, int, int, int, cudaStream_t);
-template int final_conv_bwd<bf16>(const float*, const float*, const bf16*, const float*, const float*, const float*,
-                                  bf16*, float*, float*, float*, float*, int, int, int, cudaStream_t);
+
+template void final_conv_tanh_stencil<float>(const float*, const float*, const float*, const float*, const float*, float*,
+                                             uint8_t*, int, int, int, cudaStream_t);
+template void final_conv_tanh_stencil<bf16>(const bf16*, const float*, const float*, const float*, const float*, float*,
+                                            uint8_t*, int, int, int, cudaStream_t);
+template int final_conv_bwd_stencil<float>(const float*, const float*, const float*, const float*, const float*,
+                                           const float*, float*, float*, float*, float*, float*, int, int, int,
+                                           cudaStream_t);
+template int final_conv_bwd_stencil<bf16>(const float*, const float*, const bf16*, const float*, const float*,
+                                          const float*, bf16*, float*, float*, float*, float*, int, int, int,
+                                          cudaStream_t);
+
+template <>
+void final_conv_tanh<float>(const float* in, const float* scale, const float* shift, const float* w, const float* bias,
+                            float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
+    final_conv_tanh_stencil<float>(in, scale, shift, w, bias, out, out_u8, B, S, C, s);
+}
+template <>
+void final_conv_tanh<bf16>(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias,
+                           float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
+    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128))
+        return final_conv_tanh_stencil<bf16>(in, scale, shift, w, bias, out, out_u8, B, S, C, s);
+    gfinal_fwd_mma(in, scale, shift, w, bias, out, out_u8, B, S, s);
+}
+
+template <>
+int final_conv_bwd<float>(const float* dout, const float* out, const float* y, const float* scale, const float* shift,
+                          const float* w, float* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B,
+                          int S, int C, cudaStream_t s) {
+    return final_conv_bwd_stencil<float>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, s);
+}
+template <>
+int final_conv_bwd<bf16>(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
+                         const float* w, bf16* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
+                         int C, cudaStream_t s) {
+    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128))
+        return final_conv_bwd_stencil<bf16>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, s);
+    const int grid = gfinal_bwd_mma(dout, out, y, scale, shift, w, dbn, part_w, part_bn, B, S, s);
+    vec_finalize(part_w, grid, 9 * kFC + 1, dW, 9 * kFC, dbias, s);
+    return grid;
+}
 
 }  // namespace sg

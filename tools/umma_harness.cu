@@ -10,6 +10,21 @@
 #include <vector>
 
 #include "../signature-gan_b200/csrc/sg_conv_umma.cuh"
+#include "../signature-gan_b200/csrc/sg_kernels.cuh"
+
+namespace sg {
+template <typename T>
+void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift, const float* w, const float* bias,
+                             float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s);
+template <typename T>
+int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
+                           const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
+                           int C, cudaStream_t s);
+void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
+                    uint8_t* out_u8, int B, int S, cudaStream_t s);
+int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
+                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, cudaStream_t s);
+}  // namespace sg
 
 using bf16 = __nv_bfloat16;
 
@@ -259,6 +274,114 @@ static int test_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
     return bad;
 }
 
+// ---- Generator tail (Conv3x3 32->1 + tanh) forward / backward: mma.sync kernels against the streaming stencils
+static float* dev_f32(const std::vector<float>& h) {
+    float* d;
+    CK(cudaMalloc(&d, h.size() * 4));
+    CK(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    return d;
+}
+static std::vector<float> fetch_f32(const float* d, size_t n) {
+    std::vector<float> h(n);
+    CK(cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost));
+    return h;
+}
+static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
+    const size_t px = (size_t)B * S * S;
+    Dev y;
+    y.init(px * 32, 2.0f);
+    std::vector<float> sc(32), sh(32), w(288), bias(1, 0.05f), dout(px);
+    for (int i = 0; i < 32; ++i) {
+        sc[i] = 0.6f + 0.4f * frand();
+        sh[i] = 0.3f * frand();
+    }
+    for (auto& v : w) v = 0.08f * frand();
+    for (auto& v : dout) v = frand();
+    float *d_sc = dev_f32(sc), *d_sh = dev_f32(sh), *d_w = dev_f32(w), *d_b = dev_f32(bias), *d_dout = dev_f32(dout);
+    float *out_a, *out_b, *pw, *pbn_a, *pbn_b, *dW_a, *dW_b;
+    uint8_t *u8_a, *u8_b;
+    bf16 *dbn_a, *dbn_b;
+    CK(cudaMalloc(&out_a, px * 4));
+    CK(cudaMalloc(&out_b, px * 4));
+    CK(cudaMalloc(&u8_a, px));
+    CK(cudaMalloc(&u8_b, px));
+    CK(cudaMalloc(&dbn_a, px * 64));
+    CK(cudaMalloc(&dbn_b, px * 64));
+    CK(cudaMalloc(&pw, (size_t)sg::kMaxChunks * 289 * 4));
+    CK(cudaMalloc(&pbn_a, (size_t)sg::kMaxChunks * 64 * 4));
+    CK(cudaMalloc(&pbn_b, (size_t)sg::kMaxChunks * 64 * 4));
+    CK(cudaMalloc(&dW_a, 289 * 4));
+    CK(cudaMalloc(&dW_b, 289 * 4));
+    const float* scp = affine ? d_sc : nullptr;
+    const float* shp = affine ? d_sh : nullptr;
+    sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, u8_a, B, S, 32, 0);
+    sg::gfinal_fwd_mma(y.d, scp, shp, d_w, d_b, out_b, u8_b, B, S, 0);
+    CK(cudaDeviceSynchronize());
+    int bad = 0;
+    char nm[128];
+    snprintf(nm, sizeof(nm), "%s fwd", name);
+    bad += report(nm, fetch_f32(out_b, px), fetch_f32(out_a, px), 8e-3f);
+    {
+        std::vector<uint8_t> a(px), b(px);
+        CK(cudaMemcpy(a.data(), u8_a, px, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b.data(), u8_b, px, cudaMemcpyDeviceToHost));
+        size_t off = 0;
+        for (size_t i = 0; i < px; ++i) off += abs((int)a[i] - (int)b[i]) > 2;
+        printf("%-34s u8 mismatches(>2)=%zu %s\n", nm, off, off ? "FAIL" : "PASS");
+        bad += off != 0;
+    }
+    if (affine) {
+        const int ca = sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw,
+                                                        pbn_a, B, S, 32, 0);
+        const int cb = sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0);
+        sg::vec_finalize(pw, cb, 289, dW_b, 288, dW_b + 288, 0);
+        CK(cudaDeviceSynchronize());
+        snprintf(nm, sizeof(nm), "%s bwd dbn", name);
+        bad += report(nm, fetch_bf16(dbn_b, px * 32), fetch_bf16(dbn_a, px * 32), 1.5e-2f);
+        const double nscale = sqrt((double)px);
+        snprintf(nm, sizeof(nm), "%s bwd dW,dbias", name);
+        bad += report(nm, fetch_f32(dW_b, 289), fetch_f32(dW_a, 289), (float)(2e-3 * nscale + 1e-3));
+        auto fold = [&](const float* p, int chunks) {
+            std::vector<float> h = fetch_f32(p, (size_t)chunks * 64), r(64, 0.f);
+            for (int c = 0; c < chunks; ++c)
+                for (int i = 0; i < 64; ++i) r[i] += h[(size_t)c * 64 + i];
+            return r;
+        };
+        snprintf(nm, sizeof(nm), "%s bwd bn sums", name);
+        bad += report(nm, fold(pbn_b, cb), fold(pbn_a, ca), (float)(4e-3 * nscale + 1e-3));
+    }
+    if (perf) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float ms[4];
+        for (int k = 0; k < 4; ++k) {
+            for (int i = 0; i < 13; ++i) {
+                if (i == 3) cudaEventRecord(e0);
+                if (k == 0) sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, nullptr, B, S, 32, 0);
+                if (k == 1) sg::gfinal_fwd_mma(y.d, scp, shp, d_w, d_b, out_b, nullptr, B, S, 0);
+                if (k == 2 && affine)
+                    sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw, pbn_a,
+                                                     B, S, 32, 0);
+                if (k == 3 && affine) sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0);
+            }
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            cudaEventElapsedTime(&ms[k], e0, e1);
+            ms[k] /= 10;
+        }
+        const double gb_f = px * (64.0 + 4.0) * 1e-9, gb_b = px * (128.0 + 8.0) * 1e-9;
+        printf("PERF %-24s fwd stencil %.3f ms (%.0f GB/s) mma %.3f ms (%.0f GB/s) | bwd stencil %.3f ms (%.0f GB/s) mma %.3f ms (%.0f GB/s)\n",
+               name, ms[0], gb_f / ms[0] * 1e3, ms[1], gb_f / ms[1] * 1e3, ms[2], gb_b / ms[2] * 1e3, ms[3],
+               gb_b / ms[3] * 1e3);
+    }
+    for (void* p : {(void*)d_sc, (void*)d_sh, (void*)d_w, (void*)d_b, (void*)d_dout, (void*)out_a, (void*)out_b, (void*)pw,
+                    (void*)pbn_a, (void*)pbn_b, (void*)dW_a, (void*)dW_b, (void*)u8_a, (void*)u8_b, (void*)dbn_a,
+                    (void*)dbn_b})
+        cudaFree(p);
+    return bad;
+}
+
 static bool want(const char* name);
 static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout) {
     if (!want(name)) return;
@@ -371,6 +494,10 @@ int main(int argc, char** argv) {
     RUN(test_wgrad("wgrad 2x32x32 32|32 (thin)", 2, 32, 32, 32, 32));
     RUN(test_wgrad("wgrad 3x16x16 64|32 (thin)", 3, 16, 16, 64, 32));
     RUN(test_wgrad("wgrad 5x4x4 256|128 (tail)", 5, 4, 4, 256, 128));
+    RUN(test_gfinal("gfinal 5x64 train", 5, 64, true, false));
+    RUN(test_gfinal("gfinal 3x64 eval", 3, 64, false, false));
+    RUN(test_gfinal("gfinal 3x128 train", 3, 128, true, false));
+    RUN(test_gfinal("gfinal 700x64 train (multi-image CTAs)", 700, 64, true, false));
     printf("harness: %d failing tests\n", fails);
     if (argc > 1 && (!strcmp(argv[1], "perf") || perfonly) && fails == 0) {
         const int B = 4096;
@@ -388,6 +515,10 @@ int main(int argc, char** argv) {
         perf_wgrad("wgrad c2 256|128 @8x8", B, 8, 8, 256, 128);
         perf_wgrad("wgrad c1 128|64 @16x16", B, 16, 16, 128, 64);
         perf_wgrad("wgrad up3 32|32 @32x32", B, 32, 32, 32, 32);
+        if (want("gfinal")) {
+            test_gfinal("gfinal 4096x64", B, 64, true, true);
+            test_gfinal("gfinal 1024x128", 1024, 128, true, true);
+        }
     }
     return fails ? 1 : 0;
 }
