@@ -400,7 +400,8 @@ bool set_smem(K kernel, int bytes) {
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
                     uint8_t* out_u8, int B, int S, cudaStream_t s);
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
-                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, cudaStream_t s);
+                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s);
 
 // SIGGAN_GFINAL=stencil keeps the bf16 path on the streaming-stencil kernels (A/B comparison in the harness).
 static bool use_stencil_bf16() {
@@ -482,9 +483,17 @@ int final_conv_bwd<bf16>(const float* dout, const float* out, const bf16* y, con
                          int C, cudaStream_t s) {
     if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128))
         return final_conv_bwd_stencil<bf16>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, s);
-    const int grid = gfinal_bwd_mma(dout, out, y, scale, shift, w, dbn, part_w, part_bn, B, S, s);
+    const int grid = gfinal_bwd_mma(dout, out, y, scale, shift, w, dbn, part_w, part_bn, B, S, dbn ? 0 : 1, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, s);
     vec_finalize(part_w, grid, 9 * kFC + 1, dW, 9 * kFC, dbias, s);
     return grid;
+}
+
+bool final_conv_bwd_two_pass(int S, int C) { return !use_stencil_bf16() && C == kFC && (S == 64 || S == 128); }
+void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
+                          const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
+                          const float* k3, bf16* dy, int B, int S, cudaStream_t s) {
+    gfinal_bwd_mma(dout, out, y, scale, shift, w, dy, nullptr, nullptr, B, S, 2, mean, rstd, k1, k2, k3, s);
 }
 
 }  // namespace sg

@@ -212,11 +212,20 @@ struct BwdCfg {
     static constexpr int kSmem = kDpBytes + kStageBytes + kRedBytes;
 };
 
-template <int S>
+// MODE 0: one pass — masked d(bn output) written to dbn, plus dW / dbias / (sum d, sum d*y) partial rows.
+// MODE 1: reductions only (nothing written per pixel).  MODE 2: recompute d and write the BatchNorm-backward result
+//         dy = k1 * (d - k2 - xhat * k3) directly (bn_bwd_apply folded in): with batch statistics the two passes
+//         1 + 2 move 3 activation-sized tensors through HBM where pass 0 + bn_bwd_apply move 5.
+struct BnBwdCoef {
+    const float *mean, *rstd, *k1, *k2, *k3;
+};
+template <int S, int MODE>
 __global__ void __launch_bounds__(kThr, 2)
 gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ dout, const float* __restrict__ outimg, const float* __restrict__ w,
-                      bf16* __restrict__ dbn, float* __restrict__ part_w, float* __restrict__ part_bn, int B) {
+                      bf16* __restrict__ dbn, float* __restrict__ part_w, float* __restrict__ part_bn, int B,
+                      const BnBwdCoef coef) {
+    constexpr bool kSums = MODE != 2, kWrite = MODE != 1, kApply = MODE == 2;
     using Cfg = BwdCfg<S>;
     constexpr int pitch = Cfg::kPitch;
     constexpr int lgS = S == 64 ? 6 : 7;
@@ -244,6 +253,19 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
     for (int j = 0; j < 8; ++j) {
         sc[j] = scale[8 * t + j];
         sh[j] = shift[8 * t + j];
+    }
+    // MODE 2: dy = k1*d + cA*y + cB per channel
+    float k1v[8], cA[8], cB[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        k1v[j] = cA[j] = cB[j] = 0.f;
+        if (kApply) {
+            const int ch = 8 * t + j;
+            const float k1 = coef.k1[ch], g = k1 * coef.k3[ch] * coef.rstd[ch];
+            k1v[j] = k1;
+            cA[j] = -g;
+            cB[j] = g * coef.mean[ch] - k1 * coef.k2[ch];
+        }
     }
     float accw[4][4], s0[8], s1[8], dsum = 0.f;
 #pragma unroll
@@ -320,18 +342,29 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
             for (int j = 0; j < 4; ++j) {
                 float cd[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_bf16(cd, A, bd[j][0], bd[j][1]);
-                const float e0 = a0[2 * j] > 0.f ? cd[0] : 0.f, e1 = a0[2 * j + 1] > 0.f ? cd[1] : 0.f;
-                const float f0 = a1[2 * j] > 0.f ? cd[2] : 0.f, f1 = a1[2 * j + 1] > 0.f ? cd[3] : 0.f;
-                s0[2 * j] += e0 + f0;
-                s0[2 * j + 1] += e1 + f1;
-                s1[2 * j] = fmaf(e0, y0[2 * j], fmaf(f0, y1[2 * j], s1[2 * j]));
-                s1[2 * j + 1] = fmaf(e1, y0[2 * j + 1], fmaf(f1, y1[2 * j + 1], s1[2 * j + 1]));
+                float e0 = a0[2 * j] > 0.f ? cd[0] : 0.f, e1 = a0[2 * j + 1] > 0.f ? cd[1] : 0.f;
+                float f0 = a1[2 * j] > 0.f ? cd[2] : 0.f, f1 = a1[2 * j + 1] > 0.f ? cd[3] : 0.f;
+                if (kSums) {
+                    s0[2 * j] += e0 + f0;
+                    s0[2 * j + 1] += e1 + f1;
+                    s1[2 * j] = fmaf(e0, y0[2 * j], fmaf(f0, y1[2 * j], s1[2 * j]));
+                    s1[2 * j + 1] = fmaf(e1, y0[2 * j + 1], fmaf(f1, y1[2 * j + 1], s1[2 * j + 1]));
+                }
+                if (kApply) {
+                    e0 = fmaf(k1v[2 * j], e0, fmaf(cA[2 * j], y0[2 * j], cB[2 * j]));
+                    e1 = fmaf(k1v[2 * j + 1], e1, fmaf(cA[2 * j + 1], y0[2 * j + 1], cB[2 * j + 1]));
+                    f0 = fmaf(k1v[2 * j], f0, fmaf(cA[2 * j], y1[2 * j], cB[2 * j]));
+                    f1 = fmaf(k1v[2 * j + 1], f1, fmaf(cA[2 * j + 1], y1[2 * j + 1], cB[2 * j + 1]));
+                }
                 o0[j] = pack2_bf16(e0, e1);
                 o1[j] = pack2_bf16(f0, f1);
             }
-            bf16* dst = dbn + (static_cast<size_t>(n) * S * S + pix0 + gid) * kC + t * 8;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-            *reinterpret_cast<uint4*>(dst + 8 * kC) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            if (kWrite) {
+                bf16* dst = dbn + (static_cast<size_t>(n) * S * S + pix0 + gid) * kC + t * 8;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                *reinterpret_cast<uint4*>(dst + 8 * kC) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            }
+            if (!kSums) continue;
             // ---- weight gradient: [taps][16 pixels] x [16 pixels][32 channels]
             uint32_t AW[4];
             AW[0] = pack2_bf16(dpp[2 * t + offW], dpp[2 * t + 1 + offW]);
@@ -347,6 +380,7 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
         }
     }
     cp_async_wait<0>();
+    if (!kSums) return;
     // ---- reduction: lanes of equal t hold partial (sum d, sum d*y) of channels 8t..8t+7
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
@@ -431,20 +465,32 @@ void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, cons
 #undef SG_GF_LAUNCH
 }
 
-// Returns the number of partial rows written to part_w ([chunks][9*32+1]) and part_bn ([chunks][2][32]).
+// mode 0 / 1 / 2: see gfinal_bwd_mma_kernel. Returns the number of partial rows written to part_w ([chunks][9*32+1])
+// and part_bn ([chunks][2][32]) (modes 0 and 1).
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
-                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, cudaStream_t s) {
+                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s) {
     note_launch();
-    int grid;
+    const BnBwdCoef coef{mean, rstd, k1, k2, k3};
+    int grid = 0;
+#define SG_GB_LAUNCH(SZ, MD)                                                                                          \
+    do {                                                                                                              \
+        static int per_b = -1, g_cache = 0;                                                                           \
+        if (per_b != B) {                                                                                             \
+            g_cache = grid_for(gfinal_bwd_mma_kernel<SZ, MD>, BwdCfg<SZ>::kSmem, B);                                  \
+            if (g_cache > kMaxChunks) g_cache = kMaxChunks;                                                           \
+            per_b = B;                                                                                                \
+        }                                                                                                             \
+        grid = g_cache;                                                                                               \
+        gfinal_bwd_mma_kernel<SZ, MD><<<grid, kThr, BwdCfg<SZ>::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, \
+                                                                           part_bn, B, coef);                         \
+    } while (0)
     if (S == 64) {
-        grid = grid_for(gfinal_bwd_mma_kernel<64>, BwdCfg<64>::kSmem, B);
-        if (grid > kMaxChunks) grid = kMaxChunks;
-        gfinal_bwd_mma_kernel<64><<<grid, kThr, BwdCfg<64>::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, part_bn, B);
+        if (mode == 0) SG_GB_LAUNCH(64, 0); else if (mode == 1) SG_GB_LAUNCH(64, 1); else SG_GB_LAUNCH(64, 2);
     } else {
-        grid = grid_for(gfinal_bwd_mma_kernel<128>, BwdCfg<128>::kSmem, B);
-        if (grid > kMaxChunks) grid = kMaxChunks;
-        gfinal_bwd_mma_kernel<128><<<grid, kThr, BwdCfg<128>::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, part_bn, B);
+        if (mode == 0) SG_GB_LAUNCH(128, 0); else if (mode == 1) SG_GB_LAUNCH(128, 1); else SG_GB_LAUNCH(128, 2);
     }
+#undef SG_GB_LAUNCH
     return grid;
 }
 

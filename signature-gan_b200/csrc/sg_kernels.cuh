@@ -81,6 +81,13 @@ int final_conv_bwd(const float* dout, const float* out, const T* y, const float*
                    const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S, int C,
                    cudaStream_t s);
 void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na, float* out_b, cudaStream_t s);
+// bf16 two-pass form (sg_gfinal_mma.cu): final_conv_bwd with dbn == nullptr computes only the reductions (nothing is
+// written per pixel); after bn_bwd_finalize, final_conv_bwd_apply recomputes d from y and writes the
+// BatchNorm-backward result dy = k1*(d - k2 - xhat*k3) directly — 3 activation-sized HBM passes instead of 5.
+bool final_conv_bwd_two_pass(int S, int C);
+void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
+                          const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
+                          const float* k3, bf16* dy, int B, int S, cudaStream_t s);
 
 // ---- discriminator side ----------------------------------------------------------------------
 // Conv 4x4 s2 p1, 1 -> C channels (disc…:134-139) with bias + LeakyReLU + dropout mask.

@@ -445,10 +445,13 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
     // BatchNorm-backward reductions of the last block (so that block needs no separate reduction pass below).
     float* part_bn = cpart + static_cast<size_t>(sg::kMaxChunks) * (9 * c->gch[L] + 1);
     int last_chunks = 0;
+    // bf16 with batch statistics: pass 1 = reductions only, pass 2 (below) recomputes d and applies BatchNorm backward
+    const bool two_pass = kTC && train && sg::final_conv_bwd_two_pass(c->S, c->gch[L]);
     {
-    PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L], (double)B * c->S * c->S * (8.0 + 2.0 * es * c->gch[L]));
+    PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L],
+         (double)B * c->S * c->S * (8.0 + (two_pass ? 1.0 : 2.0) * es * c->gch[L]));
     last_chunks = sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.y[L - 1]), w.scale[L], w.shift[L],
-                                        params + c->gt[c->g_final_w].offset, reinterpret_cast<T*>(cur),
+                                        params + c->gt[c->g_final_w].offset, two_pass ? nullptr : reinterpret_cast<T*>(cur),
                                         grads + c->gt[c->g_final_w].offset, grads + c->gt[c->g_final_b].offset, cpart,
                                         part_bn, B, c->S, c->gch[L], s);
     }
@@ -469,7 +472,12 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
             sg::bn_bwd_finalize(cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], nullptr, train, 0,
                                 grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
         }
-        {
+        if (i == L - 1 && two_pass) {
+            PROF((nm + ".bn_bwd_apply").c_str(), 4.0 * B * c->S * c->S * 9.0 * Cout, 2.0 * es * (double)rows * Cout);
+            sg::final_conv_bwd_apply(grad_image, w.out, reinterpret_cast<const bf16*>(w.y[i]), w.scale[L], w.shift[L],
+                                     params + c->gt[c->g_final_w].offset, w.mean[L], w.rstd[L], c->k1, c->k2, c->k3,
+                                     reinterpret_cast<bf16*>(cur), B, c->S, s);
+        } else {
         PROF((nm + ".bn_bwd_apply").c_str(), 0, 3.0 * es * (double)rows * Cout);
         sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]), w.mean[i + 1],
                             w.rstd[i + 1], c->k1, c->k2, c->k3, reinterpret_cast<T*>(cur), rows, Cout, s);

@@ -23,7 +23,8 @@ int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, cons
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
                     uint8_t* out_u8, int B, int S, cudaStream_t s);
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
-                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, cudaStream_t s);
+                   const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s);
 }  // namespace sg
 
 using bf16 = __nv_bfloat16;
@@ -333,7 +334,8 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
     if (affine) {
         const int ca = sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw,
                                                         pbn_a, B, S, 32, 0);
-        const int cb = sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0);
+        const int cb = sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0, nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, 0);
         sg::vec_finalize(pw, cb, 289, dW_b, 288, dW_b + 288, 0);
         CK(cudaDeviceSynchronize());
         snprintf(nm, sizeof(nm), "%s bwd dbn", name);
@@ -349,6 +351,50 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
         };
         snprintf(nm, sizeof(nm), "%s bwd bn sums", name);
         bad += report(nm, fold(pbn_b, cb), fold(pbn_a, ca), (float)(4e-3 * nscale + 1e-3));
+        // two-pass form: mode 1 (reductions only) must reproduce mode 0's sums; mode 2 = mode 0 + bn_bwd_apply
+        std::vector<float> r0 = fold(pbn_b, cb), w0 = fetch_f32(dW_b, 289);
+        CK(cudaMemset(pbn_b, 0, (size_t)sg::kMaxChunks * 64 * 4));
+        const int c1 = sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, nullptr, pw, pbn_b, B, S, 1, nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, 0);
+        sg::vec_finalize(pw, c1, 289, dW_b, 288, dW_b + 288, 0);
+        CK(cudaDeviceSynchronize());
+        snprintf(nm, sizeof(nm), "%s bwd pass1 sums", name);
+        bad += report(nm, fold(pbn_b, c1), r0, 1e-6f);
+        snprintf(nm, sizeof(nm), "%s bwd pass1 dW", name);
+        bad += report(nm, fetch_f32(dW_b, 289), w0, 1e-6f);
+        std::vector<float> mean(32), rstd(32), k1(32), k2(32), k3(32);
+        for (int i = 0; i < 32; ++i) {
+            mean[i] = 0.2f * frand();
+            rstd[i] = 0.9f + 0.3f * frand();
+            k1[i] = 1.0f + 0.2f * frand();
+            k2[i] = 0.01f * frand();
+            k3[i] = 0.02f * frand();
+        }
+        float *d_mean = dev_f32(mean), *d_rstd = dev_f32(rstd), *d_k1 = dev_f32(k1), *d_k2 = dev_f32(k2), *d_k3 = dev_f32(k3);
+        sg::bn_bwd_apply<bf16>(dbn_a, y.d, d_mean, d_rstd, d_k1, d_k2, d_k3, dbn_a, (long)px, 32, 0);
+        sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, nullptr, nullptr, B, S, 2, d_mean, d_rstd, d_k1, d_k2,
+                           d_k3, 0);
+        CK(cudaDeviceSynchronize());
+        snprintf(nm, sizeof(nm), "%s bwd pass2 dy", name);
+        bad += report(nm, fetch_bf16(dbn_b, px * 32), fetch_bf16(dbn_a, px * 32), 1.5e-2f);
+        if (perf) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            float m1, m2;
+            for (int k = 1; k <= 2; ++k) {
+                for (int i = 0; i < 13; ++i) {
+                    if (i == 3) cudaEventRecord(e0);
+                    sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, k == 1 ? nullptr : dbn_b, pw, pbn_b, B, S, k, d_mean,
+                                       d_rstd, d_k1, d_k2, d_k3, 0);
+                }
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                cudaEventElapsedTime(k == 1 ? &m1 : &m2, e0, e1);
+            }
+            printf("PERF %-24s bwd pass1 (sums) %.3f ms, pass2 (apply) %.3f ms\n", name, m1 / 10, m2 / 10);
+        }
+        for (float* p : {d_mean, d_rstd, d_k1, d_k2, d_k3}) cudaFree(p);
     }
     if (perf) {
         cudaEvent_t e0, e1;
@@ -363,7 +409,9 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
                 if (k == 2 && affine)
                     sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw, pbn_a,
                                                      B, S, 32, 0);
-                if (k == 3 && affine) sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0);
+                if (k == 3 && affine)
+                    sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, 0);
             }
             cudaEventRecord(e1);
             CK(cudaDeviceSynchronize());
