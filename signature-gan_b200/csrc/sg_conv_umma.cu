@@ -11,6 +11,7 @@
 #include "sg_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -120,9 +121,8 @@ struct ConvCfg {
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kColsPerWarp = kAccCols >= 64 ? kAccCols / 2 : kAccCols;
     static constexpr int kActiveEpiWarps = kAccCols >= 64 ? 8 : 4;
-    static constexpr int kTabEntries = 128;  // per-stage load table of the producer (<= 16 taps x 8 channel chunks)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kTabEntries * 16 +
-                                      1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ +
+                                      256 /*barriers*/;
     static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
     static constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of one swizzle atom
 };
@@ -174,14 +174,13 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;
-    int4* tab = reinterpret_cast<int4*>(epi_smem + kEpiWarps * kEpiStageBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tab + Cfg::kTabEntries);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready for the epilogue
     uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained, MMA may overwrite
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const int mode = args.mode;
     const int cc_n = args.Cin / BK;
@@ -220,67 +219,43 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // The producer is ONE thread and its instruction stream is on the critical path of thin stages (a 128x128x64
-        // stage is 256 MMA cycles), so everything per-stage that can be tabulated is: entry e of the table holds, for
-        // the e-th K step of a unit, {A channel offset, packed(dx+1, dy+1, parity view), B k-offset}. Transposed
-        // convolutions keep one table section per output parity.
-        if (mode != kPlain) {
-            const int n_ent = (mode == kConvT ? 4 : 1) * num_k;
-            for (int e = lane; e < n_ent; e += 32) {
-                const int ph4 = e / num_k, it = e - ph4 * num_k;
-                const int tap = it / cc_n, cc = it - tap * cc_n;
-                int4 v;
-                v.x = cc * BK;
-                if (mode == kConvS2) {
-                    const int ky = tap >> 2, kx = tap & 3;
-                    const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
-                    const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
-                    v.y = (dx + 1) | ((dy + 1) << 2) | ((yp * 2 + xp) << 4);
-                    v.z = it * BK;
+        // ---------------- TMA producer: whole warp in uniform control flow, one elected lane issues ----------------
+        // A thin stage (128 x 128 x 64) is 256 MMA cycles, so the producer's instruction stream is on the critical path:
+        // everything per-stage is tabulated on the host (args.tab, read with uniform constant loads) and the loop runs
+        // converged so that coordinates, shared-memory and barrier addresses stay in uniform registers.
+        const bool issuer = elect_one();
+        // B tile: whole (single CTA) or this CTA's half, multicast to both CTAs of the cluster
+        auto load_b = [&](uint8_t* sb, uint64_t* bar, int kc, int nc) {
+            if (CL == 1)
+                tma_load_2d(sb, &args.bmap, bar, kc, nc);
+            else
+                tma_load_2d_mc(sb + cta_rank * (Cfg::kBBytes / CL), &args.bmap, bar, kc, nc + cta_rank * (BN / CL),
+                               static_cast<uint16_t>((1u << CL) - 1));
+        };
+        int s = 0;
+        uint32_t ph = 0;  // stage index / phase bit of the running stage counter
+        const int tpi = R >= kTileM ? R / kTileM : 1, bh = kTileM / args.GW, ipt = R >= kTileM ? 1 : kTileM / R;
+        for (int t = first_unit; t < total_tiles; t += unit_step) {
+            TileCoord tc = decode_tile(t, n_tiles, phases);
+            tc.tile_m = tc.tile_m * CL + cta_rank;
+            int n0 = 0, y0 = 0;
+            if (mode != kPlain) {
+                if (R >= kTileM) {
+                    n0 = tc.tile_m / tpi;
+                    y0 = (tc.tile_m - n0 * tpi) * bh;
                 } else {
-                    const int py = ph4 >> 1, px = ph4 & 1, ty = tap >> 1, tx = tap & 1;
-                    const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                    v.y = (px - tx + 1) | ((py - ty + 1) << 2);
-                    v.z = (ky * 4 + kx) * args.Cin + cc * BK;
+                    n0 = tc.tile_m * ipt;
                 }
-                v.w = 0;
-                tab[e] = v;
             }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            // B tile: whole (single CTA) or this CTA's half, multicast to both CTAs of the cluster
-            auto load_b = [&](uint8_t* sb, uint64_t* bar, int kc, int nc) {
-                if (CL == 1)
-                    tma_load_2d(sb, &args.bmap, bar, kc, nc);
-                else
-                    tma_load_2d_mc(sb + cta_rank * (Cfg::kBBytes / CL), &args.bmap, bar, kc, nc + cta_rank * (BN / CL),
-                                   static_cast<uint16_t>((1u << CL) - 1));
-            };
-            int s = 0;
-            uint32_t ph = 0;  // stage index / phase bit of the running stage counter
-            const int tpi = R >= kTileM ? R / kTileM : 1, bh = kTileM / args.GW, ipt = R >= kTileM ? 1 : kTileM / R;
-            for (int t = first_unit; t < total_tiles; t += unit_step) {
-                TileCoord tc = decode_tile(t, n_tiles, phases);
-                tc.tile_m = tc.tile_m * CL + cta_rank;
-                int n0 = 0, y0 = 0;
-                if (mode != kPlain) {
-                    if (R >= kTileM) {
-                        n0 = tc.tile_m / tpi;
-                        y0 = (tc.tile_m - n0 * tpi) * bh;
-                    } else {
-                        n0 = tc.tile_m * ipt;
-                    }
-                }
-                const int nb = tc.tile_n * BN;
+            const int nb = tc.tile_n * BN;
 #pragma unroll 1
-                for (int sub = 0; sub < kSub; ++sub) {
-                    const int ph4 = mode == kConvT ? (kPair ? tc.phase * 2 + sub : tc.phase) : 0;
-                    const int4* tp = tab + ph4 * num_k;
+            for (int sub = 0; sub < kSub; ++sub) {
+                const int ph4 = mode == kConvT ? (kPair ? tc.phase * 2 + sub : tc.phase) : 0;
+                const int tbase = ph4 * num_k;
 #pragma unroll 1
-                    for (int it = 0; it < num_k; ++it) {
-                        mbar_wait(&empty_bar[s], ph ^ 1);
+                for (int it = 0; it < num_k; ++it) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (issuer) {
                         uint8_t* sa = smem + s * Cfg::kStageBytes;
                         uint8_t* sb = sa + Cfg::kABytes;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
@@ -288,39 +263,40 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                             tma_load_2d(sa, &args.amap[0], &full_bar[s], it * BK, tc.tile_m * kTileM);
                             load_b(sb, &full_bar[s], it * BK, nb);
                         } else {
-                            const int4 e = tp[it];
+                            const int4 e = args.tab[tbase + it];
                             tma_load_4d(sa, &args.amap[(e.y >> 4) & 3], &full_bar[s], e.x, (e.y & 3) - 1,
                                         y0 + ((e.y >> 2) & 3) - 1, n0);
                             load_b(sb, &full_bar[s], e.z, nb);
                         }
-                        if (++s == STAGES) {
-                            s = 0;
-                            ph ^= 1;
-                        }
+                    }
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
-            int s = 0;
-            uint32_t ph = 0;
-            int j = 0;  // local tile counter
-            for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
-                const int acc = j & 1;
-                mbar_wait(&tempty_bar[acc], ((j >> 1) & 1) ^ 1);
-                tc_fence_after();
+        // ---------------- MMA issuer: whole warp in uniform control flow, one elected lane issues ----------------
+        constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+        const bool issuer = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        int j = 0;  // local tile counter
+        for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
+            const int acc = j & 1;
+            mbar_wait(&tempty_bar[acc], ((j >> 1) & 1) ^ 1);
+            tc_fence_after();
 #pragma unroll 1
-                for (int sub = 0; sub < kSub; ++sub) {
-                    const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols + sub * BN;
+            for (int sub = 0; sub < kSub; ++sub) {
+                const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols + sub * BN;
 #pragma unroll 1
-                    for (int it = 0; it < num_k; ++it) {
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                        const uint32_t b_addr = a_addr + Cfg::kABytes;
+                for (int it = 0; it < num_k; ++it) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+                    if (issuer) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t da = make_smem_desc(a_addr + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
@@ -331,14 +307,14 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                             umma_commit(&empty_bar[s]);
                         else
                             umma_commit_mc(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1));
-                        if (++s == STAGES) {
-                            s = 0;
-                            ph ^= 1;
-                        }
+                    }
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1;
                     }
                 }
-                umma_commit(&tfull_bar[acc]);
             }
+            if (issuer) umma_commit(&tfull_bar[acc]);
         }
     } else if (warp - 2 < Cfg::kActiveEpiWarps) {
         // ---------------- Epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced global ----------------
@@ -594,8 +570,27 @@ int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
     return (units < slots ? units : slots) * cl;
 }
 
+// sg_conv2_umma.cu
+bool conv2_supported(ConvMode mode, int inH, int inW, int Cin, int Cout);
+int launch_conv2(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
+                 int Cin, int Cout, const ConvGemmArgs& e, cudaStream_t stream);
+static bool conv2_enabled() {  // SIGGAN_CONV2=0 keeps every layer on the one-CTA kernels (A/B comparison)
+    static const bool v = [] {
+        const char* e = getenv("SIGGAN_CONV2");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
+    if (mode != kPlain && !a.stats_partial && a.ldo == Cout && conv2_enabled() &&
+        conv2_supported(mode, inH, inW, Cin, Cout)) {
+        // CTA-pair kernel with shared shifted-input tiles (D conv1 forward, D conv1 / conv2 data gradients)
+        if (launch_conv2(mode, in, w_packed, nimg, inH, inW, Cin, Cout, a, stream))
+            SG_FAIL("conv2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     if (mode == kConvT && convt4_supported(inH, inW, Cin, Cout) && !a.bias && !a.mask && !a.gate && a.ldo == Cout &&
         (a.scale ? a.act == kActRelu : a.act == kActNone)) {
         // thin wide-grid generator blocks: all four output parities per tile, halo-shared A, resident weights
@@ -635,6 +630,31 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
                 if (make_map_nhwc(&a.amap[p], in, nimg, inH, inW, Cin, 2, p >> 1, p & 1, BK, bw, bh, bn)) return -1;
         } else {
             if (make_map_nhwc(&a.amap[0], in, nimg, inH, inW, Cin, 1, 0, 0, BK, bw, bh, bn)) return -1;
+        }
+    }
+    if (mode != kPlain) {  // producer schedule (see ConvGemmArgs::tab)
+        const int cc_n = Cin / BK, num_k = taps * cc_n / (mode == kConvT ? 4 : 1);
+        const int n_ent = (mode == kConvT ? 4 : 1) * num_k;
+        if (n_ent > 128) SG_FAIL("conv_gemm: schedule of %d entries does not fit", n_ent);
+        for (int e = 0; e < n_ent; ++e) {
+            const int ph4 = e / num_k, it = e - ph4 * num_k;
+            const int tap = it / cc_n, cc = it - tap * cc_n;
+            int4 v;
+            v.x = cc * BK;
+            if (mode == kConvS2) {
+                const int ky = tap >> 2, kx = tap & 3;
+                const int yp = (ky + 1) & 1, xp = (kx + 1) & 1;
+                const int dy = ((ky + 1) >> 1) - 1, dx = ((kx + 1) >> 1) - 1;
+                v.y = (dx + 1) | ((dy + 1) << 2) | ((yp * 2 + xp) << 4);
+                v.z = it * BK;
+            } else {
+                const int py = ph4 >> 1, px = ph4 & 1, ty = tap >> 1, tx = tap & 1;
+                const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                v.y = (px - tx + 1) | ((py - ty + 1) << 2);
+                v.z = (ky * 4 + kx) * Cin + cc * BK;
+            }
+            v.w = 0;
+            a.tab[e] = v;
         }
     }
     const int cl = BN >= 128 ? 2 : 1;  // = ConvCfg::kCluster

@@ -40,6 +40,10 @@ struct ConvGemmArgs {
     int ldmask;
     const __nv_bfloat16* gate;  // saved activation at the output position: v *= (g>0 ? 1 : slope)
     float* stats_partial;       // kConvT only, optional: [conv_gemm_stats_chunks()][2][N_total] per-CTA sum / sum of squares
+    // Producer schedule (filled by launch_conv_gemm): entry e of a section = {A channel offset, packed (dx+1) | (dy+1)<<2 |
+    // parity view<<4, B k-offset, 0} for the e-th K step; transposed convolutions keep one section per output parity.
+    // It lives in the parameter (constant) bank so that the producer warp reads it with uniform loads.
+    int4 tab[128];
 };
 
 struct WgradArgs {

@@ -131,6 +131,23 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
         "h"(cta_mask)
         : "memory");
 }
+// One lane of the (converged) warp gets true. The single-thread roles (TMA producer, MMA issuer) run their loops on the
+// WHOLE warp and guard only the issuing instructions with this: in uniform control flow the compiler keeps stage
+// counters, shared-memory descriptors and barrier addresses in uniform registers, so a tcgen05.mma costs ~3 issue slots;
+// inside an `if (lane == 0)` region every operand goes through an ELECT / R2UR.BROADCAST waterfall (~20 instructions,
+// ~100 cycles per MMA — more than a 128 x 128 x 16 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Warp index as a provably warp-uniform value (the role dispatch must not look divergent to the compiler).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -542,6 +542,13 @@ int main(int argc, char** argv) {
     RUN(test_wgrad("wgrad 2x32x32 32|32 (thin)", 2, 32, 32, 32, 32));
     RUN(test_wgrad("wgrad 3x16x16 64|32 (thin)", 3, 16, 16, 64, 32));
     RUN(test_wgrad("wgrad 5x4x4 256|128 (tail)", 5, 4, 4, 256, 128));
+    // CTA-pair kernels (sg_conv2_umma.cu): D conv1 forward and the D conv1 / conv2 data-gradient shapes, with tails
+    RUN(test_conv("conv2 S2 3x32x32x64->128 +epi", sg::kConvS2, 3, 32, 32, 64, 128, true));
+    RUN(test_conv("conv2 S2 161x32x32x64->128", sg::kConvS2, 161, 32, 32, 64, 128, true));
+    RUN(test_conv("conv2 T4 5x16x16x128->64 +epi", sg::kConvT, 5, 16, 16, 128, 64, true));
+    RUN(test_conv("conv2 T4 171x16x16x128->64", sg::kConvT, 171, 16, 16, 128, 64, false));
+    RUN(test_conv("conv2 T2 7x8x8x256->128 +epi", sg::kConvT, 7, 8, 8, 256, 128, true));
+    RUN(test_conv("conv2 T2 341x8x8x256->128", sg::kConvT, 341, 8, 8, 256, 128, true));
     RUN(test_gfinal("gfinal 5x64 train", 5, 64, true, false));
     RUN(test_gfinal("gfinal 3x64 eval", 3, 64, false, false));
     RUN(test_gfinal("gfinal 3x128 train", 3, 128, true, false));
