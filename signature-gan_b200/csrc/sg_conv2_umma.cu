@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int GW = args.GW, R = args.GH * GW;
     const int m_tiles = (args.M_total + 127) / 128;
@@ -207,66 +207,72 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer (both CTAs; completion counted on the leader's barriers) ----------------
-            int sa = 0, sb = 0;
-            uint32_t pha = 0, phb = 0;
-            long long dbg_acc[3] = {0, 0, 0};
-            const long long t_begin = clock64();
-            const int tpi = R >= 128 ? R / 128 : 1, bh = 128 / GW, ipt = R >= 128 ? 1 : 128 / R;
-            for (int u = first_unit; u < total_units; u += unit_step) {
-                const int v = u % args.variants;
-                const int tile_m = (u / args.variants) * 2 + static_cast<int>(rank);
-                int n0, y0 = 0;
-                if (R >= 128) {
-                    n0 = tile_m / tpi;
-                    y0 = (tile_m - n0 * tpi) * bh;
-                } else {
-                    n0 = tile_m * ipt;
-                }
+        // ---------------- TMA producer (both CTAs; completion counted on the leader's barriers) ----------------
+        // whole warp in uniform control flow, one elected lane issues (see elect_one() in sg_umma.cuh)
+        const bool issuer = elect_one();
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
+        long long dbg_acc[3] = {0, 0, 0};
+        const long long t_begin = clock64();
+        const int lg_tpi = R >= 128 ? 31 - __clz(R / 128) : 0, bh = 128 / GW, ipt = R >= 128 ? 1 : 128 / R;
+        const int nvar = args.variants;
+        for (int u = first_unit; u < total_units; u += unit_step) {
+            const int v = nvar == 2 ? (u & 1) : 0;
+            const int tile_m = (nvar == 2 ? (u >> 1) : u) * 2 + static_cast<int>(rank);
+            int n0, y0 = 0;
+            if (R >= 128) {
+                n0 = tile_m >> lg_tpi;
+                y0 = (tile_m & ((1 << lg_tpi) - 1)) * bh;
+            } else {
+                n0 = tile_m * ipt;
+            }
 #pragma unroll 1
-                for (int st = 0; st < args.n_stages; ++st) {
-                    const C2Stage S = args.stages[v][st];
-                    C2_TIMED_WAIT(0, &aempty[sa], pha ^ 1);
+            for (int st = 0; st < args.n_stages; ++st) {
+                const C2Stage S = args.stages[v][st];
+                C2_TIMED_WAIT(0, &aempty[sa], pha ^ 1);
+                if (issuer) {
                     if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2u * args.a_bytes);
                     tma2_load_4d(a_ring + sa * kC2ASlot, &args.amap[S.map], mapa_rank(smem_u32(&afull[sa]), 0), S.cx, S.dx,
                                  y0 + S.dy, n0);
-                    if (++sa == AST) {
-                        sa = 0;
-                        pha ^= 1;
-                    }
+                }
+                if (++sa == AST) {
+                    sa = 0;
+                    pha ^= 1;
+                }
 #pragma unroll 1
-                    for (int p = 0; p < S.nprod; ++p) {
-                        const int koff = args.prods[v][S.first_prod + p].b_koff;
-                        C2_TIMED_WAIT(1, &bempty[sb], phb ^ 1);
+                for (int p = 0; p < S.nprod; ++p) {
+                    const int koff = args.prods[v][S.first_prod + p].b_koff;
+                    C2_TIMED_WAIT(1, &bempty[sb], phb ^ 1);
+                    if (issuer) {
                         if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2u * Cfg::kBSlot);
                         tma2_load_2d(b_ring + sb * Cfg::kBSlot, &args.bmap, mapa_rank(smem_u32(&bfull[sb]), 0), koff,
                                      static_cast<int>(rank) * (BN / 2));
-                        if (++sb == BST) {
-                            sb = 0;
-                            phb ^= 1;
-                        }
+                    }
+                    if (++sb == BST) {
+                        sb = 0;
+                        phb ^= 1;
                     }
                 }
             }
-            if (args.dbg) {
-                long long* d = args.dbg + blockIdx.x * 16;
-                d[0] = dbg_acc[0];
-                d[1] = dbg_acc[1];
-                d[2] = clock64() - t_begin;
-            }
+        }
+        if (args.dbg && issuer) {
+            long long* d = args.dbg + blockIdx.x * 16;
+            d[0] = dbg_acc[0];
+            d[1] = dbg_acc[1];
+            d[2] = clock64() - t_begin;
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             // ---------------- MMA issuer (leader CTA only): 256 x BN x 16 per instruction ----------------
             constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+            const bool issuer = elect_one();
             int sa = 0, sb = 0, j = 0;
             uint32_t pha = 0, phb = 0;
             long long dbg_acc[3] = {0, 0, 0};
-            long long t_mma = 0, t_commit = 0;
             const long long t_begin = clock64();
+            const int nvar = args.variants;
             for (int u = first_unit; u < total_units; u += unit_step, ++j) {
-                const int v = u % args.variants;
+                const int v = nvar == 2 ? (u & 1) : 0;
                 const int acc = j & 1;
                 C2_TIMED_WAIT(2, &tempty[acc], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -284,41 +290,35 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                         tc_fence_after();
                         const uint32_t a_addr = a_base + P.a_off;
                         const uint32_t b_addr = smem_u32(b_ring + sb * Cfg::kBSlot);
-                        const long long tm0 = args.dbg ? clock64() : 0;
+                        if (issuer) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSW128);
-                            const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSW128);
-                            umma2_bf16_ss(tmem_acc + P.acc_col, da, db, idesc, (P.first && k == 0) ? 0u : 1u);
-                        }
-                        const long long tm1 = args.dbg ? clock64() : 0;
-                        umma2_commit(&bempty[sb]);
-                        if (args.dbg) {
-                            t_mma += tm1 - tm0;
-                            t_commit += clock64() - tm1;
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSW128);
+                                const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSW128);
+                                umma2_bf16_ss(tmem_acc + P.acc_col, da, db, idesc, (P.first && k == 0) ? 0u : 1u);
+                            }
+                            umma2_commit(&bempty[sb]);
                         }
                         if (++sb == BST) {
                             sb = 0;
                             phb ^= 1;
                         }
                     }
-                    umma2_commit(&aempty[sa]);
+                    if (issuer) umma2_commit(&aempty[sa]);
                     if (++sa == AST) {
                         sa = 0;
                         pha ^= 1;
                     }
                 }
-                umma2_commit(&tfull[acc]);
+                if (issuer) umma2_commit(&tfull[acc]);
             }
-            if (args.dbg) {
+            if (args.dbg && issuer) {
                 long long* d = args.dbg + blockIdx.x * 16;
                 d[4] = dbg_acc[0];
                 d[5] = dbg_acc[1];
                 d[6] = dbg_acc[2];
                 d[7] = clock64() - t_begin;
                 d[8] = j;
-                d[9] = t_mma;
-                d[10] = t_commit;
             }
         }
     } else {
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         long long dbg_acc[1] = {0};
         const long long t_begin = clock64();
         for (int u = first_unit; u < total_units; u += unit_step, ++j) {
-            const int v = u % args.variants;
-            const int tile_m = (u / args.variants) * 2 + static_cast<int>(rank);
+            const int v = args.variants == 2 ? (u & 1) : 0;
+            const int tile_m = (args.variants == 2 ? (u >> 1) : u) * 2 + static_cast<int>(rank);
             const int acc = j & 1;
             const int row0 = tile_m * 128 + q * 32;
             const int gm = row0 + lane;
@@ -512,8 +512,8 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
             for (int b : {0, 1, 74, 75}) {
                 const long long* d = h + b * 16;
                 printf("conv2<%d,%d> cta %3d: producer wait aempty %lld bempty %lld total %lld | mma wait afull %lld bfull "
-                       "%lld tempty %lld total %lld units %lld mma-issue %lld commit %lld | epi wait tfull %lld total %lld\n",
-                       BN, kAccCols, b, d[0], d[1], d[2], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[12], d[13]);
+                       "%lld tempty %lld total %lld units %lld | epi wait tfull %lld total %lld\n",
+                       BN, kAccCols, b, d[0], d[1], d[2], d[4], d[5], d[6], d[7], d[8], d[12], d[13]);
             }
         }
     }

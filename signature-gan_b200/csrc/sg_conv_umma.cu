@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x;
     const int n_tiles = (args.Nf + BN - 1) / BN;
@@ -741,34 +741,36 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // per 64-channel atom of B: tap -> parity view, shift and channel block (loop invariant)
-            const CUtensorMap* a_fm[BN / 64];
-            int a_dy[BN / 64], a_dx[BN / 64], a_ch[BN / 64];
+        // ---------------- TMA producer (whole warp, uniform control flow; one elected lane issues) ----------------
+        const bool issuer = elect_one();
+        // per 64-channel atom of B: tap -> parity view, shift and channel block (loop invariant)
+        const CUtensorMap* a_fm[BN / 64];
+        int a_dy[BN / 64], a_dx[BN / 64], a_ch[BN / 64];
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a) {
-                const int ta = tap + a / apt, cb = a % apt;
-                const int ky = ta >> 2, kx = ta & 3;
-                a_fm[a] = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
-                a_dy[a] = ((ky + 1) >> 1) - 1;
-                a_dx[a] = ((kx + 1) >> 1) - 1;
-                a_ch[a] = tile_n * BN + cb * 64;
-            }
-            for (int it = 0; it < num_k; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+        for (int a = 0; a < BN / 64; ++a) {
+            const int ta = tap + a / apt, cb = a % apt;
+            const int ky = ta >> 2, kx = ta & 3;
+            a_fm[a] = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
+            a_dy[a] = ((ky + 1) >> 1) - 1;
+            a_dx[a] = ((kx + 1) >> 1) - 1;
+            a_ch[a] = tile_n * BN + cb * 64;
+        }
+        const int lg_tpi = R >= kWgK ? 31 - __clz(R / kWgK) : 0, rows_per = kWgK / args.GW, ipk = R >= kWgK ? 1 : kWgK / R;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < num_k; ++it) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (issuer) {
                 uint8_t* sa = smem + s * Cfg::kStageBytes;
                 uint8_t* sb = sa + Cfg::kABytes;
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 const int kt = kt_begin + it;
                 int n0, y0;
                 if (R >= kWgK) {
-                    const int tpi = R / kWgK;
-                    n0 = kt / tpi;
-                    y0 = (kt % tpi) * (kWgK / args.GW);
+                    n0 = kt >> lg_tpi;
+                    y0 = (kt & ((1 << lg_tpi) - 1)) * rows_per;
                 } else {
-                    n0 = kt * (kWgK / R);
+                    n0 = kt * ipk;
                     y0 = 0;
                 }
                 tma_load_2d(sa, &args.cmap, &full_bar[s], tile_m * 128, kt * kWgK);
@@ -776,25 +778,30 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
                 if (args.plain) {
 #pragma unroll
                     for (int a = 0; a < BN / 64; ++a)
-                        tma_load_2d(sb + a * Cfg::kAtomBytes, &args.fmap[0], &full_bar[s], tile_n * BN + a * 64,
-                                    kt * kWgK);
+                        tma_load_2d(sb + a * Cfg::kAtomBytes, &args.fmap[0], &full_bar[s], tile_n * BN + a * 64, kt * kWgK);
                 } else {
 #pragma unroll
                     for (int a = 0; a < BN / 64; ++a)
                         tma_load_4d(sb + a * Cfg::kAtomBytes, a_fm[a], &full_bar[s], a_ch[a], a_dx[a], y0 + a_dy[a], n0);
                 }
             }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-            for (int it = 0; it < num_k; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                const uint32_t b_addr = a_addr + Cfg::kABytes;
+        // ---------------- MMA issuer (whole warp, uniform control flow) ----------------
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        const bool issuer = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < num_k; ++it) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + Cfg::kABytes;
+            if (issuer) {
 #pragma unroll
                 for (int k = 0; k < kWgK / 16; ++k) {
                     // 16 pixel rows per MMA = 2 swizzle atoms of 8 rows (SBO); 64-channel column blocks are LBO apart.
@@ -804,8 +811,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
                 }
                 umma_commit(&empty_bar[s]);
             }
-            umma_commit(accum_bar);
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
         }
+        if (issuer) umma_commit(accum_bar);
     } else {
         const int q = warp & 3;
         const int m = tile_m * 128 + q * 32 + lane;

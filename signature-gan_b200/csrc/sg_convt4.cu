@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int GW = args.GW, R = args.GH * GW;
     const int BH = 128 / GW;                          // input rows per tile
     const uint32_t abuf = static_cast<uint32_t>((BH + 2) * GW) * Cfg::kRowBytes;
@@ -118,36 +118,47 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer: resident weights once, then 3 halo'd input blocks per tile ----------------
+        // ---------------- TMA producer: resident weights once, then 3 halo'd input blocks per tile ----------------
+        // (whole warp in uniform control flow, one elected lane issues: see elect_one() in sg_umma.cuh)
+        const bool issuer = elect_one();
+        if (issuer) {
             mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
             for (int tap = 0; tap < 16; ++tap) tma_load_2d(wsm + tap * Cfg::kWTapBytes, &args.wmap, w_bar, tap * BK, 0);
-            uint32_t g = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++g) {
-                const int n0 = t / tpi, y0 = (t - n0 * tpi) * BH;
-                const int s = g % STAGES;
-                mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+        }
+        const int lg_tpi = 31 - __clz(tpi);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n0 = t >> lg_tpi, y0 = (t & (tpi - 1)) * BH;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (issuer) {
                 mbar_arrive_expect_tx(&full_bar[s], 3 * abuf);
                 uint8_t* sa = ring + s * Cfg::kStageBytes;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * abuf, &args.amap, &full_bar[s], 0, d - 1, y0 - 1, n0);
             }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-            mbar_wait(w_bar, 0);
-            const uint32_t w_addr = smem_u32(wsm);
-            const uint32_t row_step = static_cast<uint32_t>(GW) * Cfg::kRowBytes;  // one grid row of A
-            uint32_t g = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++g) {
-                const int acc = g & 1;
-                mbar_wait(&tempty_bar[acc], ((g >> 1) & 1) ^ 1);
-                const int s = g % STAGES;
-                mbar_wait(&full_bar[s], (g / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(ring + s * Cfg::kStageBytes);
+        // ---------------- MMA issuer (whole warp, uniform control flow) ----------------
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+        const bool issuer = elect_one();
+        mbar_wait(w_bar, 0);
+        const uint32_t w_addr = smem_u32(wsm);
+        const uint32_t row_step = static_cast<uint32_t>(GW) * Cfg::kRowBytes;  // one grid row of A
+        uint32_t g = 0;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++g) {
+            const int acc = g & 1;
+            mbar_wait(&tempty_bar[acc], ((g >> 1) & 1) ^ 1);
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + s * Cfg::kStageBytes);
+            if (issuer) {
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const int py = p >> 1, px = p & 1;
@@ -169,6 +180,10 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
                 }
                 umma_commit(&empty_bar[s]);
                 umma_commit(&tfull_bar[acc]);
+            }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
             }
         }
     } else {
