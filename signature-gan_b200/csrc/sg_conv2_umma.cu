@@ -34,8 +34,6 @@ namespace {
 constexpr int kC2Threads = 64 + 32 * 8;
 constexpr int kC2MaxStages = 24, kC2MaxProds = 32;
 constexpr int kC2ASlot = 20 * 1024;   // largest A box: (8+2) rows x 16 px x 128 B
-constexpr int kC2AStages = 4;
-constexpr int kC2BBytes = 64 * 1024;  // weight-tile ring
 constexpr int kC2EpiStage = 32 * 64;
 
 struct C2Stage {
@@ -126,7 +124,10 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    // default (.release.cta) semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU, which makes the warp
+    // wait for all of its outstanding global stores (~1000s of cycles per accumulator hand-back); only the TMEM reads,
+    // already complete after tcgen05.wait::ld + tcgen05.fence::before_thread_sync, have to precede this arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 __device__ __forceinline__ float c2_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -151,27 +152,29 @@ __device__ __forceinline__ uint32_t c2_epi_off(int row, int k) { return row * 64
 template <int BN, int kAccCols>
 struct C2Cfg {
     static constexpr int kBSlot = (BN / 2) * 128;           // this CTA's half of a [BN x 64] weight tile
-    static constexpr int kBStages = kC2BBytes / kBSlot;
+    static constexpr int kMaxProd = BN == 64 ? 8 : 2;       // products (weight tiles) per stage
+    // stage = one A box + the weight tiles of all its products on ONE barrier pair: the per-stage cost of the
+    // single-thread roles (wait, expect_tx, commit) is paid once per 2..8 products
+    static constexpr int kSlot = kC2ASlot + kMaxProd * kBSlot;
+    static constexpr int kStagesFit = (180 * 1024) / kSlot;
+    static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
     static constexpr int kTmemCols = 2 * kAccCols;
-    static constexpr int kBars = 2 * kC2AStages + 2 * kBStages + 4;
-    static constexpr int kSmemBytes = kC2AStages * kC2ASlot + kC2BBytes + 8 * kC2EpiStage + kBars * 8 + 16 + 1024;
+    static constexpr int kBars = 2 * kStages + 4;
+    static constexpr int kSmemBytes = kStages * kSlot + 8 * kC2EpiStage + kBars * 8 + 16 + 1024;
     static constexpr int kNCH = kAccCols / 64;              // 32-column chunks per epilogue warp
 };
 
 template <int BN, int kAccCols>
 __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
     using Cfg = C2Cfg<BN, kAccCols>;
-    constexpr int AST = kC2AStages, BST = Cfg::kBStages;
+    constexpr int STG = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = a_ring + AST * kC2ASlot;
-    uint8_t* epi_smem = b_ring + kC2BBytes;
-    uint64_t* afull = reinterpret_cast<uint64_t*>(epi_smem + 8 * kC2EpiStage);
-    uint64_t* aempty = afull + AST;
-    uint64_t* bfull = aempty + AST;
-    uint64_t* bempty = bfull + BST;
-    uint64_t* tfull = bempty + BST;
+    uint8_t* ring = smem;
+    uint8_t* epi_smem = ring + STG * Cfg::kSlot;
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + 8 * kC2EpiStage);
+    uint64_t* empty = full + STG;
+    uint64_t* tfull = empty + STG;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -186,13 +189,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.amap[0]);
         tma_prefetch_desc(&args.bmap);
-        for (int s = 0; s < AST; ++s) {
-            mbar_init(&afull[s], 1);
-            mbar_init(&aempty[s], 1);
-        }
-        for (int s = 0; s < BST; ++s) {
-            mbar_init(&bfull[s], 1);
-            mbar_init(&bempty[s], 1);
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -210,8 +209,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         // ---------------- TMA producer (both CTAs; completion counted on the leader's barriers) ----------------
         // whole warp in uniform control flow, one elected lane issues (see elect_one() in sg_umma.cuh)
         const bool issuer = elect_one();
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0;
+        int sg = 0;
+        uint32_t phs = 0;
         long long dbg_acc[3] = {0, 0, 0};
         const long long t_begin = clock64();
         const int lg_tpi = R >= 128 ? 31 - __clz(R / 128) : 0, bh = 128 / GW, ipt = R >= 128 ? 1 : 128 / R;
@@ -229,29 +228,20 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
 #pragma unroll 1
             for (int st = 0; st < args.n_stages; ++st) {
                 const C2Stage S = args.stages[v][st];
-                C2_TIMED_WAIT(0, &aempty[sa], pha ^ 1);
+                C2_TIMED_WAIT(0, &empty[sg], phs ^ 1);
                 if (issuer) {
-                    if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2u * args.a_bytes);
-                    tma2_load_4d(a_ring + sa * kC2ASlot, &args.amap[S.map], mapa_rank(smem_u32(&afull[sa]), 0), S.cx, S.dx,
-                                 y0 + S.dy, n0);
-                }
-                if (++sa == AST) {
-                    sa = 0;
-                    pha ^= 1;
-                }
+                    uint8_t* slot = ring + sg * Cfg::kSlot;
+                    const uint32_t bar = mapa_rank(smem_u32(&full[sg]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[sg], 2u * (args.a_bytes + S.nprod * Cfg::kBSlot));
+                    tma2_load_4d(slot, &args.amap[S.map], bar, S.cx, S.dx, y0 + S.dy, n0);
 #pragma unroll 1
-                for (int p = 0; p < S.nprod; ++p) {
-                    const int koff = args.prods[v][S.first_prod + p].b_koff;
-                    C2_TIMED_WAIT(1, &bempty[sb], phb ^ 1);
-                    if (issuer) {
-                        if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2u * Cfg::kBSlot);
-                        tma2_load_2d(b_ring + sb * Cfg::kBSlot, &args.bmap, mapa_rank(smem_u32(&bfull[sb]), 0), koff,
-                                     static_cast<int>(rank) * (BN / 2));
-                    }
-                    if (++sb == BST) {
-                        sb = 0;
-                        phb ^= 1;
-                    }
+                    for (int p = 0; p < S.nprod; ++p)
+                        tma2_load_2d(slot + kC2ASlot + p * Cfg::kBSlot, &args.bmap, bar,
+                                     args.prods[v][S.first_prod + p].b_koff, static_cast<int>(rank) * (BN / 2));
+                }
+                if (++sg == STG) {
+                    sg = 0;
+                    phs ^= 1;
                 }
             }
         }
@@ -266,8 +256,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
             // ---------------- MMA issuer (leader CTA only): 256 x BN x 16 per instruction ----------------
             constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
             const bool issuer = elect_one();
-            int sa = 0, sb = 0, j = 0;
-            uint32_t pha = 0, phb = 0;
+            int sg = 0, j = 0;
+            uint32_t phs = 0;
             long long dbg_acc[3] = {0, 0, 0};
             const long long t_begin = clock64();
             const int nvar = args.variants;
@@ -280,34 +270,27 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
 #pragma unroll 1
                 for (int st = 0; st < args.n_stages; ++st) {
                     const C2Stage S = args.stages[v][st];
-                    C2_TIMED_WAIT(0, &afull[sa], pha);
+                    C2_TIMED_WAIT(0, &full[sg], phs);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_ring + sa * kC2ASlot);
+                    const uint32_t a_base = smem_u32(ring + sg * Cfg::kSlot);
+                    if (issuer) {
 #pragma unroll 1
-                    for (int p = 0; p < S.nprod; ++p) {
-                        const C2Prod P = args.prods[v][S.first_prod + p];
-                        C2_TIMED_WAIT(1, &bfull[sb], phb);
-                        tc_fence_after();
-                        const uint32_t a_addr = a_base + P.a_off;
-                        const uint32_t b_addr = smem_u32(b_ring + sb * Cfg::kBSlot);
-                        if (issuer) {
+                        for (int p = 0; p < S.nprod; ++p) {
+                            const C2Prod P = args.prods[v][S.first_prod + p];
+                            const uint32_t a_addr = a_base + P.a_off;
+                            const uint32_t b_addr = a_base + kC2ASlot + p * Cfg::kBSlot;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSW128);
                                 const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSW128);
                                 umma2_bf16_ss(tmem_acc + P.acc_col, da, db, idesc, (P.first && k == 0) ? 0u : 1u);
                             }
-                            umma2_commit(&bempty[sb]);
                         }
-                        if (++sb == BST) {
-                            sb = 0;
-                            phb ^= 1;
-                        }
+                        umma2_commit(&empty[sg]);
                     }
-                    if (issuer) umma2_commit(&aempty[sa]);
-                    if (++sa == AST) {
-                        sa = 0;
-                        pha ^= 1;
+                    if (++sg == STG) {
+                        sg = 0;
+                        phs ^= 1;
                     }
                 }
                 if (issuer) umma2_commit(&tfull[acc]);
@@ -337,6 +320,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         const uint32_t tempty_leader[2] = {mapa_rank(smem_u32(&tempty[0]), 0), mapa_rank(smem_u32(&tempty[1]), 0)};
         int j = 0;
         long long dbg_acc[1] = {0};
+        long long t_ld = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
         for (int u = first_unit; u < total_units; u += unit_step, ++j) {
             const int v = args.variants == 2 ? (u & 1) : 0;
@@ -370,8 +354,10 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                     }
                 }
                 uint32_t vv[32];
+                const long long te0 = args.dbg ? clock64() : 0;
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0, vv);
                 tmem_ld_wait();
+                const long long te1 = args.dbg ? clock64() : 0;
                 if (ci == Cfg::kNCH - 1) {
                     tc_fence_before();
                     __syncwarp();
@@ -431,6 +417,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                     packed[g8] = make_uint4(c2_pack(f[0], f[1]), c2_pack(f[2], f[3]), c2_pack(f[4], f[5]),
                                             c2_pack(f[6], f[7]));
                 }
+                const long long te2 = args.dbg ? clock64() : 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + c2_epi_off(lane, i)) = packed[i];
                 __syncwarp();
@@ -443,12 +430,20 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                         *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n_base + wr_k * 8) = d;
                 }
                 __syncwarp();
+                if (args.dbg) {
+                    t_ld += te1 - te0;
+                    t_math += te2 - te1;
+                    t_store += clock64() - te2;
+                }
             }
         }
         if (args.dbg && warp == 2 && lane == 0) {
             long long* d = args.dbg + blockIdx.x * 16;
             d[12] = dbg_acc[0];
             d[13] = clock64() - t_begin;
+            d[9] = t_ld;
+            d[10] = t_math;
+            d[11] = t_store;
         }
     }
     tc_fence_before();
@@ -511,9 +506,9 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
             cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
             for (int b : {0, 1, 74, 75}) {
                 const long long* d = h + b * 16;
-                printf("conv2<%d,%d> cta %3d: producer wait aempty %lld bempty %lld total %lld | mma wait afull %lld bfull "
-                       "%lld tempty %lld total %lld units %lld | epi wait tfull %lld total %lld\n",
-                       BN, kAccCols, b, d[0], d[1], d[2], d[4], d[5], d[6], d[7], d[8], d[12], d[13]);
+                printf("conv2<%d,%d> cta %3d: producer wait empty %lld - %lld total %lld | mma wait full %lld - "
+                       "%lld tempty %lld total %lld units %lld | epi wait tfull %lld total %lld (tmem ld %lld math %lld store %lld)\n",
+                       BN, kAccCols, b, d[0], d[1], d[2], d[4], d[5], d[6], d[7], d[8], d[12], d[13], d[9], d[10], d[11]);
             }
         }
     }

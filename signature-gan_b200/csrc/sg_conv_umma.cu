@@ -99,7 +99,7 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpiStageBytes = 32 * 64;           // per epilogue warp: 32 rows x 32 bf16 columns, swizzled
+constexpr int kEpiStageBytes = 32 * 128;          // per epilogue warp: 32 rows x 32 fp32 columns, swizzled
 
 // kPair (transposed convolution, BN <= 128): one schedule unit = both horizontal output parities (px = 0, 1) of a
 // (128-input-pixel tile, py) pair, accumulated side by side in TMEM, so that the epilogue of a row writes the two
@@ -117,7 +117,7 @@ struct ConvCfg {
     // fill traffic — the resource these kernels are bound by (L2 -> SM at ~64 B/clk against 128x256x64 MMA stages).
     static constexpr int kCluster = BN >= 128 ? 2 : 1;
     static constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;   // (2 x kTmemCols <= 512 holds for BN <= 64, paired or not)
-    static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 92 : 196) * 1024) / kStageBytes;
+    static constexpr int kStagesFit = ((kCtasPerSm == 2 ? 76 : 192) * 1024) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kColsPerWarp = kAccCols >= 64 ? kAccCols / 2 : kAccCols;
     static constexpr int kActiveEpiWarps = kAccCols >= 64 ? 8 : 4;
@@ -159,9 +159,10 @@ __device__ __forceinline__ void load_vec8(const float* p, bool vec_ok, float (&v
     }
 }
 
-// Epilogue staging buffer of one warp: 32 rows x 64 bytes; 16-byte piece k of row r lives at piece k ^ ((r >> 1) & 3),
-// which makes both the row-per-lane and the 4-lanes-per-row access patterns bank-conflict free.
-__device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 64 + ((k ^ ((row >> 1) & 3)) << 4); }
+// Epilogue staging buffer of one warp: 32 rows x 128 bytes (fp32 accumulators); 16-byte piece k of row r lives at piece
+// k ^ (r & 7), which makes both the row-per-lane stores (a lane writes its row's 8 pieces) and the write-back reads
+// (4 lanes per row, 2 pieces each) bank-conflict free.
+__device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 128 + ((k ^ (row & 7)) << 4); }
 
 // kStats (paired transposed convolution only; there BN == N_total): the epilogue also accumulates per-channel sum and
 // sum of squares of the stored (bf16-rounded) outputs — the BatchNorm batch statistics of gen…:58 — and the CTA writes
@@ -336,15 +337,15 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
         for (int ci = 0; ci < (kStats ? NCH : 1); ++ci)
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) st_sum[ci][jj] = st_sq[ci][jj] = 0.f;
-        int j = 0;
-        for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
-            TileCoord tc = decode_tile(t, n_tiles, phases);
+        // GEMM rows of this warp in unit t and, per lane, the output row (pixel index) of its GEMM row (for paired
+        // units: of its px = 0 pixel)
+        auto unit_rows = [&](int t, TileCoord& tc, int& row0, int& img, int& orow) {
+            tc = decode_tile(t, n_tiles, phases);
             tc.tile_m = tc.tile_m * CL + cta_rank;
-            const int acc = j & 1;
-            const int row0 = tc.tile_m * kTileM + q * 32;   // first GEMM row of this warp
+            row0 = tc.tile_m * kTileM + q * 32;
             const int gm = row0 + lane;
-            // output row (pixel index) of this lane's GEMM row; for paired units: of its px = 0 pixel
-            int orow = gm, img = 0;
+            orow = gm;
+            img = 0;
             if (mode != kPlain) {
                 img = gm >> lgR;
                 if (mode == kConvT) {
@@ -354,6 +355,48 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                     orow = ((img * 2 * args.GH + 2 * yh + py) * 2 * args.GW) + 2 * xh + px;
                 }
             }
+        };
+        // ALL epilogue math runs in the write-back layout: lane (wr_row, wr_k) owns columns [8 wr_k, 8 wr_k + 8) of rows
+        // 8 i + wr_row (i = 0..3) of a 32 x 32 chunk. The raw fp32 accumulators are transposed through the staging
+        // buffer; bias / scale / shift / dropout mask of the lane's 8 channels are loaded ONCE per chunk, before the
+        // accumulator load (in the row-per-lane layout every group of 8 columns needed its own loads, each behind a
+        // branch: ~16 serialised L1/L2 round trips per chunk, 3-4x the time of the MMAs they overlap), and the gate
+        // (saved activation at the output position) is loaded directly in this layout, one chunk ahead.
+        auto gate_load = [&](const TileCoord& tcg, int row0g, int orowg, int ci, uint4 (&g)[4]) {
+            const int c0 = half * Cfg::kColsPerWarp + ci * 32;
+            const int sub = kPair ? c0 / BN : 0;
+            const int n_base = tcg.tile_n * BN + (kPair ? c0 - sub * BN : c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + wr_row;
+                const int o = __shfl_sync(0xffffffffu, orowg, r) + sub;
+                g[i] = make_uint4(0, 0, 0, 0);
+                if (row0g + r < args.M_total)
+                    g[i] = __ldg(reinterpret_cast<const uint4*>(args.gate + static_cast<size_t>(o) * args.ldo + n_base +
+                                                                 wr_k * 8));
+            }
+        };
+        const bool one_img = mode == kPlain || R >= 32;  // the warp's 32 rows lie in one image: one mask row per chunk
+        // two CTAs per SM run under a 96-register cap (and have 16 epilogue warps to hide latency with): there the
+        // gate is loaded at the top of its own chunk instead of one chunk ahead
+        constexpr bool kGateAhead = Cfg::kCtasPerSm == 1;
+        int j = 0;
+        TileCoord tc;
+        int row0 = 0, img = 0, orow = 0;
+        uint4 gq_next[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq_next[i] = make_uint4(0, 0, 0, 0);
+        if (first_unit < total_tiles) {
+            unit_rows(first_unit, tc, row0, img, orow);
+            if (kGateAhead && args.gate) gate_load(tc, row0, orow, 0, gq_next);
+        }
+        for (int t = first_unit; t < total_tiles; t += unit_step, ++j) {
+            const int acc = j & 1;
+            // the unit after this one (its rows are needed to prefetch its first gate tile)
+            TileCoord tc_n = tc;
+            int row0_n = row0, img_n = img, orow_n = orow;
+            const bool has_next = t + unit_step < total_tiles;
+            if (kGateAhead && has_next) unit_rows(t + unit_step, tc_n, row0_n, img_n, orow_n);
             mbar_wait(&tfull_bar[acc], (j >> 1) & 1);
             tc_fence_after();
 #pragma unroll(kStats ? NCH : 1)
@@ -361,19 +404,19 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                 const int c0 = half * Cfg::kColsPerWarp + ci * 32;
                 const int sub = kPair ? c0 / BN : 0;
                 const int n_base = tc.tile_n * BN + (kPair ? c0 - sub * BN : c0);
-                // ---- gate (saved activation at the output position): coalesced load, transposed through smem
-                uint4 gq[4];
-                if (args.gate) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = i * 8 + wr_row;
-                        const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
-                        gq[i] = make_uint4(0, 0, 0, 0);
-                        if (row0 + r < args.M_total)
-                            gq[i] = __ldg(reinterpret_cast<const uint4*>(args.gate + static_cast<size_t>(o) * args.ldo +
-                                                                         n_base + wr_k * 8));
-                    }
+                const int n8 = n_base + wr_k * 8;
+                float b8[8], sc8[8], sh8[8], m8[8];
+                if (args.bias) load_vec8(args.bias + n8, vec_ok, b8);
+                if (args.scale) {
+                    load_vec8(args.scale + n8, vec_ok, sc8);
+                    load_vec8(args.shift + n8, vec_ok, sh8);
                 }
+                if (args.mask && one_img) {
+                    const int mi = row0 < args.M_total ? (mode != kPlain ? row0 >> lgR : 0) : 0;
+                    load_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m8);
+                }
+                uint4 gq[4];
+                if (!kGateAhead && args.gate) gate_load(tc, row0, orow, ci, gq);
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols + c0, v);
                 tmem_ld_wait();
@@ -383,34 +426,35 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-                if (args.gate) {
+                if (kGateAhead) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(stage + epi_off(i * 8 + wr_row, wr_k)) = gq[i];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) gq[i] = *reinterpret_cast<const uint4*>(stage + epi_off(lane, i));
-                    __syncwarp();
+                    for (int i = 0; i < 4; ++i) gq[i] = gq_next[i];
+                    if (args.gate) {
+                        if (ci + 1 < NCH)
+                            gate_load(tc, row0, orow, ci + 1, gq_next);
+                        else if (has_next)
+                            gate_load(tc_n, row0_n, orow_n, 0, gq_next);
+                    }
                 }
-                uint4 packed[4];
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    float f[8];
+                for (int p = 0; p < 8; ++p)
+                    *reinterpret_cast<uint4*>(stage + epi_off(lane, p)) =
+                        make_uint4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+                __syncwarp();
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) f[jj] = __uint_as_float(v[g8 * 8 + jj]);
-                    const int n8 = n_base + g8 * 8;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + wr_row;
+                    const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
+                    const float4 lo4 = *reinterpret_cast<const float4*>(stage + epi_off(r, 2 * wr_k));
+                    const float4 hi4 = *reinterpret_cast<const float4*>(stage + epi_off(r, 2 * wr_k + 1));
+                    float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
                     if (args.bias) {
-                        float b[8];
-                        load_vec8(args.bias + n8, vec_ok, b);
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] += b[jj];
+                        for (int jj = 0; jj < 8; ++jj) f[jj] += b8[jj];
                     }
                     if (args.scale) {
-                        float sc[8], sh[8];
-                        load_vec8(args.scale + n8, vec_ok, sc);
-                        load_vec8(args.shift + n8, vec_ok, sh);
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc[jj], sh[jj]);
+                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc8[jj], sh8[jj]);
                     }
                     if (args.act == kActRelu) {
 #pragma unroll
@@ -420,33 +464,29 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                         for (int jj = 0; jj < 8; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
                     }
                     if (args.mask) {
-                        float m[8];
-                        const int mi = gm < args.M_total ? img : 0;
-                        load_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m);
+                        if (one_img) {
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] *= m[jj];
+                            for (int jj = 0; jj < 8; ++jj) f[jj] *= m8[jj];
+                        } else {  // tiny grids (4 x 4): the rows of a chunk span several images
+                            float m[8];
+                            const int mi = row0 + r < args.M_total ? (row0 + r) >> lgR : 0;
+                            load_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m);
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) f[jj] *= m[jj];
+                        }
                     }
                     if (args.gate) {
-                        const uint32_t w4[4] = {gq[g8].x, gq[g8].y, gq[g8].z, gq[g8].w};
+                        const uint32_t w4[4] = {gq[i].x, gq[i].y, gq[i].z, gq[i].w};
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
                             f[tt * 2] *= bf16_lo(w4[tt]) > 0.f ? 1.f : args.slope;
                             f[tt * 2 + 1] *= bf16_hi(w4[tt]) > 0.f ? 1.f : args.slope;
                         }
                     }
-                    packed[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                            pack_bf16(f[6], f[7]));
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + epi_off(lane, i)) = packed[i];
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = i * 8 + wr_row;
-                    const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
-                    const uint4 d = *reinterpret_cast<const uint4*>(stage + epi_off(r, wr_k));
+                    const uint4 d = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                               pack_bf16(f[6], f[7]));
                     if (row0 + r < args.M_total) {
-                        *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n_base + wr_k * 8) = d;
+                        *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n8) = d;
                         if (kStats) {
                             const int cs = kStats ? ci : 0;
                             const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
@@ -463,7 +503,16 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                 }
                 __syncwarp();
             }
+            if (kGateAhead) {
+                tc = tc_n;
+                row0 = row0_n;
+                img = img_n;
+                orow = orow_n;
+            } else if (has_next) {
+                unit_rows(t + unit_step, tc, row0, img, orow);
+            }
         }
+        (void)img;
         (void)stage_u32;
         if (kStats) {
             // lanes with equal wr_k hold partial sums of the same 8 channels; this warp's slot = [2][kColsPerWarp]

@@ -431,7 +431,7 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
 }
 
 static bool want(const char* name);
-static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout) {
+static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout, int epi = 0) {
     if (!want(name)) return;
     bf16 *x, *w, *out;
     const size_t xn = (size_t)N * H * W * Cin, wn = (size_t)Cout * 16 * Cin;
@@ -445,6 +445,28 @@ static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, 
     memset(&a, 0, sizeof(a));
     a.out = out;
     a.ldo = Cout;
+    bf16* gate = nullptr;
+    float *mask = nullptr, *bias = nullptr;
+    if (epi == 1) {  // data-gradient epilogue: gate (saved activation) + dropout mask
+        CK(cudaMalloc(&gate, on * 2));
+        CK(cudaMemset(gate, 0x3f, on * 2));
+        CK(cudaMalloc(&mask, (size_t)N * Cout * 4));
+        CK(cudaMemset(mask, 0, (size_t)N * Cout * 4));
+        a.gate = gate;
+        a.slope = 0.2f;
+        a.mask = mask;
+        a.ldmask = Cout;
+    } else if (epi == 2) {  // forward epilogue: bias + LeakyReLU + dropout mask
+        CK(cudaMalloc(&bias, Cout * 4));
+        CK(cudaMemset(bias, 0, Cout * 4));
+        CK(cudaMalloc(&mask, (size_t)N * Cout * 4));
+        CK(cudaMemset(mask, 0, (size_t)N * Cout * 4));
+        a.bias = bias;
+        a.act = sg::kActLeaky;
+        a.slope = 0.2f;
+        a.mask = mask;
+        a.ldmask = Cout;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -464,6 +486,9 @@ static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, 
     cudaFree(x);
     cudaFree(w);
     cudaFree(out);
+    if (gate) cudaFree(gate);
+    if (mask) cudaFree(mask);
+    if (bias) cudaFree(bias);
 }
 
 static void perf_wgrad(const char* name, int N, int cH, int cW, int Mc, int Nf) {
@@ -566,6 +591,11 @@ int main(int argc, char** argv) {
         perf_conv("D dgrad c3 512->256 @4x4", sg::kConvT, B, 4, 4, 512, 256);
         perf_conv("D dgrad c2 256->128 @8x8", sg::kConvT, B, 8, 8, 256, 128);
         perf_conv("D dgrad c1 128->64 @16x16", sg::kConvT, B, 16, 16, 128, 64);
+        perf_conv("D c1 +bias,act,mask", sg::kConvS2, B, 32, 32, 64, 128, 2);
+        perf_conv("D c2 +bias,act,mask", sg::kConvS2, B, 16, 16, 128, 256, 2);
+        perf_conv("D dgrad c3 +gate,mask", sg::kConvT, B, 4, 4, 512, 256, 1);
+        perf_conv("D dgrad c2 +gate,mask", sg::kConvT, B, 8, 8, 256, 128, 1);
+        perf_conv("D dgrad c1 +gate,mask", sg::kConvT, B, 16, 16, 128, 64, 1);
         perf_wgrad("wgrad c3 512|256 @4x4", B, 4, 4, 512, 256);
         perf_wgrad("wgrad c2 256|128 @8x8", B, 8, 8, 256, 128);
         perf_wgrad("wgrad c1 128|64 @16x16", B, 16, 16, 128, 64);
