@@ -34,7 +34,7 @@ namespace {
 constexpr int kC2Threads = 64 + 32 * 8;
 constexpr int kC2MaxStages = 24, kC2MaxProds = 32;
 constexpr int kC2ASlot = 20 * 1024;   // largest A box: (8+2) rows x 16 px x 128 B
-constexpr int kC2EpiStage = 32 * 64;
+constexpr int kC2EpiStage = 32 * 128;  // per epilogue warp: 32 rows x 32 fp32 columns
 
 struct C2Stage {
     int map, cx, dx, dy, nprod, first_prod;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void c2_vec8(const float* p, bool vec_ok, float (&v)[
         for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
     }
 }
-__device__ __forceinline__ uint32_t c2_epi_off(int row, int k) { return row * 64 + ((k ^ ((row >> 1) & 3)) << 4); }
+__device__ __forceinline__ uint32_t c2_epi_off(int row, int k) { return row * 128 + ((k ^ (row & 7)) << 4); }
 
 template <int BN, int kAccCols>
 struct C2Cfg {
@@ -156,7 +156,7 @@ struct C2Cfg {
     // stage = one A box + the weight tiles of all its products on ONE barrier pair: the per-stage cost of the
     // single-thread roles (wait, expect_tx, commit) is paid once per 2..8 products
     static constexpr int kSlot = kC2ASlot + kMaxProd * kBSlot;
-    static constexpr int kStagesFit = (180 * 1024) / kSlot;
+    static constexpr int kStagesFit = (176 * 1024) / kSlot;
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kBars = 2 * kStages + 4;
@@ -318,40 +318,97 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         const int wr_row = lane >> 2, wr_k = lane & 3;
         __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
         const uint32_t tempty_leader[2] = {mapa_rank(smem_u32(&tempty[0]), 0), mapa_rank(smem_u32(&tempty[1]), 0)};
+        // all epilogue math in the write-back layout (see sg_conv_umma.cu): lane (wr_row, wr_k) owns columns
+        // [8 wr_k, 8 wr_k + 8) of rows 8 i + wr_row of a 32 x 32 chunk; per-chunk vectors are loaded before the
+        // accumulator, the gate one chunk ahead
+        auto unit_rows = [&](int u, int& v, int& row0, int& img, int& yh, int& xh) {
+            v = args.variants == 2 ? (u & 1) : 0;
+            const int tile_m = (args.variants == 2 ? (u >> 1) : u) * 2 + static_cast<int>(rank);
+            row0 = tile_m * 128 + q * 32;
+            const int gm = row0 + lane;
+            img = gm >> lgR;
+            const int rem = gm & (R - 1);
+            yh = rem >> lgW;
+            xh = rem & (GW - 1);
+        };
+        auto chunk_orow = [&](int v, int row0, int img, int yh, int xh, int ci, int& n_base) {
+            const int c0 = half * (kAccCols / 2) + ci * 32;
+            const int blk = c0 / BN;
+            n_base = c0 - blk * BN;
+            int orow = row0 + lane;
+            if (args.convt) {
+                const int py = kAccCols == 4 * BN ? (blk >> 1) : v, px = blk & 1;
+                orow = ((img * 2 * args.GH + 2 * yh + py) * 2 * GW) + 2 * xh + px;
+            }
+            return orow;
+        };
+        auto gate_load = [&](int row0, int orow, int n_base, uint4 (&g)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + wr_row;
+                const int o = __shfl_sync(0xffffffffu, orow, r);
+                g[i] = make_uint4(0, 0, 0, 0);
+                if (row0 + r < args.M_total)
+                    g[i] = __ldg(reinterpret_cast<const uint4*>(args.gate + static_cast<size_t>(o) * args.ldo + n_base +
+                                                                 wr_k * 8));
+            }
+        };
+        const bool one_img = R >= 32;
+        const bool per_row_mask = args.mask != nullptr && !one_img;
+        const float act_slope = args.act == kActNone ? 1.f : (args.act == kActRelu ? 0.f : args.slope);
+        const uint4 kGateOne = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0: "gate open"
         int j = 0;
         long long dbg_acc[1] = {0};
         long long t_ld = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
+        int v = 0, row0 = 0, img = 0, yh = 0, xh = 0;
+        // gate tiles are fetched TWO chunks ahead (2 x 4 x 16 B per lane in flight): with one chunk ahead the 8 epilogue
+        // warps keep only 16 KB of gate reads in flight per SM, which caps them at ~1.5 TB/s chip-wide
+        uint4 gq_next[4], gq_next2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq_next[i] = gq_next2[i] = kGateOne;
+        int v_1 = 0, row0_1 = 0, img_1 = 0, yh_1 = 0, xh_1 = 0;  // the unit after the current one
+        if (first_unit < total_units) {
+            unit_rows(first_unit, v, row0, img, yh, xh);
+            if (first_unit + unit_step < total_units) unit_rows(first_unit + unit_step, v_1, row0_1, img_1, yh_1, xh_1);
+            if (args.gate) {
+                int nb;
+                int o = chunk_orow(v, row0, img, yh, xh, 0, nb);
+                gate_load(row0, o, nb, gq_next);
+                o = chunk_orow(v, row0, img, yh, xh, 1, nb);   // kNCH >= 2
+                gate_load(row0, o, nb, gq_next2);
+            }
+        }
         for (int u = first_unit; u < total_units; u += unit_step, ++j) {
-            const int v = args.variants == 2 ? (u & 1) : 0;
-            const int tile_m = (args.variants == 2 ? (u >> 1) : u) * 2 + static_cast<int>(rank);
             const int acc = j & 1;
-            const int row0 = tile_m * 128 + q * 32;
-            const int gm = row0 + lane;
-            const int img = gm >> lgR, rem = gm & (R - 1);
-            const int yh = rem >> lgW, xh = rem & (GW - 1);
+            const int v_n = v_1, row0_n = row0_1, img_n = img_1, yh_n = yh_1, xh_n = xh_1;
+            const bool has_next = u + unit_step < total_units;
             C2_TIMED_WAIT(0, &tfull[acc], (j >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int ci = 0; ci < Cfg::kNCH; ++ci) {
                 const int c0 = half * (kAccCols / 2) + ci * 32;
-                const int blk = c0 / BN, n_base = c0 - blk * BN;
-                int orow = gm;
-                if (args.convt) {
-                    const int py = kAccCols == 4 * BN ? (blk >> 1) : v, px = blk & 1;
-                    orow = ((img * 2 * args.GH + 2 * yh + py) * 2 * GW) + 2 * xh + px;
-                }
-                uint4 gq[4];
-                if (args.gate) {
+                int n_base;
+                const int orow = chunk_orow(v, row0, img, yh, xh, ci, n_base);
+                const int n8 = n_base + wr_k * 8;
+                // defaults make the per-row math below branch-free (its four rows then interleave): no bias = +0, no
+                // affine = *1 +0, no activation = slope 1 (ReLU = slope 0), no mask = *1, no gate = positive gate
+                float b8[8], sc8[8], sh8[8], m8[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = i * 8 + wr_row;
-                        const int o = __shfl_sync(0xffffffffu, orow, r);
-                        gq[i] = make_uint4(0, 0, 0, 0);
-                        if (row0 + r < args.M_total)
-                            gq[i] = __ldg(reinterpret_cast<const uint4*>(args.gate + static_cast<size_t>(o) * args.ldo +
-                                                                         n_base + wr_k * 8));
-                    }
+                for (int jj = 0; jj < 8; ++jj) {
+                    b8[jj] = 0.f;
+                    sc8[jj] = 1.f;
+                    sh8[jj] = 0.f;
+                    m8[jj] = 1.f;
+                }
+                if (args.bias) c2_vec8(args.bias + n8, vec_ok, b8);
+                if (args.scale) {
+                    c2_vec8(args.scale + n8, vec_ok, sc8);
+                    c2_vec8(args.shift + n8, vec_ok, sh8);
+                }
+                if (args.mask && one_img) {
+                    const int mi = row0 < args.M_total ? row0 >> lgR : 0;
+                    c2_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m8);
                 }
                 uint32_t vv[32];
                 const long long te0 = args.dbg ? clock64() : 0;
@@ -363,71 +420,51 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
                 }
-                if (args.gate) {
+                uint4 gq[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(stage + c2_epi_off(i * 8 + wr_row, wr_k)) = gq[i];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) gq[i] = *reinterpret_cast<const uint4*>(stage + c2_epi_off(lane, i));
-                    __syncwarp();
+                for (int i = 0; i < 4; ++i) {
+                    gq[i] = gq_next[i];
+                    gq_next[i] = gq_next2[i];
                 }
-                uint4 packed[4];
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    float f[8];
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) f[jj] = __uint_as_float(vv[g8 * 8 + jj]);
-                    const int n8 = n_base + g8 * 8;
-                    if (args.bias) {
-                        float b[8];
-                        c2_vec8(args.bias + n8, vec_ok, b);
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] += b[jj];
+                if (args.gate) {
+                    int nb;
+                    if (ci + 2 < Cfg::kNCH) {
+                        const int o = chunk_orow(v, row0, img, yh, xh, ci + 2, nb);
+                        gate_load(row0, o, nb, gq_next2);
+                    } else if (has_next) {
+                        const int o = chunk_orow(v_n, row0_n, img_n, yh_n, xh_n, ci + 2 - Cfg::kNCH, nb);
+                        gate_load(row0_n, o, nb, gq_next2);
                     }
-                    if (args.scale) {
-                        float sc[8], sh[8];
-                        c2_vec8(args.scale + n8, vec_ok, sc);
-                        c2_vec8(args.shift + n8, vec_ok, sh);
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc[jj], sh[jj]);
-                    }
-                    if (args.act == kActRelu) {
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
-                    } else if (args.act == kActLeaky) {
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
-                    }
-                    if (args.mask) {
-                        float m[8];
-                        const int mi = gm < args.M_total ? img : 0;
-                        c2_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m);
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) f[jj] *= m[jj];
-                    }
-                    if (args.gate) {
-                        const uint32_t w4[4] = {gq[g8].x, gq[g8].y, gq[g8].z, gq[g8].w};
-#pragma unroll
-                        for (int tt = 0; tt < 4; ++tt) {
-                            f[tt * 2] *= c2_lo(w4[tt]) > 0.f ? 1.f : args.slope;
-                            f[tt * 2 + 1] *= c2_hi(w4[tt]) > 0.f ? 1.f : args.slope;
-                        }
-                    }
-                    packed[g8] = make_uint4(c2_pack(f[0], f[1]), c2_pack(f[2], f[3]), c2_pack(f[4], f[5]),
-                                            c2_pack(f[6], f[7]));
                 }
                 const long long te2 = args.dbg ? clock64() : 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + c2_epi_off(lane, i)) = packed[i];
+                for (int p = 0; p < 8; ++p)
+                    *reinterpret_cast<uint4*>(stage + c2_epi_off(lane, p)) =
+                        make_uint4(vv[4 * p], vv[4 * p + 1], vv[4 * p + 2], vv[4 * p + 3]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = i * 8 + wr_row;
                     const int o = __shfl_sync(0xffffffffu, orow, r);
-                    const uint4 d = *reinterpret_cast<const uint4*>(stage + c2_epi_off(r, wr_k));
+                    const float4 lo4 = *reinterpret_cast<const float4*>(stage + c2_epi_off(r, 2 * wr_k));
+                    const float4 hi4 = *reinterpret_cast<const float4*>(stage + c2_epi_off(r, 2 * wr_k + 1));
+                    float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                    if (per_row_mask) {  // tiny grids (4 x 4): the rows of a chunk span several images
+                        const int mi = row0 + r < args.M_total ? (row0 + r) >> lgR : 0;
+                        c2_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m8);
+                    }
+                    const uint32_t w4[4] = {gq[i].x, gq[i].y, gq[i].z, gq[i].w};
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        float x = fmaf(f[jj] + b8[jj], sc8[jj], sh8[jj]);
+                        x = x > 0.f ? x : x * act_slope;
+                        const float g = (jj & 1) ? c2_hi(w4[jj >> 1]) : c2_lo(w4[jj >> 1]);
+                        f[jj] = x * m8[jj] * (g > 0.f ? 1.f : args.slope);
+                    }
+                    const uint4 d = make_uint4(c2_pack(f[0], f[1]), c2_pack(f[2], f[3]), c2_pack(f[4], f[5]),
+                                               c2_pack(f[6], f[7]));
                     if (row0 + r < args.M_total)
-                        *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n_base + wr_k * 8) = d;
+                        *reinterpret_cast<uint4*>(outp + static_cast<size_t>(o) * args.ldo + n8) = d;
                 }
                 __syncwarp();
                 if (args.dbg) {
@@ -436,6 +473,12 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                     t_store += clock64() - te2;
                 }
             }
+            v = v_n;
+            row0 = row0_n;
+            img = img_n;
+            yh = yh_n;
+            xh = xh_n;
+            if (u + 2 * unit_step < total_units) unit_rows(u + 2 * unit_step, v_1, row0_1, img_1, yh_1, xh_1);
         }
         if (args.dbg && warp == 2 && lane == 0) {
             long long* d = args.dbg + blockIdx.x * 16;
@@ -523,7 +566,8 @@ bool conv2_supported(ConvMode mode, int inH, int inW, int Cin, int Cout) {
     if (mode == kConvS2) return Cout == 128 && inW / 2 == 16 && inH / 2 >= 8 && (inH / 2) % 8 == 0;  // D conv1 forward
     if (mode == kConvT) {
         if (Cout == 64) return inW == 16 && inH % 8 == 0;   // D conv1 data gradient: four parities per unit
-        if (Cout == 128) return inW == 8 && inH == 8;       // D conv2 data gradient: one vertical parity per unit
+        // D conv2 data gradient (one vertical parity per unit) measures the same as the one-CTA kernel: opt-in only
+        if (Cout == 128) return inW == 8 && inH == 8 && getenv("SIGGAN_CONV2_T2") != nullptr;
     }
     return false;
 }
