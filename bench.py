@@ -190,10 +190,8 @@ def run_ours(args, rank, local_rank, world):
     torch.manual_seed(1234 + rank)
     gan = VanillaGAN(latent_dim=100, image_size=S, device=str(dev))
     gan._fused_ready()
-    if world > 1:   # identical initial replicas
-        dist.broadcast(gan.generator._flat.flat, 0)
-        dist.broadcast(gan.generator._flat.stats, 0)
-        dist.broadcast(gan.discriminator._flat.flat, 0)
+    from data_parallel import broadcast_replica_
+    broadcast_replica_([gan.generator._flat.flat, gan.generator._flat.stats, gan.discriminator._flat.flat])  # identical replicas
     lib = L.load_library()
     n_pool = 4     # 4 distinct real batches (268 MB fp32 at B=4096) > 126 MB L2; activations per step are several GB
     pool = synthetic_signatures(n_pool * B, S, dev, seed=1234 + rank).view(n_pool, B, 1, S, S)

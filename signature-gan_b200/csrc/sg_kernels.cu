@@ -186,21 +186,42 @@ __device__ __forceinline__ int perm_index(int j, int perm_c0) {
     return perm_c0 > 0 ? (j % perm_c0) * 16 + j / perm_c0 : j;
 }
 
+// The finalize kernels fold `chunks` (up to 592) partial rows per output element. One WARP per element: lanes stride
+// over the chunks (32 independent loads in flight) and the lane sums are folded in a fixed butterfly order, so the
+// result is deterministic. (One thread per element walking the rows serially took 20-65 us per launch for the
+// 32-channel layers — ~20 such launches per training step.)
+constexpr int kFinThreads = 256;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void chunk_sums(const float* __restrict__ partial, int chunks, long stride, long off0,
+                                           long off1, bool two, double& s0, double& s1) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (int k = lane; k < chunks; k += 32) {
+        a += partial[k * stride + off0];
+        if (two) b += partial[k * stride + off1];
+    }
+    s0 = warp_sum(a);
+    s1 = two ? warp_sum(b) : 0.0;
+}
+inline int fin_blocks(int elems) { return (elems + kFinThreads / 32 - 1) / (kFinThreads / 32); }
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, long rows, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int batch_stats, int perm_c0, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (j >= C) return;
     const int p = perm_index(j, perm_c0);
     float mu, var;
+    double s0 = 0.0, s1 = 0.0;
+    if (batch_stats) chunk_sums(partial, chunks, 2L * C, j, C + j, true, s0, s1);
+    if ((threadIdx.x & 31) != 0) return;
     if (batch_stats) {
-        double s0 = 0.0, s1 = 0.0;
-        for (int k = 0; k < chunks; ++k) {
-            s0 += partial[static_cast<long>(k) * 2 * C + j];
-            s1 += partial[static_cast<long>(k) * 2 * C + C + j];
-        }
         const double m = s0 / rows;
         double v = s1 / rows - m * m;
         if (v < 0.0) v = 0.0;
@@ -224,7 +245,7 @@ void bn_finalize(const float* partial, int chunks, long rows, int C, const float
                  float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
                  float* mean, float* rstd, float* scale, float* shift, cudaStream_t s) {
     note_launch();
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, beta, running_mean,
+    bn_finalize_kernel<<<fin_blocks(C), kFinThreads, 0, s>>>(partial, chunks, rows, C, gamma, beta, running_mean,
                                                       running_var, momentum, eps, batch_stats, perm_c0, mean, rstd,
                                                       scale, shift);
 }
@@ -257,14 +278,12 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ch
                                        float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
                                        float* __restrict__ k3) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (j >= C) return;
     const int p = perm_index(j, perm_c0);
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-        s0 += partial[static_cast<long>(k) * 2 * C + j];
-        s1 += partial[static_cast<long>(k) * 2 * C + C + j];
-    }
+    double s0, s1;
+    chunk_sums(partial, chunks, 2L * C, j, C + j, true, s0, s1);
+    if ((threadIdx.x & 31) != 0) return;
     // raw mode: the second partial is sum d*y; sum d*xhat = rstd * (sum d*y - mean * sum d)
     if (raw_mean) s1 = static_cast<double>(rstd[j]) * (s1 - static_cast<double>(raw_mean[j]) * s0);
     dbeta[p] = static_cast<float>(s0);
@@ -277,7 +296,7 @@ void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const f
                      const float* raw_mean, int batch_stats, int perm_c0, float* dgamma, float* dbeta, float* k1,
                      float* k2, float* k3, cudaStream_t s) {
     note_launch();
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, rows, C, gamma, rstd, raw_mean, batch_stats,
+    bn_bwd_finalize_kernel<<<fin_blocks(C), kFinThreads, 0, s>>>(partial, chunks, rows, C, gamma, rstd, raw_mean, batch_stats,
                                                           perm_c0, dgamma, dbeta, k1, k2, k3);
 }
 
@@ -315,20 +334,18 @@ template void bn_bwd_apply<bf16>(const bf16*, const bf16*, const float*, const f
 
 __global__ void col_finalize_kernel(const float* __restrict__ partial, int chunks, int C, int perm_c0,
                                     float* __restrict__ out0, float* __restrict__ out1) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per column
     if (j >= C) return;
     const int p = perm_index(j, perm_c0);
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-        s0 += partial[static_cast<long>(k) * 2 * C + j];
-        if (out1) s1 += partial[static_cast<long>(k) * 2 * C + C + j];
-    }
+    double s0, s1;
+    chunk_sums(partial, chunks, 2L * C, j, C + j, out1 != nullptr, s0, s1);
+    if ((threadIdx.x & 31) != 0) return;
     if (out0) out0[p] = static_cast<float>(s0);
     if (out1) out1[p] = static_cast<float>(s1);
 }
 void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* out0, float* out1, cudaStream_t s) {
     note_launch();
-    col_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, chunks, C, perm_c0, out0, out1);
+    col_finalize_kernel<<<fin_blocks(C), kFinThreads, 0, s>>>(partial, chunks, C, perm_c0, out0, out1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,10 +353,11 @@ void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* o
 // ------------------------------------------------------------------------------------------------
 __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunks, int n, float* __restrict__ out_a,
                                     int na, float* __restrict__ out_b) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per element
     if (j >= n) return;
-    double s = 0.0;
-    for (int k = 0; k < chunks; ++k) s += partial[static_cast<long>(k) * n + j];
+    double s, unused;
+    chunk_sums(partial, chunks, n, j, 0, false, s, unused);
+    if ((threadIdx.x & 31) != 0) return;
     if (j < na)
         out_a[j] = static_cast<float>(s);
     else if (out_b)
@@ -348,7 +366,7 @@ __global__ void vec_finalize_kernel(const float* __restrict__ partial, int chunk
 
 void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na, float* out_b, cudaStream_t s) {
     note_launch();
-    vec_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, chunks, n, out_a, na, out_b);
+    vec_finalize_kernel<<<fin_blocks(n), kFinThreads, 0, s>>>(partial, chunks, n, out_a, na, out_b);
 }
 
 // ------------------------------------------------------------------------------------------------

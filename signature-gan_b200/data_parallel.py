@@ -1,0 +1,48 @@
+"""Data-parallel plumbing of the training step: one process per GPU, full replicas, the step shards by
+batch. Losses are batch means, so the global-batch gradient of everything except BatchNorm statistics is the mean of
+the per-rank gradients: each rank runs its local D / G backward into the flat fp32 gradient bucket of the network
+(`_siggan_lib.FlatParams.grad_staging()`), the bucket is summed over ranks with ONE all-reduce (NCCL over
+NVLink / NVSwitch on the GPU box, gloo in the CPU tests) and scaled by 1 / world_size before the fused Adam update.
+BatchNorm statistics stay local (the DDP convention; at 4096 images per replica they match the reference run at that
+batch). The reference scripts are single-process (train…:494-502); multi-GPU runs are driven by bench.py / a launcher
+using these helpers with the same modules.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) outside a process group."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def average_gradients_(flat_grad: torch.Tensor, group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+    """In place: flat_grad <- mean over ranks of flat_grad. A no-op for a single process."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat_grad
+    n = dist.get_world_size(group)
+    if n > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.mul_(1.0 / n)
+    return flat_grad
+
+
+def broadcast_replica_(tensors: Iterable[torch.Tensor], src: int = 0) -> None:
+    """Make every rank start from rank `src`'s parameters / BatchNorm statistics (flat buffers, one broadcast each)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, src)
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) share of `n_items` for `rank`; shares differ by at most one item."""
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)

@@ -251,10 +251,8 @@ class VanillaGAN(nn.Module):
 
     def _allreduce(self, flat_grad: torch.Tensor) -> None:
         """Data-parallel: average the flat gradient bucket across ranks (NCCL over NVLink) before the update."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-            flat_grad.mul_(1.0 / dist.get_world_size())
+        from data_parallel import average_gradients_
+        average_gradients_(flat_grad)
 
     def discriminator_step_async(self, real_images: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Enqueue one D step (reference vanilla…:180-252) without synchronising; metrics stay on the device."""
