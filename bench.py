@@ -162,8 +162,11 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "training images/sec (G+D step)", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"train_step_{args.size}x{args.size}", "batch_per_step": args.cpu_batch,
-                   "note": "oracle port of the reference algorithm on torch CPU (the reference is pure PyTorch)"},
+        "config": {"workload": f"train_step_{args.size}x{args.size}_b{args.batch}_per_gpu",
+                   "global_batch": args.gpus * args.batch, "image_size": args.size, "latent_dim": 100,
+                   "parallelism": f"dp{args.gpus}", "n_critic": 1, "cpu_sample_batch": args.cpu_batch,
+                   "note": "the reference is pure PyTorch: its CPU implementation of the step (oracle port of the same "
+                           "algorithm, torch CPU fp32, all host threads) timed on a bounded sample of the workload"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -294,9 +297,23 @@ def run_ours(args, rank, local_rank, world):
         if tensor_ops:
             k, a = tensor_ops[0]
             ach = a[1] / (a[0] * 1e-3) / 1e12
+            # DRAM traffic per launch from the committed ncu --set full capture of this op's kernel (per image x the
+            # images of an average launch of the op: the D step runs it on 2B images, the G step on B)
+            traffic, traffic_src = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+                    t = json.load(f).get(k)
+                if t and S == 64:
+                    per_img = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["images"]
+                    flops_per_img = {"d.c1.dgrad": 2.0 * 256 * 16 * 64 * 128}.get(k)
+                    imgs_per_launch = (a[1] / a[3]) / flops_per_img if flops_per_img else B
+                    traffic, traffic_src = per_img * imgs_per_launch, t["source"]
+            except Exception:
+                pass
             line["roofline"] = {"bound": "tensor", "kernel": k, "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                                "ms_per_launch": a[0] / a[3], "share_of_step": a[0] / tot, "peak_source": pk["source"]}
+                                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                                "traffic_source": traffic_src, "ms_per_launch": a[0] / a[3], "share_of_step": a[0] / tot,
+                                "peak_source": pk["source"]}
         line["ops_ms_per_step"] = {k: round(a[0] / prof_steps, 4) for k, a in ops}
         line["ops_total_ms_per_step"] = tot / prof_steps
         tens = sum(a[0] for k, a in tensor_ops)

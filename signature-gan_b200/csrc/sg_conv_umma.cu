@@ -168,7 +168,7 @@ __device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 128 +
 // sum of squares of the stored (bf16-rounded) outputs — the BatchNorm batch statistics of gen…:58 — and the CTA writes
 // one partial row stats_partial[blockIdx.x][2][BN], so that no separate pass over the convolution output is needed.
 template <int BN, int BK, bool kPair, bool kStats>
-__global__ void __launch_bounds__(kThreads, ConvCfg<BN, BK, kPair>::kCtasPerSm)
+__global__ void __launch_bounds__(kThreads, kStats ? 1 : ConvCfg<BN, BK, kPair>::kCtasPerSm)  // statistics: +32..64 registers
 conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     using Cfg = ConvCfg<BN, BK, kPair>;
     constexpr int STAGES = Cfg::kStages;

@@ -447,15 +447,19 @@ static void perf_conv(const char* name, sg::ConvMode mode, int N, int H, int W, 
     a.ldo = Cout;
     bf16* gate = nullptr;
     float *mask = nullptr, *bias = nullptr;
-    if (epi == 1) {  // data-gradient epilogue: gate (saved activation) + dropout mask
-        CK(cudaMalloc(&gate, on * 2));
-        CK(cudaMemset(gate, 0x3f, on * 2));
-        CK(cudaMalloc(&mask, (size_t)N * Cout * 4));
-        CK(cudaMemset(mask, 0, (size_t)N * Cout * 4));
-        a.gate = gate;
+    if (epi == 1 || epi == 3 || epi == 4) {  // data-gradient epilogue: gate (saved activation) + dropout mask
         a.slope = 0.2f;
-        a.mask = mask;
-        a.ldmask = Cout;
+        if (epi != 4) {
+            CK(cudaMalloc(&gate, on * 2));
+            CK(cudaMemset(gate, 0x3f, on * 2));
+            a.gate = gate;
+        }
+        if (epi != 3) {
+            CK(cudaMalloc(&mask, (size_t)N * Cout * 4));
+            CK(cudaMemset(mask, 0, (size_t)N * Cout * 4));
+            a.mask = mask;
+            a.ldmask = Cout;
+        }
     } else if (epi == 2) {  // forward epilogue: bias + LeakyReLU + dropout mask
         CK(cudaMalloc(&bias, Cout * 4));
         CK(cudaMemset(bias, 0, Cout * 4));
@@ -596,6 +600,10 @@ int main(int argc, char** argv) {
         perf_conv("D dgrad c3 +gate,mask", sg::kConvT, B, 4, 4, 512, 256, 1);
         perf_conv("D dgrad c2 +gate,mask", sg::kConvT, B, 8, 8, 256, 128, 1);
         perf_conv("D dgrad c1 +gate,mask", sg::kConvT, B, 16, 16, 128, 64, 1);
+        perf_conv("D dgrad c1 +gate only", sg::kConvT, B, 16, 16, 128, 64, 3);
+        perf_conv("D dgrad c1 +mask only", sg::kConvT, B, 16, 16, 128, 64, 4);
+        perf_conv("D dgrad c2 +gate only", sg::kConvT, B, 8, 8, 256, 128, 3);
+        perf_conv("D dgrad c2 +mask only", sg::kConvT, B, 8, 8, 256, 128, 4);
         perf_wgrad("wgrad c3 512|256 @4x4", B, 4, 4, 512, 256);
         perf_wgrad("wgrad c2 256|128 @8x8", B, 8, 8, 256, 128);
         perf_wgrad("wgrad c1 128|64 @16x16", B, 16, 16, 128, 64);
