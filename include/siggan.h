@@ -69,6 +69,9 @@ int sg_g_bn_info(const sg_ctx* ctx, int index, long long* mean_offset, long long
 size_t sg_g_workspace_bytes(const sg_ctx* ctx, int batch);   /* saved activations of one G forward */
 size_t sg_d_workspace_bytes(const sg_ctx* ctx, int batch);   /* saved activations of one D forward */
 long long sg_d_mask_count(const sg_ctx* ctx, int batch);     /* floats: sum_i batch*C_i */
+/* element offset of the last conv block's weight in the flat D parameter / gradient buffer: [offset, count) is the
+ * part of the bucket whose gradients the D backward finishes first (all-reduce overlap, see sg_train_step) */
+long long sg_d_grad_tail_offset(const sg_ctx* ctx);
 long long sg_d_feature_count(const sg_ctx* ctx);             /* 512*4*4 */
 
 /* ---- Generator ------------------------------------------------------------------------------ */
@@ -117,7 +120,10 @@ typedef struct sg_train_state {
 /* metrics_out (device, 12 floats): d_loss, d_loss_real, d_loss_fake, d_real_acc, d_fake_acc, d_real_mean,
  * d_fake_mean, g_loss, g_fake_mean, 0, 0, 0.  phase: 0 = whole step; 1 = D forward+backward only (grads in
  * d_grads), 2 = D Adam, 3 = G forward+backward (grads in g_grads), 4 = G Adam — phases let a data-parallel
- * caller all-reduce the flat gradient buckets between backward and update. */
+ * caller all-reduce the flat gradient buckets between backward and update.
+ * Overlapping the D all-reduce with backward: phase 11 = D forward + the classifier / last conv block part of the
+ * backward (their gradients, the contiguous tail of the bucket from sg_d_grad_tail_offset() on — 76 % of it — are
+ * final when it returns), phase 12 = the rest of the D backward; 11 followed by 12 equals phase 1. */
 int sg_train_step(sg_ctx* ctx, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
                   int batch, float* d_grads, float* g_grads, float* metrics_out, int phase, void* stream);
 

@@ -53,6 +53,7 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_g_workspace_bytes": (_SZ, [_P, _I]),
     "sg_d_workspace_bytes": (_SZ, [_P, _I]),
     "sg_d_mask_count": (_LL, [_P, _I]),
+    "sg_d_grad_tail_offset": (_LL, [_P]),
     "sg_d_feature_count": (_LL, [_P]),
     "sg_g_forward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "sg_g_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -595,9 +595,11 @@ int d_forward_t(sg_ctx* c, const float* params, const float* x, int B, const flo
 }
 
 // dlogit: d(loss)/d(logit) per sample (already includes sigmoid').
+// stage 0: whole backward; 1: classifier + last conv block only (the tail of the gradient bucket is final afterwards);
+// 2: the remaining blocks (continues from the scratch buffers stage 1 left).
 template <typename T>
 int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_ptr, const float* masks,
-                 const float* dlogit, int B, float* grads, float* dx, cudaStream_t s) {
+                 const float* dlogit, int B, float* grads, float* dx, cudaStream_t s, int stage = 0) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     DWs w = carve_d(c, const_cast<void*>(ws_ptr), B);
     const float slope = c->cfg.leaky_slope;
@@ -607,7 +609,12 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     char* nxt = static_cast<char*>(c->bufB.p);
     const int last = c->ND - 1, Cl = c->dch[c->ND];
     const double es = c->es;
-    {
+    if (stage == 2) {  // stage 1 processed block `last` and swapped the scratch buffers once
+        char* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (stage != 2) {
     PROF("d.cls_bwd", 4.0 * B * Cl * 16, 3.0 * es * B * Cl * 16.0);
     if (grads) {
         const int chunks = sg::col_reduce<T>(2, reinterpret_cast<const T*>(w.a[last]), nullptr, nullptr, nullptr, dlogit,
@@ -618,7 +625,7 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     sg::classifier_bwd_dy<T>(dlogit, c->cls_wp, masks ? masks + mask_offset(c, B, last) : nullptr,
                              reinterpret_cast<const T*>(w.a[last]), slope, reinterpret_cast<T*>(cur), B, Cl, s);
     }
-    for (int i = last; i >= 1; --i) {
+    for (int i = (stage == 2 ? last - 1 : last); i >= (stage == 1 ? last : 1); --i) {
         const int oh = d_spatial(c, i), Cin = c->dch[i], Cout = c->dch[i + 1];
         const long rows = static_cast<long>(B) * oh * oh;
         const std::string nm = "d.c" + std::to_string(i);
@@ -664,6 +671,10 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
         nxt = t;
     }
     const int o0 = c->S / 2;
+    if (stage == 1) {
+        SG_KCHECK("d_backward");
+        return 0;
+    }
     if (grads) {
         PROF("d.c0.wgrad", 2.0 * B * o0 * o0 * 16.0 * c->dch[1], (double)B * (4.0 * c->S * c->S + es * o0 * o0 * c->dch[1]));
         sg::d_conv0_wgrad<T>(x, reinterpret_cast<const T*>(cur), grads + c->dt[c->d_conv_w[0]].offset, cpart, B, c->S,
@@ -864,6 +875,7 @@ int sg_g_bn_info(const sg_ctx* c, int index, long long* mean_offset, long long* 
 size_t sg_g_workspace_bytes(const sg_ctx* c, int batch) { return carve_g(c, nullptr, batch).bytes; }
 size_t sg_d_workspace_bytes(const sg_ctx* c, int batch) { return carve_d(c, nullptr, batch).bytes; }
 long long sg_d_mask_count(const sg_ctx* c, int batch) { return mask_offset(c, batch, c->ND); }
+long long sg_d_grad_tail_offset(const sg_ctx* c) { return c->dt[c->d_conv_w[c->ND - 1]].offset; }
 long long sg_d_feature_count(const sg_ctx* c) { return (long long)c->dch[c->ND] * 16; }
 
 int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, int batch, int bn_batch_stats, void* ws,
@@ -958,7 +970,12 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
     SG_TRY(c->dximg.ensure(img * 4));
     float* x2 = static_cast<float*>(c->x2.p);
     const bool dropout = st->dropout_p > 0.f;
-    if (phase == 0 || phase == 1) {
+    if (phase == 12) {
+        if (!d_grads) return fail("sg_train_step: D phase needs d_grads");
+        const float* masks = dropout ? static_cast<const float*>(c->masks2.p) : nullptr;
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s, 2));
+    }
+    if (phase == 0 || phase == 1 || phase == 11) {
         if (!real || !noise_d || !d_grads) return fail("sg_train_step: D phase needs real, noise_d and d_grads");
         // ---- D step (train…:281-337): D.train(), G.eval(); one 2B batch [real | G(noise)] since D has no batch coupling
         cudaError_t e = cudaMemcpyAsync(x2, real, img * 4, cudaMemcpyDeviceToDevice, s);
@@ -985,7 +1002,8 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
         SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s));
         DWs w = carve_d(c, c->d_ws.p, 2 * B);
         sg::d_loss_metrics(w.prob, B, st->label_smoothing, metrics, c->dlogit, s);
-        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s));
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s,
+                          phase == 11 ? 1 : 0));
     }
     if (phase == 0 || phase == 2) {
         if (!d_grads) return fail("sg_train_step: D update needs d_grads");

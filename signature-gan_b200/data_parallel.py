@@ -33,6 +33,22 @@ def average_gradients_(flat_grad: torch.Tensor, group: Optional["dist.ProcessGro
     return flat_grad
 
 
+def all_reduce_start(part: torch.Tensor, group: Optional["dist.ProcessGroup"] = None):
+    """Start summing `part` (a contiguous slice of a gradient bucket) over ranks without blocking the caller's stream:
+    NCCL runs the collective on its own stream after the work already enqueued on the current stream, so kernels
+    enqueued afterwards (the rest of the backward pass) overlap it. Returns a work handle for all_reduce_finish."""
+    return dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
+def all_reduce_finish(works, flat_grad: torch.Tensor, group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+    """Make the current stream wait for the started reductions, then turn the summed bucket into the mean."""
+    for w in works:
+        if w is not None:
+            w.wait()
+    flat_grad.mul_(1.0 / dist.get_world_size(group))
+    return flat_grad
+
+
 def broadcast_replica_(tensors: Iterable[torch.Tensor], src: int = 0) -> None:
     """Make every rank start from rank `src`'s parameters / BatchNorm statistics (flat buffers, one broadcast each)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

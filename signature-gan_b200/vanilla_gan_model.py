@@ -271,8 +271,18 @@ class VanillaGAN(nn.Module):
         dgrads = self.discriminator._flat.grad_staging()
         stream = L.current_stream(dev)
         args = (sctx.handle, C.byref(st), L.ptr(real), L.ptr(noise), None, B, L.ptr(dgrads), None, L.ptr(self._metrics))
-        L.check(sctx.lib.sg_train_step(*args, 1, stream), "sg_train_step(D backward)")
-        self._allreduce(dgrads)
+        import data_parallel as dp
+        if dp.world()[1] > 1:
+            # data-parallel: the all-reduce of the bucket's tail (classifier + last conv block, 76 % of the bytes,
+            # final first) runs on NCCL's stream while the rest of the D backward executes
+            tail = int(sctx.lib.sg_d_grad_tail_offset(sctx.handle))
+            L.check(sctx.lib.sg_train_step(*args, 11, stream), "sg_train_step(D backward, last block)")
+            w_tail = dp.all_reduce_start(dgrads[tail:])
+            L.check(sctx.lib.sg_train_step(*args, 12, stream), "sg_train_step(D backward, remaining blocks)")
+            w_head = dp.all_reduce_start(dgrads[:tail])
+            dp.all_reduce_finish([w_tail, w_head], dgrads)
+        else:
+            L.check(sctx.lib.sg_train_step(*args, 1, stream), "sg_train_step(D backward)")
         L.check(sctx.lib.sg_train_step(*args, 2, stream), "sg_train_step(D update)")
         self.d_optimizer.advance()
         self.discriminator._flat.expose(dgrads)

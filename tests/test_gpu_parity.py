@@ -339,3 +339,35 @@ def test_checkpoint_round_trip(tmp_path):
     gan2.d_optimizer.load_state_dict(ref_opt.state_dict())
     gan2.d_optimizer._ensure_state()
     assert gan2.d_optimizer._steps == 1 and torch.allclose(gan2.d_optimizer._m, torch.full_like(gan2.d_optimizer._m, 0.5))
+
+
+def test_split_d_backward_phases_equal_the_fused_phase():
+    """Phases 11 + 12 of sg_train_step (used to overlap the D gradient all-reduce with backward) == phase 1, bitwise."""
+    import ctypes as C
+    import _siggan_lib as L
+    B, size = 48, 64
+    real = O.synthetic_signatures(B, size, seed=3).cuda()
+    noise = O.hash_normal((B, 100), 5).cuda()
+    grads = []
+    for split in (False, True):
+        gan, _, _ = make_gan(size, 6, "bf16")
+        torch.manual_seed(11)
+        gan.discriminator.train()
+        gan.generator.eval()
+        sctx = gan._fused_ready()
+        st = gan._state(None)
+        dg = gan.discriminator._flat.grad_staging()
+        dg.fill_(float("nan"))
+        stream = L.current_stream(real.device)
+        args = (sctx.handle, C.byref(st), L.ptr(real), L.ptr(noise), None, B, L.ptr(dg), None, L.ptr(gan._metrics))
+        if split:
+            L.check(sctx.lib.sg_train_step(*args, 11, stream), "phase 11")
+            tail = int(sctx.lib.sg_d_grad_tail_offset(sctx.handle))
+            torch.cuda.synchronize()
+            assert torch.isfinite(dg[tail:]).all() and torch.isnan(dg[:tail]).all()   # only the tail is final
+            L.check(sctx.lib.sg_train_step(*args, 12, stream), "phase 12")
+        else:
+            L.check(sctx.lib.sg_train_step(*args, 1, stream), "phase 1")
+        torch.cuda.synchronize()
+        grads.append(dg.clone())
+    assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1])
