@@ -33,7 +33,7 @@ namespace {
 
 constexpr int kC2Threads = 64 + 32 * 8;
 constexpr int kC2MaxStages = 24, kC2MaxProds = 32;
-constexpr int kC2ASlot = 20 * 1024;   // largest A box: (8+2) rows x 16 px x 128 B
+constexpr int kC2ASlot = 24 * 1024;   // largest A box: (4+2) rows x 32 px x 128 B (20 KB for 16-wide grids)
 constexpr int kC2EpiStage = 32 * 128;  // per epilogue warp: 32 rows x 32 fp32 columns
 
 struct C2Stage {
@@ -156,7 +156,7 @@ struct C2Cfg {
     // stage = one A box + the weight tiles of all its products on ONE barrier pair: the per-stage cost of the
     // single-thread roles (wait, expect_tx, commit) is paid once per 2..8 products
     static constexpr int kSlot = kC2ASlot + kMaxProd * kBSlot;
-    static constexpr int kStagesFit = (176 * 1024) / kSlot;
+    static constexpr int kStagesFit = (184 * 1024) / kSlot;
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kBars = 2 * kStages + 4;
@@ -563,9 +563,10 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
 // Shapes this kernel takes over from the generic one (everything else keeps its existing path).
 bool conv2_supported(ConvMode mode, int inH, int inW, int Cin, int Cout) {
     if (Cin % 64 != 0) return false;
-    if (mode == kConvS2) return Cout == 128 && inW / 2 == 16 && inH / 2 >= 8 && (inH / 2) % 8 == 0;  // D conv1 forward
+    if (mode == kConvS2)  // D conv1 forward (64x64 and 128x128 images)
+        return Cout == 128 && (inW / 2 == 16 || inW / 2 == 32) && ((inH / 2) * (inW / 2)) % 128 == 0;
     if (mode == kConvT) {
-        if (Cout == 64) return inW == 16 && inH % 8 == 0;   // D conv1 data gradient: four parities per unit
+        if (Cout == 64) return (inW == 16 || inW == 32) && (inH * inW) % 128 == 0;   // D conv1 data gradient: four parities per unit
         // D conv2 data gradient (one vertical parity per unit) measures the same as the one-CTA kernel: opt-in only
         if (Cout == 128) return inW == 8 && inH == 8 && getenv("SIGGAN_CONV2_T2") != nullptr;
     }

@@ -55,7 +55,7 @@ struct T4Cfg {
     static constexpr int kRowBytes = BK * 2;
     static constexpr int kWTapBytes = BN * kRowBytes;
     static constexpr int kWBytes = 16 * kWTapBytes;
-    static constexpr int kABufMax = (BK == 32 ? 6 * 32 : 10 * 16) * kRowBytes;  // (BH+2)*GW rows; see convt4_supported
+    static constexpr int kABufMax = (BK == 32 ? 4 * 64 : 10 * 16) * kRowBytes;  // (BH+2)*GW rows; see convt4_supported
     static constexpr int kStageBytes = 3 * kABufMax;
     static constexpr int kStages = BK == 32 ? 3 : 2;
     static constexpr int kTmemCols = 256;  // 2 x [py][px][32]
@@ -314,7 +314,7 @@ int launch_t4(const ConvT4Args& a, int grid, cudaStream_t stream) {
 // Cout 32; Cin 32 with a 32- or 64-wide... the (BH+2)*GW row count of one A buffer must fit T4Cfg::kABufMax.
 bool convt4_supported(int inH, int inW, int Cin, int Cout) {
     if (Cout != 32 || inH * inW < 128 || (inH * inW) % 128 != 0) return false;
-    if (Cin == 32) return inW == 32;   // 6 x 32 rows per buffer
+    if (Cin == 32) return inW == 32 || inW == 64;   // 6 x 32 or 4 x 64 rows per buffer (128x128 images: last block)
     if (Cin == 64) return inW == 16;   // 10 x 16 rows per buffer
     return false;
 }

@@ -563,6 +563,7 @@ int main(int argc, char** argv) {
     // phase-fused thin transposed convolutions (sg_convt4.cu): no bias/mask/gate epilogue
     RUN(test_conv("convT4 6x32x32x32->32", sg::kConvT, 6, 32, 32, 32, 32, false));
     RUN(test_conv("convT4 40x32x32x32->32 (320 t)", sg::kConvT, 40, 32, 32, 32, 32, false));
+    RUN(test_conv("convT4 3x64x64x32->32 (128x128 tail)", sg::kConvT, 3, 64, 64, 32, 32, false));
     RUN(test_conv("convT4 5x16x16x64->32", sg::kConvT, 5, 16, 16, 64, 32, false));
     RUN(test_conv("convT4 200x16x16x64->32 (400 t)", sg::kConvT, 200, 16, 16, 64, 32, false));
     RUN(test_wgrad("wgrad 8x16x16 128|64", 8, 16, 16, 128, 64));
@@ -576,6 +577,8 @@ int main(int argc, char** argv) {
     RUN(test_conv("conv2 S2 161x32x32x64->128", sg::kConvS2, 161, 32, 32, 64, 128, true));
     RUN(test_conv("conv2 T4 5x16x16x128->64 +epi", sg::kConvT, 5, 16, 16, 128, 64, true));
     RUN(test_conv("conv2 T4 171x16x16x128->64", sg::kConvT, 171, 16, 16, 128, 64, false));
+    RUN(test_conv("conv2 S2 3x64x64x64->128 +epi", sg::kConvS2, 3, 64, 64, 64, 128, true));
+    RUN(test_conv("conv2 T4 3x32x32x128->64 +epi", sg::kConvT, 3, 32, 32, 128, 64, true));
     RUN(test_conv("conv2 T2 7x8x8x256->128 +epi", sg::kConvT, 7, 8, 8, 256, 128, true));
     RUN(test_conv("conv2 T2 341x8x8x256->128", sg::kConvT, 341, 8, 8, 256, 128, true));
     RUN(test_gfinal("gfinal 5x64 train", 5, 64, true, false));
