@@ -901,6 +901,171 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ----------------------------------------------------------------------------
+// CTA-pair weight gradient (Mc >= 256): one 256 x 256 UMMA (cta_group::2) per K step. Each CTA stages its own 128
+// coarse channels and only HALF of the fine-tensor atoms, so a stage is 32 KB per SM per 512 MMA clocks (64 B/clk,
+// the SM's ingest rate) instead of 48 KB: the one-CTA kernel above is ingest-bound at ~70 % of the tensor peak.
+// ----------------------------------------------------------------------------
+struct Wg2Cfg {
+    static constexpr int kAtomBytes = kWgK * 128;
+    static constexpr int kABytes = 2 * kAtomBytes;      // this CTA's 128 coarse channels
+    static constexpr int kBBytes = 2 * kAtomBytes;      // this CTA's half (128 columns) of the 256-column B tile
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = 6;
+    static constexpr int kTmemCols = 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(kWgThreads) wgrad2_umma_kernel(const __grid_constant__ WgradArgs args) {
+    using Cfg = Wg2Cfg;
+    constexpr int STAGES = Cfg::kStages, BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = uniform_warp_idx();
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int tile_m = blockIdx.x;  // = 2 * pair + rank
+    const int n_tiles = (args.Nf + BN - 1) / BN;
+    const int taps = 16;
+    const int tpc = args.tpc;
+    const int apt = (BN / 64) / tpc;
+    const int tap = (blockIdx.y / n_tiles) * tpc;
+    const int tile_n = blockIdx.y % n_tiles;
+    const int split = blockIdx.z;
+    const int kt_begin = static_cast<int>(static_cast<long>(args.k_tiles) * split / args.splits);
+    const int kt_end = static_cast<int>(static_cast<long>(args.k_tiles) * (split + 1) / args.splits);
+    const int num_k = kt_end - kt_begin;
+    const int R = args.GH * args.GW;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.cmap);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem2_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs; completion counted on the leader's barriers) ----------------
+        const bool issuer = elect_one();
+        const CUtensorMap* a_fm[2];
+        int a_dy[2], a_dx[2], a_ch[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int a = 2 * static_cast<int>(rank) + h;  // atom of the 256-column tile this CTA stages
+            const int ta = tap + a / apt, cb = a % apt;
+            const int ky = ta >> 2, kx = ta & 3;
+            a_fm[h] = &args.fmap[((ky + 1) & 1) * 2 + ((kx + 1) & 1)];
+            a_dy[h] = ((ky + 1) >> 1) - 1;
+            a_dx[h] = ((kx + 1) >> 1) - 1;
+            a_ch[h] = tile_n * BN + cb * 64;
+        }
+        const int lg_tpi = R >= kWgK ? 31 - __clz(R / kWgK) : 0, rows_per = kWgK / args.GW, ipk = R >= kWgK ? 1 : kWgK / R;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < num_k; ++it) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (issuer) {
+                uint8_t* sa = smem + s * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                const uint32_t bar = mapa_rank(smem_u32(&full_bar[s]), 0);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * Cfg::kStageBytes);
+                const int kt = kt_begin + it;
+                int n0, y0;
+                if (R >= kWgK) {
+                    n0 = kt >> lg_tpi;
+                    y0 = (kt & ((1 << lg_tpi) - 1)) * rows_per;
+                } else {
+                    n0 = kt * ipk;
+                    y0 = 0;
+                }
+                tma2_load_2d(sa, &args.cmap, bar, tile_m * 128, kt * kWgK);
+                tma2_load_2d(sa + Cfg::kAtomBytes, &args.cmap, bar, tile_m * 128 + 64, kt * kWgK);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma2_load_4d(sb + h * Cfg::kAtomBytes, a_fm[h], bar, a_ch[h], a_dx[h], y0 + a_dy[h], n0);
+            }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---------------- MMA issuer (leader CTA): 256 x 256 x 16 per instruction, both operands MN-major ----------------
+            constexpr uint32_t idesc = make_idesc_bf16(256, BN, 1, 1);
+            const bool issuer = elect_one();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < num_k; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint32_t b_addr = a_addr + Cfg::kABytes;
+                if (issuer) {
+#pragma unroll
+                    for (int k = 0; k < kWgK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
+                        const uint64_t db = make_smem_desc(b_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
+                        umma2_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
+                    }
+                    umma2_commit(&empty_bar[s]);
+                }
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            if (issuer) umma2_commit(accum_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = tile_m * 128 + q * 32 + lane;
+        if (num_k > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int atom = c0 >> 6;
+            const int ta = tap + atom / apt;
+            float* dst = args.partial + ((static_cast<size_t>(split) * taps + ta) * args.Mc + m) * args.Nf;
+            uint32_t v[32];
+            if (num_k > 0) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0;
+            }
+            const int n_base = tile_n * BN + (atom % apt) * 64 + (c0 & 63);
+            if (m < args.Mc && n_base < args.Nf) {
+                float4* o = reinterpret_cast<float4*>(dst + n_base);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem2_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 // partial [S][16][M][N] -> dW [M][N][16]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int S, int M, int N,
                                     int accumulate) {
@@ -933,18 +1098,39 @@ int wgrad_thin_ctas(int nimg, int cH, int cW);
 int launch_wgrad_thin(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
                       float* partial, float* dW, int accumulate, cudaStream_t stream);
 
-static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16) {
-    // Aim for ~2 waves of 148 SMs, at least 8 K-tiles per CTA.
-    const int base = m_tiles * n_tiles * taps;
-    int s = (2 * 148 + base - 1) / base;
-    if (s < 1) s = 1;
-    const int max_s = k_tiles / 8 > 0 ? k_tiles / 8 : 1;
-    if (s > max_s) s = max_s;
-    if (s > 32) s = 32;
-    return s;
+static bool wgrad_pairs(int Mc, int Nf);
+// Split-K factor: the launch is base * s CTAs (or CTA pairs) of one tile each on `slots` resident CTAs (pairs). Pick
+// the s with the smallest modelled time = waves x K-steps per CTA x MMA time of a K step + the partial buffer's
+// write + read (e.g. 32 pairs x 5 splits on 74 slots = 2.16 waves ran as 3; 23 splits fill the waves but move 193 MB).
+static int wgrad_splits(int k_tiles, int m_tiles, int n_tiles, int taps = 16, bool pairs = false, int bn = 256,
+                        double partial_bytes_per_split = 0.0) {
+    const int base = (pairs ? m_tiles / 2 : m_tiles) * n_tiles * taps;
+    const int slots = pairs ? 74 : 148;
+    int max_s = k_tiles / 16 > 0 ? k_tiles / 16 : 1;
+    if (max_s > 48) max_s = 48;
+    const double t_k = 1.25 * 2.0 * bn / 1.9e9;  // seconds per 64-pixel K step (4 MMAs of bn/2 cycles, 80 % efficiency)
+    int best = 1;
+    double best_t = 1e30;
+    for (int s = 1; s <= max_s; ++s) {
+        const int waves = (base * s + slots - 1) / slots;
+        const double t = waves * ((k_tiles + s - 1) / s) * t_k + 2.0 * s * partial_bytes_per_split / 5e12;
+        if (t < best_t * 0.99) {
+            best_t = t;
+            best = s;
+        }
+    }
+    return best;
 }
 
 static int wgrad_bn(int Nf) { return Nf >= 64 ? 256 : 64; }
+// CTA pairs along M (cta_group::2, wgrad2_umma_kernel); SIGGAN_WGRAD2=0 keeps the one-CTA kernel (A/B comparison)
+static bool wgrad_pairs(int Mc, int Nf) {
+    static const bool pair_ok = [] {
+        const char* e = getenv("SIGGAN_WGRAD2");
+        return !(e && e[0] == '0');
+    }();
+    return pair_ok && wgrad_bn(Nf) == 256 && Mc % 256 == 0;
+}
 static int fc_wgrad_bn(int Kp) { return Kp >= 256 ? 256 : (Kp >= 128 ? 128 : 64); }
 static int wgrad_tpc(int Nf) { return Nf == 64 ? 4 : (Nf == 128 ? 2 : 1); }  // filter taps stacked along N per CTA
 
@@ -952,7 +1138,8 @@ size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf) {
     if (wgrad_thin_supported(cH, cW, Mc, Nf)) return static_cast<size_t>(wgrad_thin_ctas(nimg, cH, cW)) * 16 * Mc * Nf;
     const int k_tiles = (nimg * cH * cW + kWgK - 1) / kWgK;
     const int BN = wgrad_bn(Nf);
-    const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN, 16 / wgrad_tpc(Nf));
+    const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN, 16 / wgrad_tpc(Nf), wgrad_pairs(Mc, Nf), BN,
+                               64.0 * Mc * Nf);
     return static_cast<size_t>(s) * 16 * Mc * Nf;
 }
 
@@ -995,7 +1182,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     const int BN = wgrad_bn(Nf);
     const int m_tiles = (Mc + 127) / 128, n_tiles = (Nf + BN - 1) / BN;
     a.tpc = wgrad_tpc(Nf);
-    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 16 / a.tpc);
+    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 16 / a.tpc, wgrad_pairs(Mc, Nf), BN, 64.0 * Mc * Nf);
     a.partial = partial;
     if (static_cast<size_t>(a.splits) * 16 * Mc * Nf > partial_floats) SG_FAIL("wgrad: partial workspace too small");
     if (make_map_2d(&a.cmap, coarse, Mc, pix, Mc, 64, kWgK)) return -1;
@@ -1005,7 +1192,32 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
         if (make_map_nhwc(&a.fmap[p], fine, nimg, 2 * cH, 2 * cW, Nf, 2, p >> 1, p & 1, 64, bw, bh, bn)) return -1;
     dim3 grid(m_tiles, (16 / a.tpc) * n_tiles, a.splits);
     int rc;
-    if (BN == 256)
+    if (wgrad_pairs(Mc, Nf)) {  // CTA pairs along M (cta_group::2)
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 Wg2Cfg::kSmemBytes);
+            if (e != cudaSuccess) SG_FAIL("cudaFuncSetAttribute(wgrad2_umma): %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+        note_launch();
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid;
+        lc.blockDim = dim3(kWgThreads);
+        lc.dynamicSmemBytes = Wg2Cfg::kSmemBytes;
+        lc.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        lc.attrs = &attr;
+        lc.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&lc, wgrad2_umma_kernel, a);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) SG_FAIL("wgrad2_umma launch: %s", cudaGetErrorString(e));
+        rc = 0;
+    } else if (BN == 256)
         rc = launch_wg<256>(a, grid, stream);
     else if (BN == 128)
         rc = launch_wg<128>(a, grid, stream);
@@ -1036,7 +1248,7 @@ __global__ void fc_wgrad_reduce_kernel(const float* __restrict__ partial, float*
 size_t fc_wgrad_partial_floats(int B, int F, int Kp) {
     const int k_tiles = (B + kWgK - 1) / kWgK;
     const int BN = fc_wgrad_bn(Kp);
-    const int s = wgrad_splits(k_tiles, (F + 127) / 128, (Kp + BN - 1) / BN, 1);
+    const int s = wgrad_splits(k_tiles, (F + 127) / 128, (Kp + BN - 1) / BN, 1, false, BN, 4.0 * F * Kp);
     return static_cast<size_t>(s) * F * Kp;
 }
 
@@ -1055,7 +1267,7 @@ int launch_fc_wgrad(const __nv_bfloat16* dy, const __nv_bfloat16* zp, int B, int
     a.k_tiles = (B + kWgK - 1) / kWgK;
     const int BN = fc_wgrad_bn(Kp);
     const int m_tiles = (F + 127) / 128, n_tiles = (Kp + BN - 1) / BN;
-    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 1);
+    a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 1, false, BN, 4.0 * F * Kp);
     a.partial = partial;
     if (static_cast<size_t>(a.splits) * F * Kp > partial_floats) SG_FAIL("fc_wgrad: partial workspace too small");
     if (make_map_2d(&a.cmap, dy, F, B, F, 64, kWgK)) return -1;
