@@ -40,11 +40,14 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         bs[nb][1] = bias[nb * 8 + 2 * t4 + 1];
     }
     const int ky0 = t4 >> 1, kxo = 2 * (t4 & 1);
-    const long total = static_cast<long>(B) * O * tpr;
-    for (long tile = static_cast<long>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<long>(gridDim.x) * 8) {
-        const int ox0 = static_cast<int>(tile % tpr) * 16;
-        const long r = tile / tpr;
-        const int oy = static_cast<int>(r) & (O - 1);
+    // 32-bit shift/mask index math (S and therefore tpr are powers of two): the 64-bit runtime division this replaces
+    // cost more issue slots per 16-pixel tile than its 8 MMAs
+    const int lg_tpr = ilog2(tpr);
+    const int total = B * O * tpr;
+    for (int tile = static_cast<int>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<int>(gridDim.x) * 8) {
+        const int ox0 = (tile & (tpr - 1)) * 16;
+        const int r = tile >> lg_tpr;
+        const int oy = r & (O - 1);
         const long n = r >> lgO;
         const float* xi = x + n * S * S;
         uint32_t af[4];
@@ -111,11 +114,14 @@ dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy
         for (int nb = 0; nb < 3; ++nb) acc[i][nb][0] = acc[i][nb][1] = acc[i][nb][2] = acc[i][nb][3] = 0.f;
     const uint32_t ones = gid == 0 ? 0x3F803F80u : 0u;  // B column 0 of the third block = 1.0: row sums = dbias
     const int kx = gid & 3, kyb = gid >> 2;
-    const long total = static_cast<long>(B) * O * tpr;
-    for (long tile = static_cast<long>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<long>(gridDim.x) * 8) {
-        const int ox0 = static_cast<int>(tile % tpr) * 16;
-        const long r = tile / tpr;
-        const int oy = static_cast<int>(r) & (O - 1);
+    // 32-bit shift/mask index math (S and therefore tpr are powers of two): the 64-bit runtime division this replaces
+    // cost more issue slots per 16-pixel tile than its 8 MMAs
+    const int lg_tpr = ilog2(tpr);
+    const int total = B * O * tpr;
+    for (int tile = static_cast<int>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<int>(gridDim.x) * 8) {
+        const int ox0 = (tile & (tpr - 1)) * 16;
+        const int r = tile >> lg_tpr;
+        const int oy = r & (O - 1);
         const long n = r >> lgO;
         // dy: 8-channel chunk `gid` of pixels 2*t4, 2*t4+1, 2*t4+8, 2*t4+9 of the tile
         const bf16* dp = dy + ((n * O + oy) * O + ox0) * kC0 + gid * 8;
