@@ -162,6 +162,52 @@ class Generator(nn.Module):
                 "sg_g_forward")
         return out
 
+    @torch.no_grad()
+    def sample_uint8_to_host(self, n_samples: int, batch: int = 16384, latents: Optional[torch.Tensor] = None,
+                             generator: Optional[torch.Generator] = None,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Bulk sampling egress (the batched loop of utils/inference.py:106-134 + its uint8 conversion :129): returns a
+        pinned host tensor (n_samples, 1, S, S) uint8. Chunks of `batch` latents go through the generator with the uint8
+        conversion fused into the last kernel; the device->host copy of chunk i runs on a second stream while chunk
+        i+1 is computed (two device buffers), so the PCIe transfer is hidden behind the generator instead of added to
+        it. `latents` (n_samples, latent_dim; host or device) are used if given, else drawn on the device. `out`: an
+        optional pinned uint8 host tensor to fill (page-locking hundreds of MB costs more than generating them)."""
+        dev = self.fc[0].weight.device
+        self._prepare(dev)
+        S = self.output_size
+        if out is None:
+            out = torch.empty(n_samples, 1, S, S, dtype=torch.uint8, pin_memory=True)
+        elif out.shape != (n_samples, 1, S, S) or out.dtype != torch.uint8 or out.device.type != "cpu":
+            raise ValueError("out must be a uint8 host tensor of shape (n_samples, 1, S, S)")
+        compute = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        bufs = [torch.empty(min(batch, n_samples), 1, S, S, dtype=torch.uint8, device=dev) for _ in range(2)]
+        copied = [None, None]   # event: the copy out of bufs[k] has finished
+        sctx, fp = self._ctx, self._flat
+        for i, b0 in enumerate(range(0, n_samples, batch)):
+            n = min(batch, n_samples - b0)
+            if latents is not None:
+                z = latents[b0:b0 + n].to(dev, non_blocking=True).contiguous().float()
+            else:
+                z = torch.randn(n, self.latent_dim, device=dev, generator=generator)
+            k = i % 2
+            if copied[k] is not None:
+                compute.wait_event(copied[k])
+            L.check(sctx.lib.sg_g_forward(sctx.handle, L.ptr(fp.flat), L.ptr(fp.stats), L.ptr(z), n,
+                                          1 if self.training else 0, None, None, L.ptr(bufs[k]), L.current_stream(dev)),
+                    "sg_g_forward")
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copy):
+                copy.wait_event(done)
+                out[b0:b0 + n].copy_(bufs[k][:n], non_blocking=True)
+                copied[k] = torch.cuda.Event()
+                copied[k].record(copy)
+            z.record_stream(compute)
+        copy.synchronize()
+        compute.synchronize()
+        return out
+
     # -- reference API ----------------------------------------------------------------------------
     def generate_latent(self, n_samples: int, device: Optional[torch.device] = None) -> torch.Tensor:
         if device is None:

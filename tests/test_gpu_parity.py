@@ -371,3 +371,17 @@ def test_split_d_backward_phases_equal_the_fused_phase():
         torch.cuda.synchronize()
         grads.append(dg.clone())
     assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1])
+
+
+def test_bulk_sampler_matches_chunked_sampling():
+    """sample_uint8_to_host (double-buffered egress) == sample_uint8 chunk by chunk, including a ragged last chunk."""
+    gan, _, _ = make_gan(64, 8, "bf16")
+    G = gan.generator
+    G.eval()
+    z = O.hash_normal((700, 100), 91)
+    host = G.sample_uint8_to_host(700, batch=256, latents=z.pin_memory())
+    assert host.shape == (700, 1, 64, 64) and host.dtype == torch.uint8 and host.is_pinned()
+    ref = torch.cat([G.sample_uint8(z[i:i + 256].cuda()).cpu() for i in range(0, 700, 256)])
+    assert torch.equal(host, ref)
+    drawn = G.sample_uint8_to_host(300, batch=128, generator=torch.Generator("cuda").manual_seed(5))
+    assert drawn.shape == (300, 1, 64, 64) and 0 < drawn.float().std()
