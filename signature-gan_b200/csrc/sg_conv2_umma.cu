@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         uint8_t* stage = epi_smem + (warp - 2) * kC2EpiStage;
+        const uint32_t stage_u32 = smem_u32(stage);
         const bool vec_ok = (((args.bias ? reinterpret_cast<uintptr_t>(args.bias) : 0) |
                               (args.scale ? reinterpret_cast<uintptr_t>(args.scale) : 0) |
                               (args.shift ? reinterpret_cast<uintptr_t>(args.shift) : 0) |
@@ -385,15 +386,14 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                 const long long te2 = args.dbg ? clock64() : 0;
 #pragma unroll
                 for (int p = 0; p < 8; ++p)
-                    *reinterpret_cast<uint4*>(stage + c2_epi_off(lane, p)) =
-                        make_uint4(vv[4 * p], vv[4 * p + 1], vv[4 * p + 2], vv[4 * p + 3]);
+                    sts128(stage_u32 + c2_epi_off(lane, p), vv[4 * p], vv[4 * p + 1], vv[4 * p + 2], vv[4 * p + 3]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = i * 8 + wr_row;
                     const int o = __shfl_sync(0xffffffffu, orow, r);
-                    const float4 lo4 = *reinterpret_cast<const float4*>(stage + c2_epi_off(r, 2 * wr_k));
-                    const float4 hi4 = *reinterpret_cast<const float4*>(stage + c2_epi_off(r, 2 * wr_k + 1));
+                    const float4 lo4 = lds128f(stage_u32 + c2_epi_off(r, 2 * wr_k));
+                    const float4 hi4 = lds128f(stage_u32 + c2_epi_off(r, 2 * wr_k + 1));
                     float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
                     if (per_row_mask) {  // tiny grids (4 x 4): the rows of a chunk span several images
                         const int mi = row0 + r < args.M_total ? (row0 + r) >> lgR : 0;

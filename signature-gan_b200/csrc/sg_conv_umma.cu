@@ -438,15 +438,14 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                 }
 #pragma unroll
                 for (int p = 0; p < 8; ++p)
-                    *reinterpret_cast<uint4*>(stage + epi_off(lane, p)) =
-                        make_uint4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+                    sts128(stage_u32 + epi_off(lane, p), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = i * 8 + wr_row;
                     const int o = __shfl_sync(0xffffffffu, orow, r) + sub;
-                    const float4 lo4 = *reinterpret_cast<const float4*>(stage + epi_off(r, 2 * wr_k));
-                    const float4 hi4 = *reinterpret_cast<const float4*>(stage + epi_off(r, 2 * wr_k + 1));
+                    const float4 lo4 = lds128f(stage_u32 + epi_off(r, 2 * wr_k));
+                    const float4 hi4 = lds128f(stage_u32 + epi_off(r, 2 * wr_k + 1));
                     float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
                     if (args.bias) {
 #pragma unroll

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
         // ---------------- Epilogue ----------------
         const int q = warp & 3, py = (warp - 2) >> 2;
         uint8_t* stage = epi_smem + (warp - 2) * kT4EpiBytes;
+        const uint32_t stage_u32 = smem_u32(stage);
         const int lgW = 31 - __clz(GW);
         const int wr_row = lane >> 3, wr_k = lane & 7;   // write-back role: 8 lanes per 128-byte row
         const int ch0 = (wr_k & 3) * 8;                  // channels of this lane's 16-byte piece
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
                                                 t4_pack(__uint_as_float(v[k * 8 + 2]), __uint_as_float(v[k * 8 + 3])),
                                                 t4_pack(__uint_as_float(v[k * 8 + 4]), __uint_as_float(v[k * 8 + 5])),
                                                 t4_pack(__uint_as_float(v[k * 8 + 6]), __uint_as_float(v[k * 8 + 7])));
-                    *reinterpret_cast<uint4*>(stage + t4_off(lane, px * 4 + k)) = pk;
+                    sts128(stage_u32 + t4_off(lane, px * 4 + k), pk.x, pk.y, pk.z, pk.w);
                 }
             }
             __syncwarp();
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
             for (int i = 0; i < 8; ++i) {
                 const int r = i * 4 + wr_row;
                 const int o = __shfl_sync(0xffffffffu, orow, r);
-                uint4 d = *reinterpret_cast<const uint4*>(stage + t4_off(r, wr_k));
+                const float4 df = lds128f(stage_u32 + t4_off(r, wr_k));
+                uint4 d = make_uint4(__float_as_uint(df.x), __float_as_uint(df.y), __float_as_uint(df.z), __float_as_uint(df.w));
                 uint32_t w4[4] = {d.x, d.y, d.z, d.w};
                 if (args.scale) {
 #pragma unroll
