@@ -44,13 +44,19 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     // cost more issue slots per 16-pixel tile than its 8 MMAs
     const int lg_tpr = ilog2(tpr);
     const int total = B * O * tpr;
-    for (int tile = static_cast<int>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<int>(gridDim.x) * 8) {
+    const int stride = static_cast<int>(gridDim.x) * 8;
+    // The kernel is latency-bound (ncu: half of all stall samples wait on the image / mask loads at their first use):
+    // the loads of the NEXT tile are issued before the current tile is computed.
+    struct TileIn {
+        float xv[8];     // im2col values: [h][rr][e]
+        float2 mk[8];    // dropout keep-scale of the tile's image, this lane's two channels per n-block
+    };
+    auto load_tile = [&](int tile, TileIn& in) {
         const int ox0 = (tile & (tpr - 1)) * 16;
         const int r = tile >> lg_tpr;
         const int oy = r & (O - 1);
         const long n = r >> lgO;
         const float* xi = x + n * S * S;
-        uint32_t af[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int iy = 2 * oy - 1 + ky0 + 2 * h;
@@ -58,11 +64,28 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int ix = 2 * (ox0 + gid + 8 * rr) - 1 + kxo;
-                const float v0 = (yok && ix >= 0) ? __ldg(xi + iy * S + ix) : 0.f;
-                const float v1 = (yok && ix + 1 < S) ? __ldg(xi + iy * S + ix + 1) : 0.f;
-                af[h * 2 + rr] = pack2_bf16(v0, v1);
+                in.xv[(h * 2 + rr) * 2] = (yok && ix >= 0) ? __ldg(xi + iy * S + ix) : 0.f;
+                in.xv[(h * 2 + rr) * 2 + 1] = (yok && ix + 1 < S) ? __ldg(xi + iy * S + ix + 1) : 0.f;
             }
         }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            in.mk[nb] = mask ? __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4))
+                             : make_float2(1.f, 1.f);
+    };
+    TileIn nxt;
+    int tile = static_cast<int>(blockIdx.x) * 8 + warp;
+    if (tile < total) load_tile(tile, nxt);
+    for (; tile < total; tile += stride) {
+        const TileIn cur = nxt;
+        if (tile + stride < total) load_tile(tile + stride, nxt);
+        const int ox0 = (tile & (tpr - 1)) * 16;
+        const int r = tile >> lg_tpr;
+        const int oy = r & (O - 1);
+        const long n = r >> lgO;
+        uint32_t af[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) af[k] = pack2_bf16(cur.xv[2 * k], cur.xv[2 * k + 1]);
         float acc[8][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
@@ -71,12 +94,7 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         }
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            float m0 = 1.f, m1 = 1.f;
-            if (mask) {
-                const float2 mk = __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4));
-                m0 = mk.x;
-                m1 = mk.y;
-            }
+            const float m0 = cur.mk[nb].x, m1 = cur.mk[nb].y;
             float v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -118,33 +136,48 @@ dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy
     // cost more issue slots per 16-pixel tile than its 8 MMAs
     const int lg_tpr = ilog2(tpr);
     const int total = B * O * tpr;
-    for (int tile = static_cast<int>(blockIdx.x) * 8 + warp; tile < total; tile += static_cast<int>(gridDim.x) * 8) {
+    const int stride = static_cast<int>(gridDim.x) * 8;
+    // latency-bound like the forward kernel (ncu: 64 % of the stall samples wait on the first use of a load): the
+    // gradient and image loads of the NEXT tile are issued before the current tile's MMAs
+    struct TileIn {
+        uint4 L[4];   // dy: 8-channel chunk `gid` of pixels 2*t4, 2*t4+1, 2*t4+8, 2*t4+9 of the tile
+        float v[8];   // im2col(x): taps gid (block 0) and 8 + gid (block 1) at the same four pixels
+    };
+    auto load_tile = [&](int tile, TileIn& in) {
         const int ox0 = (tile & (tpr - 1)) * 16;
         const int r = tile >> lg_tpr;
         const int oy = r & (O - 1);
         const long n = r >> lgO;
-        // dy: 8-channel chunk `gid` of pixels 2*t4, 2*t4+1, 2*t4+8, 2*t4+9 of the tile
         const bf16* dp = dy + ((n * O + oy) * O + ox0) * kC0 + gid * 8;
-        const uint4 L0 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4) * kC0));
-        const uint4 L1 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 1) * kC0));
-        const uint4 L2 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 8) * kC0));
-        const uint4 L3 = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 9) * kC0));
-        // im2col(x): taps gid (block 0) and 8 + gid (block 1) at the same four pixels
+        in.L[0] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4) * kC0));
+        in.L[1] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 1) * kC0));
+        in.L[2] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 8) * kC0));
+        in.L[3] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 9) * kC0));
         const float* xi = x + n * S * S;
-        uint32_t b[2][2];
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
             const int iy = 2 * oy - 1 + nb * 2 + kyb;
             const bool yok = iy >= 0 && iy < S;
-            float v[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const int px = 2 * t4 + (p & 1) + 8 * (p >> 1);
                 const int ix = 2 * (ox0 + px) - 1 + kx;
-                v[p] = (yok && ix >= 0 && ix < S) ? __ldg(xi + iy * S + ix) : 0.f;
+                in.v[nb * 4 + p] = (yok && ix >= 0 && ix < S) ? __ldg(xi + iy * S + ix) : 0.f;
             }
-            b[nb][0] = pack2_bf16(v[0], v[1]);
-            b[nb][1] = pack2_bf16(v[2], v[3]);
+        }
+    };
+    TileIn nxt;
+    int tile = static_cast<int>(blockIdx.x) * 8 + warp;
+    if (tile < total) load_tile(tile, nxt);
+    for (; tile < total; tile += stride) {
+        const TileIn cur = nxt;
+        if (tile + stride < total) load_tile(tile + stride, nxt);
+        const uint4 L0 = cur.L[0], L1 = cur.L[1], L2 = cur.L[2], L3 = cur.L[3];
+        uint32_t b[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            b[nb][0] = pack2_bf16(cur.v[nb * 4], cur.v[nb * 4 + 1]);
+            b[nb][1] = pack2_bf16(cur.v[nb * 4 + 2], cur.v[nb * 4 + 3]);
         }
         const uint32_t l0[4] = {L0.x, L0.y, L0.z, L0.w}, l1[4] = {L1.x, L1.y, L1.z, L1.w};
         const uint32_t l2[4] = {L2.x, L2.y, L2.z, L2.w}, l3[4] = {L3.x, L3.y, L3.z, L3.w};
