@@ -250,16 +250,27 @@ void bn_finalize(const float* partial, int chunks, long rows, int C, const float
                                                       scale, shift);
 }
 
+// Per-channel vectors are read as two float4 per 8 channels: with scalar loads these kernels issued 16-40 LDG per
+// 16-byte activation load and sat on the load/store queue (ncu: stall_lg at the first vector load).
+__device__ __forceinline__ void ldvec8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 template <typename T>
 __global__ void bn_apply_relu_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                                      const float* __restrict__ shift, T* __restrict__ a, long n8, int C) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
         const int c0 = static_cast<int>((i * 8) & (C - 1));
-        float v[8];
+        float v[8], sc[8], sh[8];
         load8(y + i * 8, v);
+        ldvec8(scale + c0, sc);
+        ldvec8(shift + c0, sh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], scale[c0 + j], shift[c0 + j]), 0.f);
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
         store8(a + i * 8, v);
     }
 }
@@ -308,14 +319,18 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ d, const T* __restrict
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
         const int c0 = static_cast<int>((i * 8) & (C - 1));
-        float dv[8], yv[8];
+        float dv[8], yv[8], mu[8], rs[8], a1[8], a2[8], a3[8];
         load8(d + i * 8, dv);
         load8(y + i * 8, yv);
+        ldvec8(mean + c0, mu);
+        ldvec8(rstd + c0, rs);
+        ldvec8(k1 + c0, a1);
+        ldvec8(k2 + c0, a2);
+        ldvec8(k3 + c0, a3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            const float xhat = (yv[j] - mean[c]) * rstd[c];
-            dv[j] = k1[c] * (dv[j] - k2[c] - xhat * k3[c]);
+            const float xhat = (yv[j] - mu[j]) * rs[j];
+            dv[j] = a1[j] * (dv[j] - a2[j] - xhat * a3[j]);
         }
         store8(dy + i * 8, dv);
     }

@@ -260,9 +260,10 @@ int ensure_scratch(sg_ctx* c, int B) {
     }
     SG_TRY(c->wpart.ensure(wp * 4));
     SG_TRY(c->cpart.ensure(static_cast<size_t>(sg::kMaxChunks) * 2 * 2048 * 4));
-    SG_TRY(c->small.ensure((static_cast<size_t>(B) + 3 * 8192) * 4));
+    const size_t b_pad = (static_cast<size_t>(B) + 63) / 64 * 64;  // keeps k1..k3 16-byte aligned (float4 loads)
+    SG_TRY(c->small.ensure((b_pad + 3 * 8192) * 4));
     c->dlogit = static_cast<float*>(c->small.p);
-    c->k1 = c->dlogit + B;
+    c->k1 = c->dlogit + b_pad;
     c->k2 = c->k1 + 8192;
     c->k3 = c->k2 + 8192;
     c->scratch_batch = B;
