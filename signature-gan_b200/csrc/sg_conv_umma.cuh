@@ -70,6 +70,12 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs epi /* only epilogue fields read */, cudaStream_t stream);
 
+// Fused eval-mode tail of the Generator (sg_convt4_final.cu): last ConvT block (32 -> 32) + running-stat BatchNorm + ReLU
+// + Conv3x3(32 -> 1) + bias + tanh; out (fp32) and out_u8 are (nimg, 1, 2 inH, 2 inW), either may be null.
+bool convt4_final_supported(int inH, int inW, int Cin, int Cout);
+int launch_convt4_final(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
+                        const float* scale, const float* shift, const float* w3, const float* b3, float* out,
+                        uint8_t* out_u8, cudaStream_t stream);
 // Number of partial rows a kConvT launch with `stats_partial` set writes, 0 if this shape cannot fuse the statistics.
 int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout);
 

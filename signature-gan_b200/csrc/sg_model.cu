@@ -163,6 +163,7 @@ struct sg_ctx {
     bf16 *fc_Wp, *g_packF[6], *g_packB[6], *d_packF[6], *d_packB[6];
     float *fc_biasp, *cls_wp;
     DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
+    bool u8_only = false;  // current sg_g_forward call wants the uint8 image only (no caller-visible fp32 image)
     float *dlogit, *k1, *k2, *k3;
     int scratch_batch = 0;
     Profiler prof;
@@ -365,8 +366,22 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     }
     // ---- upsample blocks: ConvT 4x4 s2 p1 (no bias) + BN2d + ReLU (gen…:46-60)
     const char* in = w.fc_a;
+    float* out = save ? w.out : out_image;
+    bool tail_done = false;
     for (int i = 0; i < c->L; ++i) {
         const int ih = g_spatial(c, i) / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
+        if (kTC && fused_eval && i == c->L - 1 && sg::convt4_final_supported(ih, ih, Cin, Cout)) {
+            // last block + Conv3x3 + tanh in one kernel: the full-resolution 32-channel level never reaches HBM
+            const bool u8_only = out_u8 && c->u8_only;
+            PROF("g.tail_fused", 2.0 * B * ih * ih * 16.0 * Cin * Cout + 2.0 * B * c->S * c->S * 9.0 * Cout,
+                 (double)B * (es * ih * ih * Cin + c->S * c->S * ((u8_only ? 0.0 : 4.0) + (out_u8 ? 1.0 : 0.0))));
+            if (sg::launch_convt4_final(reinterpret_cast<const bf16*>(in), c->g_packF[i], B, ih, ih, w.scale[i + 1],
+                                        w.shift[i + 1], params + c->gt[c->g_final_w].offset,
+                                        params + c->gt[c->g_final_b].offset, u8_only ? nullptr : out, out_u8, s))
+                return fail("g_forward: fused tail launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            tail_done = true;
+            break;
+        }
         const long rows = static_cast<long>(B) * 4 * ih * ih;
         const bool fuse = kTC && fused_eval;
         T* dst = reinterpret_cast<T*>(fuse ? w.a[i] : w.y[i]);
@@ -414,8 +429,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
         in = (fuse || i < c->L - 1) ? w.a[i] : w.y[i];
     }
     // ---- Conv3x3 + tanh (gen…:153-163)
-    float* out = save ? w.out : out_image;
-    {
+    if (!tail_done) {
     PROF("g.final", 2.0 * B * c->S * c->S * 9.0 * c->gch[c->L], (double)B * c->S * c->S * (es * c->gch[c->L] + 4.0));
     const bool affine = !(kTC && fused_eval);
     sg::final_conv_tanh<T>(reinterpret_cast<const T*>(in), affine ? w.scale[c->L] : nullptr,
@@ -888,6 +902,7 @@ int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SG_TRY(ensure_scratch(c, batch));
     bool save = ws != nullptr;
+    c->u8_only = !ws && !out_image && out_u8;
     if (!ws) {
         SG_TRY(c->gws_tmp.ensure(sg_g_workspace_bytes(c, batch)));
         ws = c->gws_tmp.p;
