@@ -42,10 +42,25 @@ constexpr int kFWBytes = 16 * kFWTapBytes;
 constexpr int kFABufMax = 4 * 64 * kFRowBytes;  // (BH+2)*GW input pixel rows: 6 x 32 or 4 x 64
 constexpr int kFStageBytes = 3 * kFABufMax;
 constexpr int kFStages = 2;
-constexpr int kFTmemCols = 256;                 // 2 x [py][px][32]
+constexpr int kFTmemCols = 256;                 // 2 x [px][py][32]
 constexpr int kFPBytes = 24 * 9 * 84 * 4;       // P ring: 3 tiles x (8 rows x 9 x 84 | 4 rows x 9 x 148) floats
 constexpr int kFSmemBytes = kFWBytes + kFStages * kFStageBytes + kFPBytes + 1024 + 256;
 constexpr uint32_t kFSBO = 8 * kFRowBytes;
+
+// Products of one tile, grouped by input shift (dy, dx) so that parities sharing a shifted input block are ONE MMA
+// with their tap matrices stacked along N (the A block is read from shared memory once per MMA whatever N is, and with
+// N = 32 those reads, not the math, bound the tensor pipe). Accumulator columns are ordered [px][py][32]: the dy = 0
+// shifts then address 2 or 4 adjacent parities. 11 MMAs per k-step instead of 16.
+struct T4Prod { int dy, dx, slot, n, col; };
+__device__ constexpr T4Prod kProds[11] = {
+    {0, 0, 0, 128, 0},                                                           // all four parities
+    {0, -1, 4, 64, 0},   {0, 1, 6, 64, 64},                                       // px = 0 / px = 1, both py
+    {-1, 0, 8, 32, 0},   {-1, 0, 9, 32, 64},  {1, 0, 10, 32, 32}, {1, 0, 11, 32, 96},
+    {-1, -1, 12, 32, 0}, {-1, 1, 13, 32, 64}, {1, -1, 14, 32, 32}, {1, 1, 15, 32, 96}};
+// resident weight slot -> filter tap ky*4+kx (parity (py, px) with tap shift (dy, dx) uses ky = 1-py+2(py-dy),
+// kx likewise)
+__device__ constexpr int kSlotTap[16] = {1 * 4 + 1, 2 * 4 + 1, 1 * 4 + 2, 2 * 4 + 2, 1 * 4 + 3, 2 * 4 + 3, 1 * 4 + 0, 2 * 4 + 0,
+                                         3 * 4 + 1, 3 * 4 + 2, 0 * 4 + 1, 0 * 4 + 2, 3 * 4 + 3, 3 * 4 + 0, 0 * 4 + 3, 0 * 4 + 0};
 
 struct ConvT4FinalArgs {
     CUtensorMap amap;  // input [C][W][H][N], box {32, GW, BH+2, 1}
@@ -134,7 +149,9 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
         const bool issuer = elect_one();
         if (issuer) {
             mbar_arrive_expect_tx(w_bar, kFWBytes);
-            for (int tap = 0; tap < 16; ++tap) tma_load_2d(wsm + tap * kFWTapBytes, &args.wmap, w_bar, tap * kFC, 0);
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl)
+                tma_load_2d(wsm + sl * kFWTapBytes, &args.wmap, w_bar, kSlotTap[sl] * kFC, 0);
         }
         int s = 0;
         uint32_t ph = 0;
@@ -154,7 +171,6 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (whole warp, uniform control flow) ----------------
-        constexpr uint32_t idesc = make_idesc_bf16(128, kFC, 0, 0);
         const bool issuer = elect_one();
         mbar_wait(w_bar, 0);
         const uint32_t w_addr = smem_u32(wsm);
@@ -169,22 +185,15 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
             const uint32_t a_addr = smem_u32(ring + s * kFStageBytes);
             if (issuer) {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int py = p >> 1, px = p & 1;
-                    const uint32_t tmem_d = tmem_base + acc * 128 + p * kFC;
+                for (int k = 0; k < kFC / 16; ++k) {
 #pragma unroll
-                    for (int tp = 0; tp < 4; ++tp) {
-                        const int ty = tp >> 1, tx = tp & 1;
-                        const int dy = py - ty, dx = px - tx;
-                        const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                        const uint32_t a0 = a_addr + (dx + 1) * abuf + (1 + dy) * row_step;
-                        const uint32_t b0 = w_addr + (ky * 4 + kx) * kFWTapBytes;
-#pragma unroll
-                        for (int k = 0; k < kFC / 16; ++k) {
-                            const uint64_t da = make_smem_desc(a0 + k * 32, 0, kFSBO, kLayoutSW64);
-                            const uint64_t db = make_smem_desc(b0 + k * 32, 0, kFSBO, kLayoutSW64);
-                            umma_bf16_ss(tmem_d, da, db, idesc, (tp | k) != 0);
-                        }
+                    for (int i = 0; i < 11; ++i) {
+                        const uint32_t a0 = a_addr + (kProds[i].dx + 1) * abuf + (1 + kProds[i].dy) * row_step;
+                        const uint32_t b0 = w_addr + kProds[i].slot * kFWTapBytes;
+                        const uint64_t da = make_smem_desc(a0 + k * 32, 0, kFSBO, kLayoutSW64);
+                        const uint64_t db = make_smem_desc(b0 + k * 32, 0, kFSBO, kLayoutSW64);
+                        umma_bf16_ss(tmem_base + acc * 128 + kProds[i].col, da, db,
+                                     make_idesc_bf16(128, kProds[i].n, 0, 0), (i | k) != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -236,6 +245,37 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
                 }
         }
         const float b3 = __ldg(args.b3);
+        // emission role (fixed per thread: 512 = RPT * OW): output column e_x of tile-relative output row e_ro
+        const int e_x = te & (OW - 1), e_ro = (te >> lgOW) - 1;
+        const uint32_t row_bytes = 9 * pitch * 4;
+        // byte offsets of (x-1, tap 0), (x, tap 1), (x+1, tap 2) inside a tap-row triple (parity-split columns)
+        const uint32_t xo_l = (((e_x - 1) & 1) * HP + ((e_x - 1) >> 1)) * 4;
+        const uint32_t xo_m = (pitch + (e_x & 1) * HP + (e_x >> 1)) * 4;
+        const uint32_t xo_r = (2 * pitch + ((e_x + 1) & 1) * HP + ((e_x + 1) >> 1)) * 4;
+        const bool has_l = e_x > 0, has_r = e_x < OW - 1;
+        // source rows e_ro-1, e_ro, e_ro+1 with filter rows ky = 0, 1, 2; negative rows live in the previous tile's slots
+        uint32_t e_off[3];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int rr = e_ro + ky - 1;
+            e_off[ky] = static_cast<uint32_t>((rr < 0 ? RPT + rr : rr) * 9 + ky * 3) * pitch * 4;
+        }
+        auto tap_row = [&](uint32_t base) -> float {   // sum over kx of one source row's taps at columns x-1, x, x+1
+            const float l = has_l ? lds32f(base + xo_l) : 0.f;
+            const float r = has_r ? lds32f(base + xo_r) : 0.f;
+            return l + lds32f(base + xo_m) + r;
+        };
+        auto put = [&](float a, int n, int yo) {
+            // tanh(a) = 1 - 2 / (exp(2a) + 1): exact limits at +-inf, absolute error ~1e-7 (the output is an image)
+            const float v = 1.f - __fdividef(2.f, __expf(2.f * a) + 1.f);
+            const size_t o = (static_cast<size_t>(n) * OH + yo) * OW + e_x;
+            if (args.out) args.out[o] = v;
+            if (args.out_u8) {
+                float qv = (v + 1.f) * 127.5f;
+                qv = fminf(fmaxf(qv, 0.f), 255.f);
+                args.out_u8[o] = static_cast<uint8_t>(qv);  // numpy astype(uint8) truncates (utils/inference.py:129)
+            }
+        };
 
         for (int g = 0; g < my_tiles; ++g) {
             const int acc = g & 1;
@@ -247,7 +287,7 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
             // accumulator -> registers in the mma.sync C-fragment layout (16 pixels x 32 channels per load): after
             // BatchNorm + ReLU and bf16 packing that IS the A fragment of the tap GEMM — no shared-memory staging
             uint32_t v[2][16];
-            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + (py * 2 + px) * kFC;
+            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + (px * 2 + py) * kFC;
             tmem_ld_16x256b_x4(tsrc, v[0]);
             tmem_ld_16x256b_x4(tsrc + (16u << 16), v[1]);
             tmem_ld_wait();
@@ -284,37 +324,19 @@ __global__ void __launch_bounds__(kFThreads, 1) convt4_final_kernel(const __grid
                 }
             }
             epi_bar();
-            // rows ti*RPT-1 .. ti*RPT+RPT-2 of the image are complete now (+ the last row at the last tile)
-            const int n_emit = RPT * OW + (ti == tpi - 1 ? OW : 0);
-            for (int idx = te; idx < n_emit; idx += 512) {
-                const int ro = (idx >> lgOW) - 1;                  // output row relative to the tile's first row
-                const int x = idx & (OW - 1);
-                const int yo = ti * RPT + ro;
-                if (yo < 0) continue;
-                // columns of x-1, x, x+1 in the parity-split row layout
-                const int c0 = ((x - 1) & 1) * HP + ((x - 1) >> 1), c1 = (x & 1) * HP + (x >> 1),
-                          c2 = ((x + 1) & 1) * HP + ((x + 1) >> 1);
-                const bool has_l = x > 0, has_r = x < OW - 1;
+            // rows ti*RPT-1 .. ti*RPT+RPT-2 of the image are complete now: one pixel per thread (+ the last row at the
+            // last tile)
+            const uint32_t cur = P_u32 + slot0 * row_bytes, prev = P_u32 + slotp * row_bytes;
+            if (ti > 0 || e_ro >= 0) {
                 float a = b3;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int rr = ro + ky - 1, yy = yo + ky - 1;  // source row relative to the tile / in the image
-                    if (yy < 0 || yy >= OH) continue;
-                    const int slot = rr < 0 ? slotp + RPT + rr : slot0 + rr;
-                    const uint32_t pr = P_u32 + (slot * 9 + ky * 3) * pitch * 4;       // tap (ky, 0) of that row
-                    const float l = has_l ? lds32f(pr + c0 * 4) : 0.f;
-                    const float m = lds32f(pr + (pitch + c1) * 4);
-                    const float r = has_r ? lds32f(pr + (2 * pitch + c2) * 4) : 0.f;
-                    a += l + m + r;
-                }
-                const float v = tanhf(a);
-                const size_t o = (static_cast<size_t>(n0) * OH + yo) * OW + x;
-                if (args.out) args.out[o] = v;
-                if (args.out_u8) {
-                    float qv = (v + 1.f) * 127.5f;
-                    qv = fminf(fmaxf(qv, 0.f), 255.f);
-                    args.out_u8[o] = static_cast<uint8_t>(qv);  // numpy astype(uint8) truncates (utils/inference.py:129)
-                }
+                if (ti > 0 || e_ro > 0) a += tap_row((e_ro >= 1 ? cur : prev) + e_off[0]);
+                a += tap_row((e_ro >= 0 ? cur : prev) + e_off[1]);
+                a += tap_row(cur + e_off[2]);
+                put(a, n0, ti * RPT + e_ro);
+            }
+            if (ti == tpi - 1 && te < OW) {
+                const uint32_t last = cur + (RPT - 2) * row_bytes;
+                put(b3 + tap_row(last) + tap_row(last + row_bytes + 3 * pitch * 4), n0, OH - 1);
             }
         }
     }
