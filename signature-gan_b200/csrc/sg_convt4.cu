@@ -9,8 +9,9 @@
 //     which is the padding). The operand of tap shift (dy, dx) is the dx buffer advanced by (1+dy) grid rows — a
 //     whole number of swizzle atoms — so 3 loads feed all 16 (parity, tap) products: 4.6x fewer TMA rows.
 //   * B: the 16 packed tap matrices [Cout x Cin] stay resident in shared memory for the whole launch.
-//   * D: four accumulators [py][px][Cout] side by side in TMEM (128 columns), double-buffered, so the epilogue of a
-//     tile overlaps the MMAs of the next; 16 x Cin/16 tcgen05.mma per tile, all issued by one thread.
+//   * D: four accumulators [px][py][Cout] side by side in TMEM (128 columns), double-buffered, so the epilogue of a
+//     tile overlaps the MMAs of the next; products that share a shifted input block are one MMA with the tap matrices
+//     stacked along N: 11 x Cin/16 tcgen05.mma per tile instead of 16 x Cin/16, all issued by one thread.
 //   * epilogue: warp (lane quarter q, py) owns 32 input pixels x {px = 0, 1} x 32 channels = for each input pixel
 //     the 128 contiguous output bytes of pixels (2y+py, 2x), (2y+py, 2x+1); the warp's block is transposed through
 //     swizzled shared memory and leaves as full 128-byte lines (a whole output row segment), optionally with the
@@ -58,11 +59,26 @@ struct T4Cfg {
     static constexpr int kABufMax = (BK == 32 ? 4 * 64 : 10 * 16) * kRowBytes;  // (BH+2)*GW rows; see convt4_supported
     static constexpr int kStageBytes = 3 * kABufMax;
     static constexpr int kStages = BK == 32 ? 3 : 2;
-    static constexpr int kTmemCols = 256;  // 2 x [py][px][32]
+    static constexpr int kTmemCols = 256;  // 2 x [px][py][32]
     static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + 8 * kT4EpiBytes + 1024 + 256;
     static constexpr uint32_t kLayout = (BK == 64) ? kLayoutSW128 : kLayoutSW64;
     static constexpr uint32_t kSBO = 8 * kRowBytes;
 };
+
+// Products of one tile grouped by input shift (dy, dx): parities that share a shifted input block are ONE MMA with
+// their tap matrices stacked along N (the A block is read from shared memory once per MMA whatever N is, and with
+// N = 32 those reads, not the math, bound the tensor pipe). Accumulator columns are ordered [px][py][32], so the
+// dy = 0 shifts address 2 or 4 adjacent parities: 11 MMAs per k-step instead of 16.
+struct T4Prod { int dy, dx, slot, n, col; };
+__device__ constexpr T4Prod kT4Prods[11] = {
+    {0, 0, 0, 128, 0},                                                           // all four parities
+    {0, -1, 4, 64, 0},   {0, 1, 6, 64, 64},                                       // px = 0 / px = 1, both py
+    {-1, 0, 8, 32, 0},   {-1, 0, 9, 32, 64},  {1, 0, 10, 32, 32}, {1, 0, 11, 32, 96},
+    {-1, -1, 12, 32, 0}, {-1, 1, 13, 32, 64}, {1, -1, 14, 32, 32}, {1, 1, 15, 32, 96}};
+// resident weight slot -> filter tap ky*4+kx (parity (py, px) with tap shift (dy, dx): ky = 1-py+2(py-dy), kx alike)
+__device__ constexpr int kT4SlotTap[16] = {1 * 4 + 1, 2 * 4 + 1, 1 * 4 + 2, 2 * 4 + 2, 1 * 4 + 3, 2 * 4 + 3,
+                                           1 * 4 + 0, 2 * 4 + 0, 3 * 4 + 1, 3 * 4 + 2, 0 * 4 + 1, 0 * 4 + 2,
+                                           3 * 4 + 3, 3 * 4 + 0, 0 * 4 + 3, 0 * 4 + 0};
 
 __device__ __forceinline__ float t4_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float t4_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -123,7 +139,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
         const bool issuer = elect_one();
         if (issuer) {
             mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
-            for (int tap = 0; tap < 16; ++tap) tma_load_2d(wsm + tap * Cfg::kWTapBytes, &args.wmap, w_bar, tap * BK, 0);
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl)
+                tma_load_2d(wsm + sl * Cfg::kWTapBytes, &args.wmap, w_bar, kT4SlotTap[sl] * BK, 0);
         }
         const int lg_tpi = 31 - __clz(tpi);
         int s = 0;
@@ -144,7 +162,6 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (whole warp, uniform control flow) ----------------
-        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
         const bool issuer = elect_one();
         mbar_wait(w_bar, 0);
         const uint32_t w_addr = smem_u32(wsm);
@@ -160,22 +177,15 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
             const uint32_t a_addr = smem_u32(ring + s * Cfg::kStageBytes);
             if (issuer) {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int py = p >> 1, px = p & 1;
-                    const uint32_t tmem_d = tmem_base + acc * 128 + p * BN;
+                for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-                    for (int tp = 0; tp < 4; ++tp) {
-                        const int ty = tp >> 1, tx = tp & 1;
-                        const int dy = py - ty, dx = px - tx;
-                        const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                        const uint32_t a0 = a_addr + (dx + 1) * abuf + (1 + dy) * row_step;
-                        const uint32_t b0 = w_addr + (ky * 4 + kx) * Cfg::kWTapBytes;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t da = make_smem_desc(a0 + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                            const uint64_t db = make_smem_desc(b0 + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
-                            umma_bf16_ss(tmem_d, da, db, idesc, (tp | k) != 0);
-                        }
+                    for (int i = 0; i < 11; ++i) {
+                        const uint32_t a0 = a_addr + (kT4Prods[i].dx + 1) * abuf + (1 + kT4Prods[i].dy) * row_step;
+                        const uint32_t b0 = w_addr + kT4Prods[i].slot * Cfg::kWTapBytes;
+                        const uint64_t da = make_smem_desc(a0 + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                        const uint64_t db = make_smem_desc(b0 + k * 32, 0, Cfg::kSBO, Cfg::kLayout);
+                        umma_bf16_ss(tmem_base + acc * 128 + kT4Prods[i].col, da, db,
+                                     make_idesc_bf16(128, kT4Prods[i].n, 0, 0), (i | k) != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) convt4_kernel(const __grid_cons
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + (py * 2 + px) * BN, v);
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + (px * 2 + py) * BN, v);
                 tmem_ld_wait();
                 if (px == 1) {
                     tc_fence_before();

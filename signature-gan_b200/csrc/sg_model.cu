@@ -307,6 +307,16 @@ sg::ConvGemmArgs epi_args(void* out, int ldo) {
 // ------------------------------------------------------------------------------------------------
 // Generator
 // ------------------------------------------------------------------------------------------------
+// SIGGAN_FUSED_TAIL=0 keeps the last block and the Conv3x3 as two kernels (A/B comparison)
+static bool fused_tail_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SIGGAN_FUSED_TAIL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 template <typename T>
 int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, int B, int train, void* ws_ptr,
                 float* out_image, uint8_t* out_u8, bool save, cudaStream_t s) {
@@ -370,7 +380,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     bool tail_done = false;
     for (int i = 0; i < c->L; ++i) {
         const int ih = g_spatial(c, i) / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
-        if (kTC && fused_eval && i == c->L - 1 && sg::convt4_final_supported(ih, ih, Cin, Cout)) {
+        if (kTC && fused_eval && i == c->L - 1 && fused_tail_enabled() && sg::convt4_final_supported(ih, ih, Cin, Cout)) {
             // last block + Conv3x3 + tanh in one kernel: the full-resolution 32-channel level never reaches HBM
             const bool u8_only = out_u8 && c->u8_only;
             PROF("g.tail_fused", 2.0 * B * ih * ih * 16.0 * Cin * Cout + 2.0 * B * c->S * c->S * 9.0 * Cout,

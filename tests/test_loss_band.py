@@ -8,8 +8,12 @@ The stated band: SURVEY.md suggested +-0.15 (losses) / +-0.1 (means) around the 
 meet that against itself — leaving one reference seed out, its EMA(50) leaves the envelope of the other two by up to
 0.31 (d_loss), 1.40 (g_loss), 0.12 (d_real_mean / d_fake_mean): GAN training is chaotic at batch 32. The band used
 here is therefore max(suggested band, 1.25 x the reference's own worst leave-one-out excursion), computed from the
-fixture, plus a tighter check on the time average over the second half of the run, which must lie within the spread of
-the reference seeds' averages (widened by that spread, at least 0.05)."""
+fixture, plus a check on the time average over the second half of the run, which must lie within the range of the
+reference seeds' averages widened by TWICE their spread (at least 0.05) on either side. One spread was too tight a
+window to draw from three samples: 12 runs of this implementation (tools/loss_band_probe.py, six seeds x two builds,
+profiles/r01_loss_band_probe.log) put the second-half g_loss mean at 1.81 .. 2.56 (mean 2.18) against 2.01 .. 2.22
+(mean 2.15) for the three reference seeds — same centre, run-to-run scatter of about +-0.2 — so the +-1-spread window
+[1.81, 2.42] rejected about one run in six whatever the kernels were."""
 import os
 
 import pytest
@@ -52,7 +56,7 @@ def test_thousand_step_loss_band(golden_dir, precision):
         band[k] = max(BAND[k], 1.25 * loo)
         means = [sum(ref["curves"][s][k][steps // 2:]) / (steps - steps // 2) for s in seeds]
         spread = max(max(means) - min(means), 0.05)
-        avg_lo[k], avg_hi[k] = min(means) - spread, max(means) + spread
+        avg_lo[k], avg_hi[k] = min(means) - 2 * spread, max(means) + 2 * spread
     pool = O.synthetic_signatures(pool_n, size, seed=1234).cuda()
     worst = {k: 0.0 for k in KEYS}
     for seed in seeds[:2]:
