@@ -39,10 +39,20 @@ constexpr int kC2EpiStage = 32 * 128;  // per epilogue warp: 32 rows x 32 fp32 c
 struct C2Stage {
     int map, cx, dx, dy, nprod, first_prod;
 };
+// One weight slot of a stage ([BN/2 rows x 64 k] per CTA). An entry with nmul > 0 issues ONE MMA of N = BN * nmul whose
+// B operand is this slot and the nmul - 1 following ones (entries with nmul = 0 are covered by an earlier entry):
+// products that read the same shifted A block and write adjacent accumulators are stacked along N, because with
+// N = 64 a tcgen05.mma is bound by its 4 KB A-operand read, not by math. For a stacked MMA each CTA of the pair must
+// hold a contiguous HALF of the stacked [BN * nmul x 64] tile, so what a slot is loaded with depends on the CTA rank.
 struct C2Prod {
     uint32_t a_off;
     int b_koff, acc_col, first;
+    int nmul;
+    int koff_r[2], nrow_r[2];  // per CTA rank: K offset of the weight tile loaded into this slot and its first row
 };
+static C2Prod c2_single(uint32_t a_off, int koff, int acc_col, int first, int bn) {
+    return C2Prod{a_off, koff, acc_col, first, 1, {koff, koff}, {0, bn / 2}};
+}
 
 struct Conv2Args {
     CUtensorMap amap[4];
@@ -183,7 +193,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
 #pragma unroll 1
                     for (int p = 0; p < S.nprod; ++p)
                         tma2_load_2d(slot + kC2ASlot + p * Cfg::kBSlot, &args.bmap, bar,
-                                     args.prods[v][S.first_prod + p].b_koff, static_cast<int>(rank) * (BN / 2));
+                                     args.prods[v][S.first_prod + p].koff_r[rank],
+                                     args.prods[v][S.first_prod + p].nrow_r[rank]);
                 }
                 if (++sg == STG) {
                     sg = 0;
@@ -200,7 +211,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
     } else if (warp == 1) {
         if (rank == 0) {
             // ---------------- MMA issuer (leader CTA only): 256 x BN x 16 per instruction ----------------
-            constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+            constexpr uint32_t idesc1 = make_idesc_bf16(256, BN, 0, 0);
+            constexpr uint32_t idesc2 = make_idesc_bf16(256, BN * 2 <= 256 ? BN * 2 : BN, 0, 0);
+            constexpr uint32_t idesc4 = make_idesc_bf16(256, BN * 4 <= 256 ? BN * 4 : BN, 0, 0);
             const bool issuer = elect_one();
             int sg = 0, j = 0;
             uint32_t phs = 0;
@@ -223,6 +236,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
 #pragma unroll 1
                         for (int p = 0; p < S.nprod; ++p) {
                             const C2Prod P = args.prods[v][S.first_prod + p];
+                            if (P.nmul == 0) continue;
+                            const uint32_t idesc = P.nmul == 1 ? idesc1 : (P.nmul == 2 ? idesc2 : idesc4);
                             const uint32_t a_addr = a_base + P.a_off;
                             const uint32_t b_addr = a_base + kC2ASlot + p * Cfg::kBSlot;
 #pragma unroll
@@ -559,8 +574,8 @@ int launch_conv2(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_
                         S = {yp * 2 + xp, cc * 64, dx, dy0, 2, np};
                         for (int dyj = 0; dyj < 2; ++dyj) {
                             const int ky = yp ? (dyj ? 2 : 0) : (dyj ? 3 : 1);
-                            a.prods[0][np] = {static_cast<uint32_t>(dyj * a.GW * 128), (ky * 4 + kx) * Cin + cc * 64, 0,
-                                              np == 0 ? 1 : 0};
+                            a.prods[0][np] = c2_single(static_cast<uint32_t>(dyj * a.GW * 128),
+                                                       (ky * 4 + kx) * Cin + cc * 64, 0, np == 0 ? 1 : 0, 128);
                             ++np;
                         }
                     }
@@ -578,22 +593,54 @@ int launch_conv2(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_
         const int BH = 128 / a.GW;
         a.a_bytes = (BH + 2) * a.GW * 128;
         if (make_map_nhwc(&a.amap[0], in, nimg, inH, inW, Cin, 1, 0, 0, 64, a.GW, BH + 2, 1)) return -1;
+        // stage order per 64-channel chunk: dx = 0 first — its dy = 0 group writes all four accumulators in one
+        // N = 256 MMA, so at the first chunk every accumulator is initialised by the same instruction
         int ns = 0, np = 0;
-        bool seen[4] = {false, false, false, false};
+        static const int kDxOrder[3] = {0, -1, 1};
+        const bool stack = getenv("SIGGAN_CONV2_NOSTACK") == nullptr;
         for (int cc = 0; cc < kc; ++cc)
-            for (int dx = -1; dx <= 1; ++dx) {
+            for (int di = 0; di < 3; ++di) {
+                const int dx = kDxOrder[di];
                 if (ns >= kC2MaxStages) return -1;
                 C2Stage& S = a.stages[0][ns++];
                 S = {0, cc * 64, dx, -1, 0, np};
+                auto koff_of = [&](int py, int px, int ty, int tx) {
+                    const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+                    return (ky * 4 + kx) * Cin + cc * 64;
+                };
+                const int first = (cc == 0 && di == 0) ? 1 : 0;
+                if (dx == 0 && stack) {
+                    // tx = px. dy = 0: all four parities (ty = py); dy = -1: py = 0, ty = 1; dy = +1: py = 1, ty = 0
+                    struct G { int dy, cnt, ph0; } groups[3] = {{0, 4, 0}, {-1, 2, 0}, {1, 2, 2}};
+                    for (const G& g : groups) {
+                        if (np + g.cnt > kC2MaxProds) return -1;
+                        int koffs[4];
+                        for (int i = 0; i < g.cnt; ++i) {
+                            const int ph = g.ph0 + i, py = ph >> 1, px = ph & 1;
+                            koffs[i] = koff_of(py, px, py - g.dy, px);
+                        }
+                        for (int j = 0; j < g.cnt; ++j) {
+                            C2Prod P{static_cast<uint32_t>((1 + g.dy) * a.GW * 128), koffs[0], g.ph0 * 64,
+                                     g.dy == 0 ? first : 0, j == 0 ? g.cnt : 0, {0, 0}, {0, 0}};
+                            for (int r = 0; r < 2; ++r) {
+                                P.koff_r[r] = koffs[r * (g.cnt / 2) + j / 2];
+                                P.nrow_r[r] = (j & 1) * 32;
+                            }
+                            a.prods[0][np++] = P;
+                            ++S.nprod;
+                        }
+                    }
+                    continue;
+                }
                 for (int ph = 0; ph < 4; ++ph)
                     for (int tp = 0; tp < 4; ++tp) {
                         const int py = ph >> 1, px = ph & 1, ty = tp >> 1, tx = tp & 1;
                         if (px - tx != dx) continue;
                         if (np >= kC2MaxProds) return -1;
-                        const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                        a.prods[0][np++] = {static_cast<uint32_t>((1 + py - ty) * a.GW * 128),
-                                            (ky * 4 + kx) * Cin + cc * 64, ph * 64, seen[ph] ? 0 : 1};
-                        seen[ph] = true;
+                        // (without stacking the first write of each accumulator is its own first product of stage 0)
+                        const int f = (!stack && cc == 0 && di == 0 && ty == 0) ? 1 : 0;
+                        a.prods[0][np++] = c2_single(static_cast<uint32_t>((1 + py - ty) * a.GW * 128),
+                                                     koff_of(py, px, ty, tx), ph * 64, f, 64);
                         ++S.nprod;
                     }
             }
@@ -620,7 +667,7 @@ int launch_conv2(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_
                             if (px - tx != dx) continue;
                             if (np >= kC2MaxProds) return -1;
                             const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-                            a.prods[py][np++] = {0u, (ky * 4 + kx) * Cin + cc * 64, px * 128, seen[px] ? 0 : 1};
+                            a.prods[py][np++] = c2_single(0u, (ky * 4 + kx) * Cin + cc * 64, px * 128, seen[px] ? 0 : 1, 128);
                             seen[px] = true;
                             ++S.nprod;
                         }
