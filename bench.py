@@ -24,6 +24,9 @@ sys.path.insert(0, os.path.join(ROOT, "signature-gan_b200"))
 
 FLOP_PER_IMG_TRAIN = {64: 1.9707e9, 128: 9.2199e9}     # algorithmically necessary conv/linear FLOPs
 FLOP_PER_IMG_SAMPLE = {64: 87.06e6, 128: 413.73e6}
+# sampling, algorithmic HBM bytes per image with the eval tail fused: z (400) + every bf16 level up to the input of the
+# last block written and read once (8K + 16K + 32K + 64K, x2) + the fp32 image (16K)
+SAMPLE_BYTES_PER_IMG = {64: 400 + 2 * (8192 + 16384 + 32768 + 65536) + 16384}
 
 
 def parse():
@@ -360,6 +363,11 @@ def run_ours(args, rank, local_rank, world):
             line["sampling"] = {"batch": SB, "images_per_s_fp32_out": SB / (samp_ms * 1e-3),
                                 "images_per_s_uint8_out": SB / (samp8_ms * 1e-3), "ms_fp32_out": samp_ms,
                                 "achieved_tflops": sf, "tensor_frac": sf / pk["bf16_tflops"],
+                                # layered bf16 activations with the tail fused: z + fc + 3 ConvT levels
+                                # read and written once + the fp32 image
+                                "bytes_per_image": SAMPLE_BYTES_PER_IMG.get(S),
+                                "hbm_frac": (SAMPLE_BYTES_PER_IMG[S] * SB / (samp_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
+                                if S in SAMPLE_BYTES_PER_IMG else None,
                                 "e2e_images_per_s_uint8_host": samp_e2e,
                                 "e2e_bytes": {"h2d": SB * 400, "d2h": SB * S * S},
                                 "e2e_api": "Generator.sample_uint8_to_host (8 chunks, double-buffered D2H)"}
