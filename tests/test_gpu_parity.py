@@ -385,3 +385,34 @@ def test_bulk_sampler_matches_chunked_sampling():
     assert torch.equal(host, ref)
     drawn = G.sample_uint8_to_host(300, batch=128, generator=torch.Generator("cuda").manual_seed(5))
     assert drawn.shape == (300, 1, 64, 64) and 0 < drawn.float().std()
+
+
+@pytest.mark.parametrize("size,B", [(64, 300), (128, 37)])
+def test_fused_eval_tail_matches_layered_path(size, B):
+    """The one-kernel eval tail (sg_convt4_final.cu: last ConvT block + BatchNorm + ReLU + Conv3x3 + tanh, taken under
+    no_grad) against the layered path the same module takes with autograd enabled, on a batch that gives every CTA
+    several whole images plus a ragged remainder (the 3x3 row halo is carried from tile to tile inside an image and
+    must not leak across images), with non-trivial running statistics; then the uint8-only egress (no fp32 image
+    written) against the conversion of the fp32 image (utils/inference.py:129)."""
+    gan, g_sd, _ = make_gan(size, 21, "bf16")
+    G = gan.generator
+    with torch.no_grad():   # running statistics away from their (0, 1) initial values
+        for k, v in G.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(0.05 * O.hash_normal(tuple(v.shape), 300 + len(k)).to(v.device))
+            elif k.endswith("running_var"):
+                v.copy_(0.5 + O.hash_normal(tuple(v.shape), 400 + len(k)).abs().to(v.device))
+    G.eval()
+    z = O.hash_normal((B, 100), 77).cuda()
+    with torch.no_grad():
+        fused = G(z)
+        u8 = G.sample_uint8(z)
+    layered = G(z).detach()
+    assert torch.isfinite(fused).all() and fused.abs().max() <= 1
+    _check("fused tail vs layered path", fused, layered, 4e-3)   # both bf16 paths; they differ in rounding points only
+    ref, _, _ = O.g_forward({k: v.cpu() for k, v in G.state_dict().items()}, z.cpu(), size, train=False)
+    _check("fused tail vs oracle", fused, ref, tol("bf16"))
+    assert torch.equal(u8, ((fused + 1) * 127.5).clamp(0, 255).to(torch.uint8))
+    # first and last rows / columns are where the zero padding of the 3x3 stencil lives
+    for sl in ((..., 0, slice(None)), (..., size - 1, slice(None)), (..., slice(None), 0), (..., slice(None), size - 1)):
+        _check("border", fused[sl], ref[sl], 2e-2)
