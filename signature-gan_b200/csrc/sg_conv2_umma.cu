@@ -32,6 +32,7 @@ namespace sg {
 namespace {
 
 constexpr int kC2Threads = 64 + 32 * 8;
+constexpr int kC2ThreadsLean = 64 + 32 * 16;
 constexpr int kC2MaxStages = 24, kC2MaxProds = 32;
 constexpr int kC2ASlot = 24 * 1024;   // largest A box: (4+2) rows x 32 px x 128 B (20 KB for 16-wide grids)
 constexpr int kC2EpiStage = 32 * 128;  // per epilogue warp: 32 rows x 32 fp32 columns
@@ -103,6 +104,17 @@ __device__ __forceinline__ void c2_vec8(const float* p, bool vec_ok, float (&v)[
         for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
     }
 }
+// 16 TMEM lanes x 32 columns in the mma.sync accumulator layout (probed: tools/probes/tmem_ld_layout.cu):
+// r[4n + j] = lane (t >> 2) + 8 * (j >> 1), column 8n + 2 * (t & 3) + (j & 1)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t c2_epi_off(int row, int k) { return row * 128 + ((k ^ (row & 7)) << 4); }
 
 template <int BN, int kAccCols>
@@ -120,8 +132,11 @@ struct C2Cfg {
     static constexpr int kNCH = kAccCols / 64;              // 32-column chunks per epilogue warp
 };
 
-template <int BN, int kAccCols>
-__global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
+// kLean: the data-gradient epilogue of the four-parity mode (BN = 64, no bias / affine / activation; optional dropout
+// mask and LeakyReLU gate) with 16 epilogue warps working straight from registers — see the epilogue branch below.
+template <int BN, int kAccCols, bool kLean>
+__global__ void __launch_bounds__(kLean ? kC2ThreadsLean : kC2Threads, 1)
+conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
     using Cfg = C2Cfg<BN, kAccCols>;
     constexpr int STG = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 16);  // 8 epilogue warps in each CTA of the pair
+            mbar_init(&tempty[a], kLean ? 32 : 16);  // 8 (16) epilogue warps in each CTA of the pair
         }
         mbar_fence_init();
     }
@@ -263,6 +278,100 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2_umma_kernel(const __grid_
                 d[6] = dbg_acc[2];
                 d[7] = clock64() - t_begin;
                 d[8] = j;
+            }
+        }
+    } else if constexpr (kLean) {
+        // ---------------- Lean epilogue (data gradient, four parities): 16 warps, registers only ----------------
+        // The generic epilogue below (8 warps, fp32 staging in shared memory, one 32 x 32 chunk at a time) is a serial
+        // latency chain: with the gate read it held the MMA issuer on the accumulator hand-back for 27 % of the
+        // kernel (SIGGAN_CONV2_DEBUG counters), ~2000 cycles per chunk. Here warp (q, parity) owns 32 rows x the 64
+        // channels of one parity; tcgen05.ld.16x256b returns the accumulator with a lane's 8 columns per 32-column
+        // chunk fixed (mma.sync C layout), so the dropout mask is 8 registers, the gate is read and the result written
+        // with 4-byte accesses in that same layout (a quad covers 16 contiguous bytes, a thread's next column block
+        // the other half of the sector) — no staging, no shuffles, no barrier.
+        const int q = warp & 3, par = (warp - 2) >> 2;
+        const int gid = lane >> 2, t4 = lane & 3;
+        const int py = par >> 1, px = par & 1;
+        const int lgR = 31 - __clz(R), lgW = 31 - __clz(GW);
+        __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
+        const uint32_t tempty_leader[2] = {mapa_rank(smem_u32(&tempty[0]), 0), mapa_rank(smem_u32(&tempty[1]), 0)};
+        const float slope = args.slope;
+        // element offsets of this lane's four rows (gid + 8k) of a unit at column 2 * t4 of the parity's 64 channels
+        auto unit_offsets = [&](int u, size_t (&off)[4], bool (&ok)[4]) {
+            const int row0 = (u * 2 + static_cast<int>(rank)) * 128 + q * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int gm = row0 + gid + 8 * k;
+                ok[k] = gm < args.M_total;
+                const int img = gm >> lgR, rem = gm & (R - 1);
+                const int yh = rem >> lgW, xh = rem & (GW - 1);
+                const size_t orow = (static_cast<size_t>(img) * 2 * args.GH + 2 * yh + py) * 2 * GW + 2 * xh + px;
+                off[k] = orow * args.ldo + 2 * t4;
+            }
+        };
+        auto gate_fetch = [&](const size_t (&off)[4], const bool (&ok)[4], int ch, uint32_t (&g)[16]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+                    g[k * 4 + n] = (args.gate && ok[k])
+                                       ? __ldg(reinterpret_cast<const uint32_t*>(args.gate + off[k] + ch * 32 + 8 * n))
+                                       : 0x3f803f80u;   // bf16 (1, 1): gate open
+        };
+        // gate words: chunk 0 before the accumulator is waited for, chunk 1 while chunk 0 is processed. (Fetching the
+        // next unit's chunk 0 during chunk 1 instead measured slower: 0.416 vs 0.364 ms at B = 4096.)
+        int j = 0;
+        for (int u = first_unit; u < total_units; u += unit_step, ++j) {
+            const int acc = j & 1;
+            const int row0 = (u * 2 + static_cast<int>(rank)) * 128 + q * 32;
+            const int mi = row0 < args.M_total ? row0 >> lgR : 0;   // a 32-row group never spans two images (R >= 128)
+            size_t off[4];
+            bool ok[4];
+            unit_offsets(u, off, ok);
+            uint32_t gw[2][16];
+            gate_fetch(off, ok, 0, gw[0]);
+            mbar_wait(&tfull[acc], (j >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + par * 64 + ch * 32;
+                uint32_t v[2][16];
+                tmem_ld_16x256b_x4(tsrc, v[0]);
+                tmem_ld_16x256b_x4(tsrc + (16u << 16), v[1]);
+                if (ch == 0) gate_fetch(off, ok, 1, gw[1]);
+                float mk[4][2];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    mk[n][0] = mk[n][1] = 1.f;
+                    if (args.mask) {
+                        const float2 m2 = __ldg(reinterpret_cast<const float2*>(
+                            args.mask + static_cast<size_t>(mi) * args.ldmask + ch * 32 + 8 * n + 2 * t4));
+                        mk[n][0] = m2.x;
+                        mk[n][1] = m2.y;
+                    }
+                }
+                tmem_ld_wait();
+                if (ch == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) {
+                        const int k = h * 2 + rs;          // row gid + 8k
+#pragma unroll
+                        for (int n = 0; n < 4; ++n) {
+                            const uint32_t g = gw[ch][k * 4 + n];
+                            const float f0 = __uint_as_float(v[h][4 * n + 2 * rs]) * mk[n][0] *
+                                             (c2_lo(g) > 0.f ? 1.f : slope);
+                            const float f1 = __uint_as_float(v[h][4 * n + 2 * rs + 1]) * mk[n][1] *
+                                             (c2_hi(g) > 0.f ? 1.f : slope);
+                            if (ok[k])
+                                *reinterpret_cast<uint32_t*>(outp + off[k] + ch * 32 + 8 * n) = c2_pack(f0, f1);
+                        }
+                    }
             }
         }
     } else {
@@ -465,12 +574,12 @@ int c2_sm_count() {
     return n;
 }
 
-template <int BN, int kAccCols>
+template <int BN, int kAccCols, bool kLean = false>
 int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
     using Cfg = C2Cfg<BN, kAccCols>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv2_umma_kernel<BN, kAccCols>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(conv2_umma_kernel<BN, kAccCols, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes) != cudaSuccess)
             return -1;
         attr_set = true;
@@ -490,7 +599,7 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
     note_launch();
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kC2Threads);
+    lc.blockDim = dim3(kLean ? kC2ThreadsLean : kC2Threads);
     lc.dynamicSmemBytes = Cfg::kSmemBytes;
     lc.stream = stream;
     cudaLaunchAttribute attr;
@@ -500,7 +609,7 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
     attr.val.clusterDim.z = 1;
     lc.attrs = &attr;
     lc.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&lc, conv2_umma_kernel<BN, kAccCols>, a);
+    cudaError_t e = cudaLaunchKernelEx(&lc, conv2_umma_kernel<BN, kAccCols, kLean>, a);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (debug && e == cudaSuccess) {
         static int shown = 0;
@@ -645,7 +754,12 @@ int launch_conv2(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_
                     }
             }
         a.n_stages = ns;
-        return launch_c2<64, 256>(a, stream);
+        // data-gradient epilogue (mask / gate only) on 16 register-only epilogue warps; SIGGAN_CONV2_LEAN=0: generic one
+        static const bool lean_on = !(getenv("SIGGAN_CONV2_LEAN") && getenv("SIGGAN_CONV2_LEAN")[0] == '0');
+        const bool lean = lean_on && !e.bias && !e.scale && !e.shift && e.act == kActNone && R >= 128 &&
+                          (!e.mask || (reinterpret_cast<uintptr_t>(e.mask) % 8 == 0 && e.ldmask % 2 == 0)) &&
+                          e.ldo % 2 == 0;
+        return lean ? launch_c2<64, 256, true>(a, stream) : launch_c2<64, 256>(a, stream);
     }
     // Cout == 128, 8x8 grids: a 128-row tile is two whole images; one box per (dy, dx), one vertical parity per unit
     a.variants = 2;

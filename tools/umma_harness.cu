@@ -164,7 +164,8 @@ static void cpu_wgrad(const std::vector<float>& c, const std::vector<float>& f, 
             }
 }
 
-static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout, bool epi) {
+// epi: 0 none, 1 bias + LeakyReLU + dropout mask + gate, 2 mask + gate only (the data-gradient epilogue)
+static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, int Cin, int Cout, int epi) {
     Dev x, w;
     const int taps = mode == sg::kPlain ? 1 : 16;
     x.init(mode == sg::kPlain ? (size_t)N * Cin : (size_t)N * H * W * Cin, 1.0f);
@@ -202,11 +203,16 @@ static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, i
         std::vector<float> hb(Cout), hm((size_t)N * Cout);
         for (auto& v : hb) v = frand() * 0.5f;
         for (auto& v : hm) v = frand() > -0.5f ? 4.f / 3.f : 0.f;
-        CK(cudaMalloc(&bias, Cout * 4));
-        CK(cudaMemcpy(bias, hb.data(), Cout * 4, cudaMemcpyHostToDevice));
-        a.bias = bias;
-        a.act = sg::kActLeaky;
-        a.slope = 0.2f;
+        if (epi == 2) {
+            for (auto& v : hb) v = 0.f;
+            a.slope = 0.2f;
+        } else {
+            CK(cudaMalloc(&bias, Cout * 4));
+            CK(cudaMemcpy(bias, hb.data(), Cout * 4, cudaMemcpyHostToDevice));
+            a.bias = bias;
+            a.act = sg::kActLeaky;
+            a.slope = 0.2f;
+        }
         if (mode != sg::kPlain) {
             CK(cudaMalloc(&mask, hm.size() * 4));
             CK(cudaMemcpy(mask, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice));
@@ -219,7 +225,7 @@ static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, i
             const int co = (int)(i % Cout);
             const size_t pix = i / Cout;
             float v = ref[i] + hb[co];
-            v = v > 0 ? v : 0.2f * v;
+            if (epi != 2) v = v > 0 ? v : 0.2f * v;
             if (mode != sg::kPlain) {
                 v *= hm[(pix / opi) * Cout + co];
                 v *= gate.h[i] > 0 ? 1.f : 0.2f;
@@ -588,6 +594,8 @@ int main(int argc, char** argv) {
     RUN(test_conv("conv2 S2 161x32x32x64->128", sg::kConvS2, 161, 32, 32, 64, 128, true));
     RUN(test_conv("conv2 T4 5x16x16x128->64 +epi", sg::kConvT, 5, 16, 16, 128, 64, true));
     RUN(test_conv("conv2 T4 171x16x16x128->64", sg::kConvT, 171, 16, 16, 128, 64, false));
+    RUN(test_conv("conv2 T4 171x16x16x128->64 +gate,mask", sg::kConvT, 171, 16, 16, 128, 64, 2));
+    RUN(test_conv("conv2 T4 3x32x32x128->64 +gate,mask", sg::kConvT, 3, 32, 32, 128, 64, 2));
     RUN(test_conv("conv2 S2 3x64x64x64->128 +epi", sg::kConvS2, 3, 64, 64, 64, 128, true));
     RUN(test_conv("conv2 T4 3x32x32x128->64 +epi", sg::kConvT, 3, 32, 32, 128, 64, true));
     RUN(test_conv("conv2 T2 7x8x8x256->128 +epi", sg::kConvT, 7, 8, 8, 256, 128, true));
