@@ -115,6 +115,18 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// 4 x 4 transpose of 32-bit words across the four lanes of a quad: lane i holds row i on entry, column i on exit
+// (two butterfly exchanges). It converts between the accumulator-fragment layout (lane t4 owns 4 bytes of each of the
+// four 16-byte column blocks of a row) and the memory layout (lane t4 owns the whole 16-byte block t4).
+__device__ __forceinline__ void quad_transpose(uint32_t (&a)[4], int t4) {
+    const bool o1 = t4 & 1, o2 = t4 & 2;
+    const uint32_t s0 = __shfl_xor_sync(0xffffffffu, o1 ? a[0] : a[1], 1);
+    const uint32_t s1 = __shfl_xor_sync(0xffffffffu, o1 ? a[2] : a[3], 1);
+    if (o1) { a[0] = s0; a[2] = s1; } else { a[1] = s0; a[3] = s1; }
+    const uint32_t u0 = __shfl_xor_sync(0xffffffffu, o2 ? a[0] : a[2], 2);
+    const uint32_t u1 = __shfl_xor_sync(0xffffffffu, o2 ? a[1] : a[3], 2);
+    if (o2) { a[0] = u0; a[1] = u1; } else { a[2] = u0; a[3] = u1; }
+}
 __device__ __forceinline__ uint32_t c2_epi_off(int row, int k) { return row * 128 + ((k ^ (row & 7)) << 4); }
 
 template <int BN, int kAccCols>
@@ -286,9 +298,10 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
         // latency chain: with the gate read it held the MMA issuer on the accumulator hand-back for 27 % of the
         // kernel (SIGGAN_CONV2_DEBUG counters), ~2000 cycles per chunk. Here warp (q, parity) owns 32 rows x the 64
         // channels of one parity; tcgen05.ld.16x256b returns the accumulator with a lane's 8 columns per 32-column
-        // chunk fixed (mma.sync C layout), so the dropout mask is 8 registers, the gate is read and the result written
-        // with 4-byte accesses in that same layout (a quad covers 16 contiguous bytes, a thread's next column block
-        // the other half of the sector) — no staging, no shuffles, no barrier.
+        // chunk fixed (mma.sync C layout), so the dropout mask is 8 registers; the gate is read and the result written
+        // as one 16-byte access per row and lane, converted from / to the fragment layout by 4 x 4 transposes inside
+        // each quad (4 shuffles per row) — no staging, no barrier. (4-byte accesses directly in the fragment layout
+        // ran the L1 at 80 % of its throughput: profiles/r01_ncu_conv2_lean.txt.)
         const int q = warp & 3, par = (warp - 2) >> 2;
         const int gid = lane >> 2, t4 = lane & 3;
         const int py = par >> 1, px = par & 1;
@@ -296,7 +309,8 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
         __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
         const uint32_t tempty_leader[2] = {mapa_rank(smem_u32(&tempty[0]), 0), mapa_rank(smem_u32(&tempty[1]), 0)};
         const float slope = args.slope;
-        // element offsets of this lane's four rows (gid + 8k) of a unit at column 2 * t4 of the parity's 64 channels
+        // element offsets of this lane's four rows (gid + 8k) of a unit at its 16-byte block (columns 8 * t4 ..) of a
+        // 32-channel chunk of the parity's 64 channels
         auto unit_offsets = [&](int u, size_t (&off)[4], bool (&ok)[4]) {
             const int row0 = (u * 2 + static_cast<int>(rank)) * 128 + q * 32;
 #pragma unroll
@@ -306,17 +320,15 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
                 const int img = gm >> lgR, rem = gm & (R - 1);
                 const int yh = rem >> lgW, xh = rem & (GW - 1);
                 const size_t orow = (static_cast<size_t>(img) * 2 * args.GH + 2 * yh + py) * 2 * GW + 2 * xh + px;
-                off[k] = orow * args.ldo + 2 * t4;
+                off[k] = orow * args.ldo + 8 * t4;
             }
         };
-        auto gate_fetch = [&](const size_t (&off)[4], const bool (&ok)[4], int ch, uint32_t (&g)[16]) {
+        // one 16-byte load per row: the gate in memory layout; transposed to the fragment layout where it is used
+        auto gate_fetch = [&](const size_t (&off)[4], const bool (&ok)[4], int ch, uint4 (&g)[4]) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int n = 0; n < 4; ++n)
-                    g[k * 4 + n] = (args.gate && ok[k])
-                                       ? __ldg(reinterpret_cast<const uint32_t*>(args.gate + off[k] + ch * 32 + 8 * n))
-                                       : 0x3f803f80u;   // bf16 (1, 1): gate open
+                g[k] = (args.gate && ok[k]) ? __ldg(reinterpret_cast<const uint4*>(args.gate + off[k] + ch * 32))
+                                            : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // open
         };
         // gate words: chunk 0 before the accumulator is waited for, chunk 1 while chunk 0 is processed. (Fetching the
         // next unit's chunk 0 during chunk 1 instead measured slower: 0.416 vs 0.364 ms at B = 4096.)
@@ -328,7 +340,7 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
             size_t off[4];
             bool ok[4];
             unit_offsets(u, off, ok);
-            uint32_t gw[2][16];
+            uint4 gw[2][4];
             gate_fetch(off, ok, 0, gw[0]);
             mbar_wait(&tfull[acc], (j >> 1) & 1);
             tc_fence_after();
@@ -361,16 +373,20 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
 #pragma unroll
                     for (int rs = 0; rs < 2; ++rs) {
                         const int k = h * 2 + rs;          // row gid + 8k
+                        uint32_t g4[4] = {gw[ch][k].x, gw[ch][k].y, gw[ch][k].z, gw[ch][k].w};
+                        quad_transpose(g4, t4);            // g4[n] = gate of columns 8n + 2 t4, +1
+                        uint32_t r4[4];
 #pragma unroll
                         for (int n = 0; n < 4; ++n) {
-                            const uint32_t g = gw[ch][k * 4 + n];
                             const float f0 = __uint_as_float(v[h][4 * n + 2 * rs]) * mk[n][0] *
-                                             (c2_lo(g) > 0.f ? 1.f : slope);
+                                             (c2_lo(g4[n]) > 0.f ? 1.f : slope);
                             const float f1 = __uint_as_float(v[h][4 * n + 2 * rs + 1]) * mk[n][1] *
-                                             (c2_hi(g) > 0.f ? 1.f : slope);
-                            if (ok[k])
-                                *reinterpret_cast<uint32_t*>(outp + off[k] + ch * 32 + 8 * n) = c2_pack(f0, f1);
+                                             (c2_hi(g4[n]) > 0.f ? 1.f : slope);
+                            r4[n] = c2_pack(f0, f1);
                         }
+                        quad_transpose(r4, t4);            // r4 = columns 8 t4 .. 8 t4 + 7 of the row
+                        if (ok[k])
+                            *reinterpret_cast<uint4*>(outp + off[k] + ch * 32) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
                     }
             }
         }
