@@ -386,6 +386,9 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own messages (e.g. its version banner under NCCL_DEBUG=VERSION) go to
+    # stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
