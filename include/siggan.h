@@ -104,6 +104,18 @@ int sg_bce_backward(const float* prob, const float* target, int n, const float* 
 int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                  float beta1, float beta2, float eps, long long step, void* stream);
 
+/* ---- torch.nn.utils.spectral_norm on a Discriminator weight (disc…:61-62 Conv2d, :201-202 Linear) ---- */
+/* w_orig = weight_orig viewed as (rows = Cout, cols = Cin*kh*kw); u (rows) / v (cols) = weight_u / weight_v,
+ * updated IN PLACE by `power_iterations` power iterations (1 in training mode, 0 in eval mode):
+ *   v <- W^T u / max(|W^T u|, eps);  u <- W v / max(|W v|, eps);  sigma = u.(W v);  w_out = W / sigma.
+ * sigma_out: 1 float (device), kept by the caller for the backward. scratch: >= max(rows, 512) floats. */
+int sg_spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, int cols, int power_iterations,
+                            float eps, float* w_out, float* sigma_out, float* scratch, void* stream);
+/* grad holds dL/dw_eff on entry and dL/dw_orig = (grad - <grad, w_eff> u v^T) / sigma on return (u, v, sigma as
+ * the matching sg_spectral_norm_weight call left them). */
+int sg_spectral_norm_backward(const float* w_eff, const float* u, const float* v, const float* sigma, int rows,
+                              int cols, float* grad, float* scratch, void* stream);
+
 /* ---- Fused D step + G step (vanilla…:308-336 with n_critic = 1) ------------------------------- */
 typedef struct sg_train_state {
     float* g_params; float* g_running_stats; float* g_exp_avg; float* g_exp_avg_sq;

@@ -197,6 +197,94 @@ def d_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dprob: Tensor, i
 
 
 # --------------------------------------------------------------------------------------------
+# Spectral-norm variant of the Discriminator (disc…:61-62 Conv2d, :201-202 Linear wrapped in
+# torch.nn.utils.spectral_norm; built by ablation_vanilla_gan_signatures.py:367-371). The arithmetic lives in
+# torch (SpectralNorm.compute_weight, torch/nn/utils/spectral_norm.py); restated here.
+# --------------------------------------------------------------------------------------------
+SN_EPS = 1e-12  # spectral_norm default eps
+
+
+def sn_layer_names(image_size: int) -> List[str]:
+    return [f"conv_blocks.{i}.block.0" for i in range(len(d_channels(image_size)) - 1)] + ["classifier.0"]
+
+
+def spectral_weight(w_orig: Tensor, u: Tensor, v: Tensor, power_iterations: int, eps: float = SN_EPS):
+    """One compute_weight call. Returns (weight, u', v', sigma); u', v' are what the buffers hold afterwards.
+    W = weight_orig as (Cout, -1); v <- normalize(W^T u); u <- normalize(W v); sigma = u.(W v); weight = W_orig/sigma.
+    normalize(x) = x / max(||x||_2, eps)."""
+    W = w_orig.reshape(w_orig.shape[0], -1)
+    for _ in range(power_iterations):
+        t = W.t() @ u
+        v = t / torch.clamp(t.norm(), min=eps)
+        s = W @ v
+        u = s / torch.clamp(s.norm(), min=eps)
+    sigma = torch.dot(u, W @ v)
+    return w_orig / sigma, u, v, sigma
+
+
+def spectral_grad(g_eff: Tensor, w_eff: Tensor, u: Tensor, v: Tensor, sigma: Tensor) -> Tensor:
+    """dL/dweight_orig from dL/dweight with u, v constant: (G - <G, weight> u v^T) / sigma."""
+    inner = (g_eff * w_eff).sum()
+    return (g_eff - inner * torch.outer(u, v).view_as(g_eff)) / sigma
+
+
+def sn_effective(sd: Dict[str, Tensor], image_size: int, train: bool):
+    """sd keyed like the reference's SN state_dict ({p}.weight_orig / weight_u / weight_v / bias). Returns the plain
+    state dict the layers run on, the per-layer (u', v', sigma), and the buffers after the call."""
+    eff: Dict[str, Tensor] = {}
+    aux: Dict[str, Tuple[Tensor, Tensor, Tensor]] = {}
+    new_buffers: Dict[str, Tensor] = {}
+    for p in sn_layer_names(image_size):
+        w, u, v, sigma = spectral_weight(sd[p + ".weight_orig"], sd[p + ".weight_u"], sd[p + ".weight_v"],
+                                         1 if train else 0)
+        eff[p + ".weight"], eff[p + ".bias"] = w, sd[p + ".bias"]
+        aux[p] = (u, v, sigma)
+        new_buffers[p + ".weight_u"], new_buffers[p + ".weight_v"] = u, v
+    return eff, aux, new_buffers
+
+
+def d_forward_sn(sd: Dict[str, Tensor], x: Tensor, image_size: int = 64, masks: Optional[List[Tensor]] = None,
+                 train: bool = False):
+    """Forward of Discriminator(use_spectral_norm=True). `train` = module.training (power iteration on/off); masks as
+    in d_forward. Returns (prob, cache, new_buffers)."""
+    eff, aux, new_buffers = sn_effective(sd, image_size, train)
+    prob, cache = d_forward(eff, x, image_size, masks)
+    cache["__eff"], cache["__aux"] = eff, aux
+    return prob, cache, new_buffers
+
+
+def d_backward_sn(cache: Dict[str, Tensor], dprob: Tensor, image_size: int = 64,
+                  masks: Optional[List[Tensor]] = None, need_dx: bool = False) -> Dict[str, Tensor]:
+    eff, aux = cache["__eff"], cache["__aux"]
+    g = d_backward(eff, cache, dprob, image_size, masks, need_dx)
+    out: Dict[str, Tensor] = {}
+    for k, val in g.items():
+        if k.endswith(".weight"):
+            p = k[:-len(".weight")]
+            u, v, sigma = aux[p]
+            out[p + ".weight_orig"] = spectral_grad(val, eff[k], u, v, sigma)
+        else:
+            out[k] = val
+    return out
+
+
+def make_sn_state_dict(image_size: int = 64, seed: int = 0) -> Dict[str, Tensor]:
+    """SN-variant state dict in the reference's key order: kaiming-scale weight_orig (the reference's DCGAN init
+    does not reach weight_orig, disc…:212-239 initialises the derived `weight`), unit-norm u / v."""
+    _, d = make_state_dicts(image_size, 100, seed)
+    out: Dict[str, Tensor] = {}
+    for k, p in enumerate(sn_layer_names(image_size)):
+        w = d[p + ".weight"] * 2.5
+        out[p + ".bias"] = d[p + ".bias"]
+        out[p + ".weight_orig"] = w
+        u = hash_normal((w.shape[0],), seed * 1000 + 500 + k)
+        v = hash_normal((w[0].numel(),), seed * 1000 + 520 + k)
+        out[p + ".weight_u"] = u / u.norm()
+        out[p + ".weight_v"] = v / v.norm()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # nn.BCELoss on probabilities (vanilla…:107): log clamped at -100, mean reduction
 # --------------------------------------------------------------------------------------------
 def bce(p: Tensor, y: Tensor) -> Tensor:

@@ -63,6 +63,8 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_bce_forward": (_I, [_P, _P, _I, _P, _P]),
     "sg_bce_backward": (_I, [_P, _P, _I, _P, _P, _P]),
     "sg_adam_step": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _LL, _P]),
+    "sg_spectral_norm_weight": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "sg_spectral_norm_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "sg_train_step": (_I, [_P, C.POINTER(SgTrainState), _P, _P, _P, _I, _P, _P, _P, _I, _P]),
 }
 
@@ -189,15 +191,21 @@ class FlatParams:
         self._gbuf: List[Optional[torch.Tensor]] = [None, None]
         self.params: List[torch.nn.Parameter] = []
         self.layout: List[Tuple[int, int, Tuple[int, ...]]] = []
+        self._names: List[str] = []
 
     def sync(self, ctx: Context, bns: Optional[list] = None) -> None:
         """(Re)build the flat buffers if any parameter no longer lives at its slot (first call, .to(), ...)."""
-        params = list(self.module.parameters())
         table = ctx.tensor_table(self.net) if not self.layout else None
         if table is not None:
-            named = [n for n, _ in self.module.named_parameters()]
-            if [t[0] for t in table] != named:
-                raise RuntimeError(f"parameter table mismatch between module and libsiggan: {named} vs {[t[0] for t in table]}")
+            # A spectral-normalised layer (torch.nn.utils.spectral_norm, disc…:61-62, 201-202) owns `weight_orig`
+            # where the library's table says `weight`, and lists it after `bias`: bind by name, in table order.
+            named = dict(self.module.named_parameters())
+            self._names = [n if n in named else n + "_orig" for n in (t[0] for t in table)]
+            if sorted(self._names) != sorted(named):
+                raise RuntimeError(f"parameter table mismatch between module and libsiggan: {sorted(named)} vs {[t[0] for t in table]}")
+        named = dict(self.module.named_parameters())
+        params = [named[n] for n in self._names]
+        if table is not None:
             for p, (_, off, shape) in zip(params, table):
                 if tuple(p.shape) != shape:
                     raise RuntimeError(f"parameter shape mismatch: {tuple(p.shape)} vs {shape}")

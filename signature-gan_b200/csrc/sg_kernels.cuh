@@ -150,6 +150,13 @@ template <typename T>
 void fc_dz_direct(const T* dy, const float* W, float* dz, int B, int C0, int latent, cudaStream_t s);
 
 const char* kernels_last_error();
+// ---- spectral normalisation of a (rows, cols) weight matrix (sg_spectral.cu) -----------------------
+// scratch: at least max(rows, 512) floats.
+void spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, int cols, int power_iterations, float eps,
+                          float* w_out, float* sigma, float* scratch, cudaStream_t s);
+void spectral_norm_backward(const float* w_eff, const float* u, const float* v, const float* sigma, int rows, int cols,
+                            float* grad, float* scratch, cudaStream_t s);
+
 int kernels_check(const char* what);  // cudaGetLastError -> 0 / -1 (message kept)
 
 }  // namespace sg

@@ -163,6 +163,7 @@ struct sg_ctx {
     bf16 *fc_Wp, *g_packF[6], *g_packB[6], *d_packF[6], *d_packB[6];
     float *fc_biasp, *cls_wp;
     DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
+    const float* d_pack_src = nullptr;  // parameter buffer the Discriminator packs were last built from
     bool u8_only = false;  // current sg_g_forward call wants the uint8 image only (no caller-visible fp32 image)
     float *dlogit, *k1, *k2, *k3;
     int scratch_batch = 0;
@@ -286,6 +287,7 @@ int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
 }
 int pack_discriminator(sg_ctx* c, const float* params, cudaStream_t s) {
     PROF("d.pack", 0, 10.0 * c->d_count);
+    c->d_pack_src = params;
     sg::pack_classifier(params + c->dt[c->d_cls_w].offset, c->cls_wp, c->dch[c->ND], s);
     if (c->cfg.precision == SG_PREC_BF16) {
         for (int i = 1; i < c->ND; ++i)  // W (Cout, Cin, 4, 4): forward pack [Cout][16][Cin] = AB, dgrad pack = BA
@@ -951,6 +953,9 @@ int sg_d_backward(sg_ctx* c, const float* params, const float* x, const void* ws
     SG_TRY(ensure_scratch(c, batch));
     DWs w = carve_d(c, const_cast<void*>(ws), batch);
     sg::sigmoid_bwd(w.prob, grad_prob, c->dlogit, batch, s);
+    // the packs are those of the latest forward: a backward for an earlier forward that ran on OTHER weights (the
+    // spectral-norm variant hands every forward its own weight_orig / sigma buffer) packs its own again
+    if (c->d_pack_src != params) SG_TRY(pack_discriminator(c, params, s));
     return DISPATCH_T(c, d_backward_t, c, params, x, ws, masks, c->dlogit, batch, grads_out, dx_out, s);
 }
 
@@ -980,6 +985,25 @@ int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail("sg_adam_step: bad argument");
     sg::adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_adam_step");
+    return 0;
+}
+
+int sg_spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, int cols, int power_iterations,
+                            float eps, float* w_out, float* sigma_out, float* scratch, void* stream) {
+    if (!w_orig || !u || !v || !w_out || !sigma_out || !scratch || rows < 1 || cols < 1 || power_iterations < 0 ||
+        !(eps > 0.f))
+        return fail("sg_spectral_norm_weight: bad argument");
+    sg::spectral_norm_weight(w_orig, u, v, rows, cols, power_iterations, eps, w_out, sigma_out, scratch,
+                             static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_spectral_norm_weight");
+    return 0;
+}
+int sg_spectral_norm_backward(const float* w_eff, const float* u, const float* v, const float* sigma, int rows,
+                              int cols, float* grad, float* scratch, void* stream) {
+    if (!w_eff || !u || !v || !sigma || !grad || !scratch || rows < 1 || cols < 1)
+        return fail("sg_spectral_norm_backward: bad argument");
+    sg::spectral_norm_backward(w_eff, u, v, sigma, rows, cols, grad, scratch, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_spectral_norm_backward");
     return 0;
 }
 

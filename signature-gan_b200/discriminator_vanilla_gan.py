@@ -11,6 +11,7 @@ from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
+from torch.nn.utils import spectral_norm
 
 import _siggan_lib as L
 
@@ -22,11 +23,16 @@ class DownsampleBlock(nn.Module):
                  use_batch_norm: bool = False, use_spectral_norm: bool = False, dropout: float = 0.25,
                  leaky_slope: float = 0.2) -> None:
         super().__init__()
-        if use_batch_norm or use_spectral_norm:
-            raise NotImplementedError("siggan_b200 covers the reference Discriminator's default blocks "
-                                      "(no BatchNorm; spectral norm is a later row of the scope table)")
-        mods: List[nn.Module] = [nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
-                                           padding=padding, bias=True), nn.LeakyReLU(leaky_slope, inplace=True)]
+        if use_batch_norm:
+            raise NotImplementedError("siggan_b200 covers the blocks the reference Discriminator builds "
+                                      "(use_batch_norm is never set by it, disc…:131-194)")
+        conv = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, bias=True)
+        if use_spectral_norm:
+            # same wrapper as the reference (disc…:61-62): registers weight_orig / weight_u / weight_v with torch's
+            # own initialisation, state-dict versioning and load hooks; its forward pre-hook never runs here (the
+            # holder is not called) — Discriminator.forward does the power iteration through sg_spectral_norm_weight.
+            conv = spectral_norm(conv)
+        mods: List[nn.Module] = [conv, nn.LeakyReLU(leaky_slope, inplace=True)]
         if dropout > 0:
             mods.append(nn.Dropout2d(dropout))
         self.block = nn.Sequential(*mods)
@@ -36,6 +42,21 @@ class DownsampleBlock(nn.Module):
 
 
 _mask_counter = [0]
+
+
+class _SpectralWeights:
+    """Effective weights of one forward of the spectral-norm variant: flat copy of the parameters with every
+    weight divided by its sigma, plus the (u, v, sigma) that forward used (torch SpectralNorm.compute_weight)."""
+
+    def __init__(self, eff: torch.Tensor, layers: list, sigma: torch.Tensor, scratch: torch.Tensor) -> None:
+        self.eff, self.layers, self.sigma, self.scratch = eff, layers, sigma, scratch
+
+    def backward(self, sctx: "L.Context", gflat: torch.Tensor, dev: torch.device) -> None:
+        """dL/dweight -> dL/dweight_orig, in place in the flat gradient buffer."""
+        for k, (off, rows, cols, u, v) in enumerate(self.layers):
+            L.check(sctx.lib.sg_spectral_norm_backward(
+                L.ptr(self.eff) + 4 * off, L.ptr(u), L.ptr(v), L.ptr(self.sigma) + 4 * k, rows, cols,
+                L.ptr(gflat) + 4 * off, L.ptr(self.scratch), L.current_stream(dev)), "sg_spectral_norm_backward")
 
 
 class _DiscriminatorFn(torch.autograd.Function):
@@ -50,9 +71,13 @@ class _DiscriminatorFn(torch.autograd.Function):
         ws = None
         if save:
             ws = torch.empty(int(sctx.lib.sg_d_workspace_bytes(sctx.handle, B)), dtype=torch.uint8, device=dev)
-        L.check(sctx.lib.sg_d_forward(sctx.handle, L.ptr(fp.flat), L.ptr(x), B, L.ptr(masks), L.ptr(ws), L.ptr(prob),
+        # spectral-norm variant: the layers run on weight_orig / sigma; what this call's power iteration left in
+        # (u, v, sigma) is kept for its own backward (a later forward of the same module iterates again)
+        sn = disc._spectral_weights(dev) if disc.use_spectral_norm else None
+        weights = sn.eff if sn is not None else fp.flat
+        L.check(sctx.lib.sg_d_forward(sctx.handle, L.ptr(weights), L.ptr(x), B, L.ptr(masks), L.ptr(ws), L.ptr(prob),
                                       None, L.current_stream(dev)), "sg_d_forward")
-        ctx.disc, ctx.ws, ctx.masks, ctx.x, ctx.B = disc, ws, masks, x, B
+        ctx.disc, ctx.ws, ctx.masks, ctx.x, ctx.B, ctx.sn = disc, ws, masks, x, B, (sn if save else None)
         ctx.x_needs_grad = x.requires_grad
         ctx.w_needs_grad = any(p.requires_grad for p in params)
         return prob
@@ -67,10 +92,14 @@ class _DiscriminatorFn(torch.autograd.Function):
         dev = grad_prob.device
         gflat = fp.fresh_grad() if ctx.w_needs_grad else None
         dx = torch.empty_like(ctx.x) if ctx.x_needs_grad else None
-        L.check(sctx.lib.sg_d_backward(sctx.handle, L.ptr(fp.flat), L.ptr(ctx.x), L.ptr(ctx.ws), L.ptr(ctx.masks),
+        sn = ctx.sn
+        weights = sn.eff if sn is not None else fp.flat
+        L.check(sctx.lib.sg_d_backward(sctx.handle, L.ptr(weights), L.ptr(ctx.x), L.ptr(ctx.ws), L.ptr(ctx.masks),
                                        L.ptr(grad_prob), ctx.B, L.ptr(gflat), L.ptr(dx), L.current_stream(dev)),
                 "sg_d_backward")
-        ctx.ws = None
+        if sn is not None and gflat is not None:
+            sn.backward(sctx, gflat, dev)
+        ctx.ws = ctx.sn = None
         grads = fp.grad_views(gflat) if gflat is not None else [None] * len(fp.params)
         return (None, None, None, dx, *grads)
 
@@ -97,7 +126,10 @@ class Discriminator(nn.Module):
             DownsampleBlock(a, b, use_spectral_norm=use_spectral_norm, dropout=dropout, leaky_slope=leaky_slope)
             for a, b in zip(ladder[:-1], ladder[1:])])
         self.flatten = nn.Flatten()
-        self.classifier = nn.Sequential(nn.Linear(ladder[-1] * 4 * 4, 1), nn.Sigmoid())
+        fc = nn.Linear(ladder[-1] * 4 * 4, 1)
+        if use_spectral_norm:
+            fc = spectral_norm(fc)                  # disc…:199-202
+        self.classifier = nn.Sequential(fc, nn.Sigmoid())
         self.apply(self._init_weights)
         self._flat = L.FlatParams(self, L.SG_NET_D)
         self._ctx: Optional[L.Context] = None
@@ -123,6 +155,39 @@ class Discriminator(nn.Module):
                                   self.leaky_slope)
         self._flat.sync(self._ctx)
 
+    def _sn_modules(self) -> List[nn.Module]:
+        return [blk.block[0] for blk in self.conv_blocks] + [self.classifier[0]]
+
+    def _spectral_weights(self, device: torch.device, classifier: bool = True) -> _SpectralWeights:
+        """One SpectralNorm.compute_weight per wrapped layer, as the reference's forward pre-hooks do on every call
+        (disc…:61-62, 201-202): a power iteration that updates weight_u / weight_v in place when the module is in
+        training mode, none in eval mode; then weight = weight_orig / sigma."""
+        sctx, fp = self._ctx, self._flat
+        mods = self._sn_modules()
+        eff = fp.flat.clone()                       # biases travel unchanged
+        sigma = torch.empty(len(mods), dtype=torch.float32, device=device)
+        scratch = torch.empty(1024, dtype=torch.float32, device=device)
+        by_name = {n: k for k, n in enumerate(fp._names)}
+        layers = []
+        names = [f"conv_blocks.{i}.block.0" for i in range(len(self.conv_blocks))] + ["classifier.0"]
+        if not classifier:                          # forward_features never calls the classifier (disc…:262-274)
+            names, mods = names[:-1], mods[:-1]
+        for k, (name, m) in enumerate(zip(names, mods)):
+            off, n, shape = fp.layout[by_name[name + ".weight_orig"]]
+            rows, cols = shape[0], n // shape[0]
+            hook = next(h for h in m._forward_pre_hooks.values() if hasattr(h, "n_power_iterations"))
+            u, v = m.weight_u, m.weight_v
+            if u.device != device or v.device != device or not u.is_contiguous() or not v.is_contiguous():
+                raise RuntimeError("spectral-norm buffers must live on the module's CUDA device")
+            iters = hook.n_power_iterations if self.training else 0
+            L.check(sctx.lib.sg_spectral_norm_weight(
+                L.ptr(fp.flat) + 4 * off, L.ptr(u), L.ptr(v), rows, cols, iters, float(hook.eps),
+                L.ptr(eff) + 4 * off, L.ptr(sigma) + 4 * k, L.ptr(scratch), L.current_stream(device)),
+                "sg_spectral_norm_weight")
+            # torch clones u / v after iterating so that a backward of this forward is not disturbed by the next one
+            layers.append((off, rows, cols, u.clone() if iters else u, v.clone() if iters else v))
+        return _SpectralWeights(eff, layers, sigma, scratch)
+
     def set_precision(self, precision: str) -> "Discriminator":
         self._precision = {"bf16": L.SG_PREC_BF16, "fp32": L.SG_PREC_FP32}[precision]
         return self
@@ -144,7 +209,7 @@ class Discriminator(nn.Module):
         return masks
 
     def _check_input(self, x: torch.Tensor) -> torch.device:
-        dev = self.classifier[0].weight.device
+        dev = self.classifier[0].bias.device
         if dev.type != "cuda" or x.device.type != "cuda":
             raise RuntimeError(f"siggan_b200 Discriminator runs on CUDA only (no CPU path); module on {dev}, input on {x.device}")
         if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] != self.input_size or x.shape[3] != self.input_size:
@@ -168,7 +233,8 @@ class Discriminator(nn.Module):
         sctx, fp = self._ctx, self._flat
         B = x.shape[0]
         feat = torch.empty(B, int(sctx.lib.sg_d_feature_count(sctx.handle)), dtype=torch.float32, device=dev)
-        L.check(sctx.lib.sg_d_forward(sctx.handle, L.ptr(fp.flat), L.ptr(x), B, L.ptr(self._masks(B, dev)), None, None,
+        weights = self._spectral_weights(dev, classifier=False).eff if self.use_spectral_norm else fp.flat
+        L.check(sctx.lib.sg_d_forward(sctx.handle, L.ptr(weights), L.ptr(x), B, L.ptr(self._masks(B, dev)), None, None,
                                       L.ptr(feat), L.current_stream(dev)), "sg_d_forward")
         return feat
 

@@ -215,7 +215,7 @@ class VanillaGAN(nn.Module):
             raise RuntimeError("siggan_b200 VanillaGAN trains on CUDA only (no CPU path)")
         g, d = self.generator, self.discriminator
         g._prepare(g.fc[0].weight.device)
-        d._prepare(d.classifier[0].weight.device)
+        d._prepare(d.classifier[0].bias.device)
         self.g_optimizer._ensure_state()
         self.d_optimizer._ensure_state()
         if self._metrics is None or self._metrics.device != g._flat.flat.device:

@@ -57,6 +57,8 @@ def test_state_dict_contract_matches_reference(golden_dir):
         assert [(k, tuple(v.shape), str(v.dtype)) for k, v in D.state_dict().items()] == gold[f"d{size}"]
         assert G.get_num_params() == gold[f"g{size}.nparams"] and D.get_num_params() == gold[f"d{size}.nparams"]
         assert G.get_output_shape() == (1, size, size) and D.get_input_shape() == (1, size, size)
+    Dsn = Discriminator(64, use_spectral_norm=True)     # disc…:61-62, 201-202: weight_orig / weight_u / weight_v
+    assert [(k, tuple(v.shape), str(v.dtype)) for k, v in Dsn.state_dict().items()] == gold["d64sn"]
 
 
 def test_module_surface():

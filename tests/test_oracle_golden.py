@@ -116,3 +116,39 @@ def test_closed_form_facts():
     assert len(vals) == 2 and vals[0] == 0.0 and vals[1] == pytest.approx(4 / 3)
     img = O.synthetic_signatures(4, 64)
     assert img.shape == (4, 1, 64, 64) and img.max() <= 1 and img.min() >= -1 and (img < 0).any()
+
+
+def test_spectral_norm_variant_matches_reference(golden_dir):
+    """Discriminator(use_spectral_norm=True) (disc…:61-62, 201-202): power iteration, weight_orig / sigma, the
+    gradient through sigma, eval mode without iteration — against tests/golden/sn_64.pt (make_golden_sn.py)."""
+    gold = torch.load(os.path.join(golden_dir, "sn_64.pt"), weights_only=False)
+    size, B = gold["size"], gold["B"]
+    sd = O.make_sn_state_dict(size, seed=3)
+    assert list(sd.keys()) == gold["keys"]
+    x = O.synthetic_signatures(B, size, seed=7)
+    masks = gold["train1.masks"]
+    p1, cache, buf1 = O.d_forward_sn(sd, x, size, masks, train=True)
+    assert torch.allclose(p1, gold["train1.prob"], rtol=RTOL, atol=1e-6)
+    target = torch.full_like(p1, 0.9)
+    assert abs(float(O.bce(p1, target)) - gold["train1.loss"]) < 1e-5
+    for k, v in buf1.items():
+        assert torch.allclose(v, gold[f"train1.buf.{k}"], rtol=RTOL, atol=1e-6), k
+    for name in O.sn_layer_names(size):
+        check_probe(f"weight.{name}", cache["__eff"][name + ".weight"], gold[f"train1.weight.{name}"])
+    grads = O.d_backward_sn(cache, O.bce_grad(p1, target), size, masks)
+    for k in gold["keys"]:
+        if k.endswith("weight_orig") or k.endswith("bias"):
+            check_probe(f"grad.{k}", grads[k], gold[f"train1.grad.{k}"], rtol=GTOL)
+    sd2 = dict(sd)
+    sd2.update(buf1)
+    p2, _, buf2 = O.d_forward_sn(sd2, x, size, gold["train2.masks"], train=True)
+    assert torch.allclose(p2, gold["train2.prob"], rtol=RTOL, atol=1e-6)
+    for k, v in buf2.items():
+        assert torch.allclose(v, gold[f"train2.buf.{k}"], rtol=RTOL, atol=1e-6), k
+    sd3 = dict(sd2)
+    sd3.update(buf2)
+    pe, ce, buf3 = O.d_forward_sn(sd3, x, size, None, train=False)
+    assert torch.allclose(pe, gold["eval.prob"], rtol=RTOL, atol=1e-6)
+    check_probe("eval.feat", ce["feat"], gold["eval.feat"])
+    for k, v in buf3.items():
+        assert torch.equal(v, sd3[k]), f"{k}: eval mode must not iterate"
