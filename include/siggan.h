@@ -139,6 +139,18 @@ typedef struct sg_train_state {
 int sg_train_step(sg_ctx* ctx, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
                   int batch, float* d_grads, float* g_grads, float* metrics_out, int phase, void* stream);
 
+/* ---- synchronised BatchNorm for data-parallel runs ------------------------------- */
+/* With a callback set, every training-mode BatchNorm of the Generator (gen…:58,126) normalises with the statistics of
+ * the GLOBAL batch: the per-channel sums (sum x, sum x^2 in forward; sum d, sum d*xhat in backward; 2*C floats) are
+ * placed in `buf`, `fn(user, buf, count, stream)` must sum them in place over the `world_size` ranks (enqueued on
+ * `stream`, e.g. an NCCL all-reduce; return 0 on success), and the row count is scaled by world_size. BatchNorm weight
+ * / bias gradients stay local sums — the caller averages the gradient bucket as for every other parameter — so that
+ * W ranks x B images reproduce one process at W*B images. buf: caller-owned device memory, >= 4 * the largest BatchNorm
+ * channel count floats (16 * init_channels for the fc BatchNorm1d). fn == NULL switches back to local statistics. */
+typedef int (*sg_allreduce_fn)(void* user, float* buf, long long count, void* stream);
+int sg_set_sync_batchnorm(sg_ctx* ctx, sg_allreduce_fn fn, void* user, int world_size, float* buf,
+                          long long buf_floats);
+
 /* ---- measurement aid: per-operation device time (CUDA events on the launch stream) --------------- */
 /* on != 0 starts recording (and clears earlier records); every op of the plans is bracketed by two events. */
 int sg_profile_enable(sg_ctx* ctx, int on);

@@ -65,6 +65,7 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_adam_step": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _LL, _P]),
     "sg_spectral_norm_weight": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sg_spectral_norm_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "sg_set_sync_batchnorm": (_I, [_P, _P, _P, _I, _P, _LL]),
     "sg_train_step": (_I, [_P, C.POINTER(SgTrainState), _P, _P, _P, _I, _P, _P, _P, _I, _P]),
 }
 
@@ -142,6 +143,35 @@ class Context:
             ctx = cls(device, image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum)
             cls._cache[key] = ctx
         return ctx
+
+    def set_sync_batchnorm(self, group=None, enable: bool = True) -> None:
+        """Synchronised BatchNorm for data-parallel runs (include/siggan.h: sg_set_sync_batchnorm): the Generator's
+        training-mode BatchNorm sums are all-reduced over `group` (default: the world group) from inside the library
+        through a ctypes callback, on the stream the library launches on. NCCL on the GPU box; gloo works too."""
+        import torch.distributed as dist
+        if not enable or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            check(self.lib.sg_set_sync_batchnorm(self.handle, None, None, 1, None, 0), "sg_set_sync_batchnorm")
+            self._sync = None
+            return
+        buf = torch.empty(4 * 16 * 1024, dtype=torch.float32, device=self.device)   # fc BatchNorm1d: <= 16*512 channels
+        base = buf.data_ptr()
+        errors: list = []
+
+        def _allreduce(user, ptr_, count, stream) -> int:
+            try:
+                off = (int(ptr_) - base) // 4
+                if int(stream or 0) != torch.cuda.current_stream(self.device).cuda_stream:
+                    raise RuntimeError("SyncBN all-reduce must run on the stream the step was launched on")
+                dist.all_reduce(buf[off:off + int(count)], op=dist.ReduceOp.SUM, group=group)
+                return 0
+            except Exception as e:  # never let an exception cross the C frame
+                errors.append(e)
+                return -1
+
+        cb = C.CFUNCTYPE(_I, _P, _P, _LL, _P)(_allreduce)
+        check(self.lib.sg_set_sync_batchnorm(self.handle, C.cast(cb, _P), None, dist.get_world_size(group), ptr(buf),
+                                             buf.numel()), "sg_set_sync_batchnorm")
+        self._sync = (cb, buf, errors)   # keep the callback and its buffer alive as long as the library may call them
 
     def tensor_table(self, net: int) -> List[Tuple[str, int, Tuple[int, ...]]]:
         out = []

@@ -164,6 +164,12 @@ struct sg_ctx {
     float *fc_biasp, *cls_wp;
     DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
     const float* d_pack_src = nullptr;  // parameter buffer the Discriminator packs were last built from
+    // SyncBN (sg_set_sync_batchnorm): per-channel BatchNorm sums are all-reduced over the ranks through the caller's callback
+    sg_allreduce_fn sync_fn = nullptr;
+    void* sync_user = nullptr;
+    int sync_world = 1;
+    float* sync_buf = nullptr;  // caller-owned, >= 4 * (largest BatchNorm channel count) floats
+    long long sync_cap = 0;
     bool u8_only = false;  // current sg_g_forward call wants the uint8 image only (no caller-visible fp32 image)
     float *dlogit, *k1, *k2, *k3;
     int scratch_batch = 0;
@@ -273,6 +279,35 @@ int ensure_scratch(sg_ctx* c, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SyncBN: the per-CTA partial rows [chunks][2][C] of a BatchNorm reduction are folded into one row, summed over the
+// ranks by the caller's all-reduce and handed to the same finalize kernels with the global row count.
+// ------------------------------------------------------------------------------------------------
+inline bool sync_bn_on(const sg_ctx* c) { return c->sync_fn != nullptr && c->sync_world > 1; }
+
+int sync_partials(sg_ctx* c, const float*& partial, int& chunks, long& rows, int C, cudaStream_t s) {
+    if (!sync_bn_on(c)) return 0;
+    if (4LL * C > c->sync_cap) return fail("SyncBN buffer too small: %lld floats for %d channels", c->sync_cap, C);
+    sg::col_finalize(partial, chunks, C, 0, c->sync_buf, c->sync_buf + C, s);
+    SG_KCHECK("sync_partials");
+    if (c->sync_fn(c->sync_user, c->sync_buf, 2LL * C, s) != 0) return fail("SyncBN: the all-reduce callback failed");
+    partial = c->sync_buf;
+    chunks = 1;
+    rows *= c->sync_world;
+    return 0;
+}
+
+// Backward: dgamma / dbeta stay the LOCAL sums (the gradient bucket's all-reduce averages them like every other
+// parameter gradient); the coefficients of the data gradient (k2, k3 = batch means of d and d*xhat) become global.
+int sync_bn_bwd_coefficients(sg_ctx* c, const float* partial, int chunks, long rows, int C, const float* gamma,
+                             const float* rstd, const float* raw_mean, int perm_c0, cudaStream_t s) {
+    if (!sync_bn_on(c)) return 0;
+    SG_TRY(sync_partials(c, partial, chunks, rows, C, s));
+    sg::bn_bwd_finalize(partial, chunks, rows, C, gamma, rstd, raw_mean, 1, perm_c0, c->sync_buf + 2L * C,
+                        c->sync_buf + 3L * C, c->k1, c->k2, c->k3, s);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packs
 // ------------------------------------------------------------------------------------------------
 int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
@@ -364,9 +399,12 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
         if (!(kTC && fused_eval)) {
             if (train) {
                 PROF("g.fc.bn_stats", 0, es * B * (double)F0);
-                const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.fc_y), nullptr, nullptr, nullptr,
-                                                     nullptr, B, F0, static_cast<float*>(c->cpart.p), s);
-                sg::bn_finalize(static_cast<float*>(c->cpart.p), chunks, B, F0, params + c->bn[0].gamma_off,
+                int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.fc_y), nullptr, nullptr, nullptr,
+                                               nullptr, B, F0, static_cast<float*>(c->cpart.p), s);
+                const float* part = static_cast<float*>(c->cpart.p);
+                long nrows = B;
+                SG_TRY(sync_partials(c, part, chunks, nrows, F0, s));
+                sg::bn_finalize(part, chunks, nrows, F0, params + c->bn[0].gamma_off,
                                 params + c->bn[0].beta_off, stats + c->bn[0].mean_off, stats + c->bn[0].var_off,
                                 c->cfg.bn_momentum, c->cfg.bn_eps, 1, c->gch[0], w.mean[0], w.rstd[0], w.scale[0],
                                 w.shift[0], s);
@@ -423,11 +461,14 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
         if (!fuse) {
             if (train) {
                 PROF((nm + ".bn_stats").c_str(), 0, stat_chunks > 0 ? 0.0 : es * (double)rows * Cout);
-                const int chunks = stat_chunks > 0
-                                       ? stat_chunks
-                                       : sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.y[i]), nullptr, nullptr, nullptr,
-                                                           nullptr, rows, Cout, static_cast<float*>(c->cpart.p), s);
-                sg::bn_finalize(static_cast<float*>(c->cpart.p), chunks, rows, Cout, params + c->bn[i + 1].gamma_off,
+                int chunks = stat_chunks > 0
+                                 ? stat_chunks
+                                 : sg::col_reduce<T>(0, reinterpret_cast<const T*>(w.y[i]), nullptr, nullptr, nullptr,
+                                                     nullptr, rows, Cout, static_cast<float*>(c->cpart.p), s);
+                const float* part = static_cast<float*>(c->cpart.p);
+                long nrows = rows;
+                SG_TRY(sync_partials(c, part, chunks, nrows, Cout, s));
+                sg::bn_finalize(part, chunks, nrows, Cout, params + c->bn[i + 1].gamma_off,
                                 params + c->bn[i + 1].beta_off, stats + c->bn[i + 1].mean_off,
                                 stats + c->bn[i + 1].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 1, 0, w.mean[i + 1],
                                 w.rstd[i + 1], w.scale[i + 1], w.shift[i + 1], s);
@@ -492,12 +533,18 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
         if (i == L - 1) {
             sg::bn_bwd_finalize(part_bn, last_chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], w.mean[i + 1],
                                 train, 0, grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+            if (train)
+                SG_TRY(sync_bn_bwd_coefficients(c, part_bn, last_chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1],
+                                                w.mean[i + 1], 0, s));
         } else {
             PROF((nm + ".bn_bwd_reduce").c_str(), 0, 2.0 * es * (double)rows * Cout);
             const int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]),
                                                  w.mean[i + 1], w.rstd[i + 1], nullptr, rows, Cout, cpart, s);
             sg::bn_bwd_finalize(cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], nullptr, train, 0,
                                 grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+            if (train)
+                SG_TRY(sync_bn_bwd_coefficients(c, cpart, chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], nullptr,
+                                                0, s));
         }
         if (i == L - 1 && two_pass) {
             PROF((nm + ".bn_bwd_apply").c_str(), 4.0 * B * c->S * c->S * 9.0 * Cout, 2.0 * es * (double)rows * Cout);
@@ -545,6 +592,8 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
                                    w.rstd[0], nullptr, B, F0, cpart, s);
     sg::bn_bwd_finalize(cpart, chunks, B, F0, params + bn.gamma_off, w.rstd[0], nullptr, train, c->gch[0],
                         grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+    if (train)
+        SG_TRY(sync_bn_bwd_coefficients(c, cpart, chunks, B, F0, params + bn.gamma_off, w.rstd[0], nullptr, c->gch[0], s));
     sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.fc_y), w.mean[0], w.rstd[0], c->k1,
                         c->k2, c->k3, reinterpret_cast<T*>(cur), B, F0, s);
     chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr, nullptr, B, F0, cpart, s);
@@ -985,6 +1034,17 @@ int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail("sg_adam_step: bad argument");
     sg::adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_adam_step");
+    return 0;
+}
+
+int sg_set_sync_batchnorm(sg_ctx* c, sg_allreduce_fn fn, void* user, int world_size, float* buf, long long buf_floats) {
+    if (!c) return fail("sg_set_sync_batchnorm: null ctx");
+    if (fn && (world_size < 1 || !buf || buf_floats < 4)) return fail("sg_set_sync_batchnorm: bad argument");
+    c->sync_fn = fn;
+    c->sync_user = user;
+    c->sync_world = fn ? world_size : 1;
+    c->sync_buf = fn ? buf : nullptr;
+    c->sync_cap = fn ? buf_floats : 0;
     return 0;
 }
 

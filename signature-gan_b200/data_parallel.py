@@ -3,8 +3,9 @@ batch. Losses are batch means, so the global-batch gradient of everything except
 the per-rank gradients: each rank runs its local D / G backward into the flat fp32 gradient bucket of the network
 (`_siggan_lib.FlatParams.grad_staging()`), the bucket is summed over ranks with ONE all-reduce (NCCL over
 NVLink / NVSwitch on the GPU box, gloo in the CPU tests) and scaled by 1 / world_size before the fused Adam update.
-BatchNorm statistics stay local (the DDP convention; at 4096 images per replica they match the reference run at that
-batch). The reference scripts are single-process (train…:494-502); multi-GPU runs are driven by bench.py / a launcher
+BatchNorm statistics stay local by default (the DDP convention; at 4096 images per replica they match the reference
+run at that batch); `enable_sync_batchnorm` switches the Generator's BatchNorm layers to global-batch statistics, so
+that W ranks x B images reproduce ONE process at W*B images. The reference scripts are single-process (train…:494-502); multi-GPU runs are driven by bench.py / a launcher
 using these helpers with the same modules.
 """
 from __future__ import annotations
@@ -62,3 +63,13 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     base, extra = divmod(n_items, world_size)
     begin = rank * base + min(rank, extra)
     return begin, begin + base + (1 if rank < extra else 0)
+
+
+def enable_sync_batchnorm(generator, group: Optional["dist.ProcessGroup"] = None, enable: bool = True) -> None:
+    """Global-batch BatchNorm statistics for `generator` (a siggan_b200 Generator already on its CUDA device): the
+    per-channel sums of every training-mode BatchNorm forward / backward are all-reduced over `group` from inside
+    libsiggan (sg_set_sync_batchnorm; ten 2*C-float latency-bound collectives per G step). Affects every module
+    that shares the generator's library context (same device / image size / precision)."""
+    dev = next(generator.parameters()).device
+    generator._prepare(dev)
+    generator._ctx.set_sync_batchnorm(group, enable)
