@@ -139,6 +139,22 @@ typedef struct sg_train_state {
 int sg_train_step(sg_ctx* ctx, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
                   int batch, float* d_grads, float* g_grads, float* metrics_out, int phase, void* stream);
 
+/* ---- input pipeline: augmentation of a device-resident 8-bit image pool --------------- */
+/* Replaces the per-image PIL work of src/data_loader_signatures.py:154-219 `get_train_transforms` (applied in
+ * SignatureDataset.__getitem__, :120-135): RandomRotation(fill=255) -> RandomAffine(degrees=0, scale, fill=255)
+ * [-> horizontal flip] -> ToTensor -> Normalize(0.5, 0.5). Nearest-neighbour resampling on 8-bit pixels: the output
+ * is bit-identical to torchvision + Pillow for the same sampled (angle, scale, flip).
+ * sg_augment_params (HOST pointers, no GPU work): per image, Pillow's 16.16 fixed-point rotation coefficients
+ * (6 ints: a0 a1 a2 a3 a4 a5 of `affine_fixed`, half-pixel offset folded into a2 / a5) and the start / step of the
+ * scaling coordinates (4 doubles: a0, xo, a4, yo of `ImagingScaleAffine`). angles in degrees; NULL = no rotation /
+ * no scaling. */
+int sg_augment_params(const double* host_angles, const double* host_scales, int n, int image_size, int* host_rot_fixed,
+                      double* host_scale_affine);
+/* pool: (N, S, S) uint8; index: `batch` pool indices or NULL (= 0..batch-1); rot_fixed / scale_affine: device copies
+ * of the tables above; flip: `batch` bytes or NULL; out: (batch, 1, S, S) fp32 in [-1, 1]. */
+int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed, const double* scale_affine,
+                     const uint8_t* flip, int batch, int image_size, float* out, void* stream);
+
 /* ---- synchronised BatchNorm for data-parallel runs ------------------------------- */
 /* With a callback set, every training-mode BatchNorm of the Generator (gen…:58,126) normalises with the statistics of
  * the GLOBAL batch: the per-channel sums (sum x, sum x^2 in forward; sum d, sum d*xhat in backward; 2*C floats) are

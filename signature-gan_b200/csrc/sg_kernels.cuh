@@ -157,6 +157,11 @@ void spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, int
 void spectral_norm_backward(const float* w_eff, const float* u, const float* v, const float* sigma, int rows, int cols,
                             float* grad, float* scratch, cudaStream_t s);
 
+// ---- input-pipeline augmentation on a device-resident uint8 pool (sg_augment.cu) --------------------
+int augment_batch(const uint8_t* pool, const int* index, const int* rot, const double* sc, const uint8_t* flip, int batch,
+                  int size, float* out, cudaStream_t s);
+void augment_params(const double* angles, const double* scales, int n, int size, int* rot, double* sc);  // host only
+
 int kernels_check(const char* what);  // cudaGetLastError -> 0 / -1 (message kept)
 
 }  // namespace sg

@@ -1037,6 +1037,25 @@ int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     return 0;
 }
 
+int sg_augment_params(const double* host_angles, const double* host_scales, int n, int image_size, int* host_rot_fixed,
+                      double* host_scale_affine) {
+    if (n < 0 || !host_rot_fixed || !host_scale_affine || (image_size != 64 && image_size != 128))
+        return fail("sg_augment_params: bad argument");
+    sg::augment_params(host_angles, host_scales, n, image_size, host_rot_fixed, host_scale_affine);
+    return 0;
+}
+int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed, const double* scale_affine,
+                     const uint8_t* flip, int batch, int image_size, float* out, void* stream) {
+    if (!pool || !rot_fixed || !scale_affine || !out || batch < 1) return fail("sg_augment_batch: bad argument");
+    if (image_size != 64 && image_size != 128)
+        return fail("sg_augment_batch: image_size must be 64 or 128, got %d", image_size);
+    if ((reinterpret_cast<uintptr_t>(pool) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return fail("sg_augment_batch: pool and out must be 16-byte aligned");
+    sg::augment_batch(pool, index, rot_fixed, scale_affine, flip, batch, image_size, out, static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_augment_batch");
+    return 0;
+}
+
 int sg_set_sync_batchnorm(sg_ctx* c, sg_allreduce_fn fn, void* user, int world_size, float* buf, long long buf_floats) {
     if (!c) return fail("sg_set_sync_batchnorm: null ctx");
     if (fn && (world_size < 1 || !buf || buf_floats < 4)) return fail("sg_set_sync_batchnorm: bad argument");
