@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--sampling-batch", type=int, default=16384)
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / cpu baseline / per-op profile")
+    ap.add_argument("--sync-bn", action="store_true", help="N > 1: global-batch BatchNorm statistics (sg_set_sync_batchnorm)")
     return ap.parse_args()
 
 
@@ -178,6 +179,84 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# input pipeline: DeviceSignatureLoader (sg_augment_batch) next to the reference's PIL / torchvision transforms
+# ------------------------------------------------------------------------------------------------
+def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu):
+    """Augmented batches of B images from an 8-bit pool in HBM: kernel alone (CUDA events; 1 byte read + 4 bytes
+    written per pixel against the measured HBM peak) and through the loader (host parameter sampling +
+    sg_augment_params + one 56 B/image upload + kernel). CPU side: the reference's own transform stack
+    (data_loader_signatures.py:154-219: torchvision on PIL images), one process, bounded sample."""
+    import numpy as np
+    import torch
+    from device_data_loader import DeviceSignatureLoader
+    imgs = ((pool_f32.reshape(-1, S, S) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    ld = DeviceSignatureLoader(imgs, batch_size=B, device=dev, seed=5)
+    n = imgs.shape[0]
+    idx = torch.randperm(n, device=dev)[:B].to(torch.int32)
+    angles, scales, _ = ld.sample_params(B)
+    for _ in range(3):
+        ld.batch(idx, angles, scales)
+    torch.cuda.synchronize()
+    # kernel alone: same tables every launch, the 80 MB it touches per launch are swept out of L2 by a 256 MB write
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    lib, cur = ld.lib, torch.cuda.current_stream(dev).cuda_stream
+    import ctypes as C
+    rot = np.empty((B, 6), np.int32)
+    sc = np.empty((B, 4), np.float64)
+    lib.sg_augment_params(angles.ctypes.data, scales.ctypes.data, B, S, rot.ctypes.data, sc.ctypes.data)
+    rot_d, sc_d = torch.from_numpy(rot).to(dev), torch.from_numpy(sc).to(dev)
+    out = torch.empty(B, 1, S, S, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, iters = 0.0, 10
+    for _ in range(iters):
+        flush.zero_()
+        e0.record()
+        rc = lib.sg_augment_batch(imgs.data_ptr(), idx.data_ptr(), rot_d.data_ptr(), sc_d.data_ptr(), None, B, S,
+                                  out.data_ptr(), cur)
+        e1.record()
+        torch.cuda.synchronize()
+        assert rc == 0
+        ms += e0.elapsed_time(e1)
+    ms /= iters
+    gbs = 5.0 * S * S * B / (ms * 1e-3) / 1e9
+    # through the loader
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        ld.batch(idx)
+    torch.cuda.synchronize()
+    loader_ips = B * reps / (time.perf_counter() - t0)
+    res = {"kernel": "sg_augment_batch", "batch": B, "ms_per_batch": ms, "images_per_s_kernel": B / (ms * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                        "bytes_per_image": 5 * S * S, "l2": "256 MB flush between launches"},
+           "images_per_s_loader": loader_ips,
+           "loader_api": "DeviceSignatureLoader.batch(index): host sampling + sg_augment_params + 56 B/image H2D + kernel"}
+    if measure_cpu:
+        try:
+            from PIL import Image
+            from torchvision import transforms
+            tf = transforms.Compose([transforms.Resize((S, S)), transforms.RandomRotation(degrees=5.0, fill=255),
+                                     transforms.RandomAffine(degrees=0, scale=(0.9, 1.1), fill=255),
+                                     transforms.ToTensor(), transforms.Normalize(mean=[0.5], std=[0.5])])
+            host = imgs[:512].cpu().numpy()
+            pils = [Image.fromarray(h) for h in host]
+            t0 = time.perf_counter()
+            count = 0
+            while time.perf_counter() - t0 < 5.0:
+                for pimg in pils:
+                    tf(pimg)
+                count += len(pils)
+            res["cpu_baseline"] = {"value": count / (time.perf_counter() - t0), "unit": "images/s", "cores": 1,
+                                   "kind": "reference",
+                                   "sample": "torchvision/PIL transform stack of get_train_transforms on decoded 8-bit "
+                                             f"{S}x{S} images, one process, ~5 s (the reference runs 4 such workers)"}
+        except Exception as e:  # torchvision / PIL missing on the box
+            res["cpu_baseline"] = {"unavailable": str(e)[:120]}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
@@ -198,6 +277,10 @@ def run_ours(args, rank, local_rank, world):
     gan._fused_ready()
     from data_parallel import broadcast_replica_
     broadcast_replica_([gan.generator._flat.flat, gan.generator._flat.stats, gan.discriminator._flat.flat])  # identical replicas
+    sync_bn = bool(args.sync_bn and world > 1)
+    if sync_bn:
+        from data_parallel import enable_sync_batchnorm
+        enable_sync_batchnorm(gan.generator)
     lib = L.load_library()
     n_pool = 4     # 4 distinct real batches (268 MB fp32 at B=4096) > 126 MB L2; activations per step are several GB
     pool = synthetic_signatures(n_pool * B, S, dev, seed=1234 + rank).view(n_pool, B, 1, S, S)
@@ -263,7 +346,7 @@ def run_ours(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"train_step_{S}x{S}_b{B}_per_gpu", "global_batch": world * B, "image_size": S,
-                   "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1,
+                   "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1, "sync_bn": sync_bn,
                    "l2": "4 rotating real batches (268 MB) and multi-GB per-step activations exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": 48,
                 "steps": e2e_steps, "api": "VanillaGAN.train_step(real) from pinned host batches, double-buffered H2D"},
@@ -371,6 +454,9 @@ def run_ours(args, rank, local_rank, world):
                                 "e2e_images_per_s_uint8_host": samp_e2e,
                                 "e2e_bytes": {"h2d": SB * 400, "d2h": SB * S * S},
                                 "e2e_api": "Generator.sample_uint8_to_host (8 chunks, double-buffered D2H)"}
+        # ---- input pipeline: augmentation kernel over a device-resident uint8 pool ------
+        if rank == 0:
+            line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1))
         # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------
         if rank == 0 and world == 1:
             steps_cpu = 12

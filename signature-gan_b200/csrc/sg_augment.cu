@@ -27,8 +27,15 @@
 namespace sg {
 namespace {
 
-constexpr int kAugThreads = 256;
+constexpr int kAugWorkers = 256;              // threads that move pixels
+constexpr int kAugThreads = kAugWorkers + 32;  // + one warp that only builds the scaling coordinate tables
 
+// What the ncu captures showed (profiles/r01_ncu_augment.txt): the first version had every thread k < 2S rebuild table
+// entry k with k dependent double additions — 4096 DADD per 64x64 image — and sat on the FP64 pipe (31 us per 4096
+// images); with the chains moved to two lanes of a ninth warp it was issue-bound at 37 thread-instructions per pixel
+// (28 us), most of them spent on the intermediate rotated tile. The two resamplings are now COMPOSED per output pixel —
+// (y, x) -> scaled source (yt[y], xt[x]) -> its fixed-point rotation source — which is the same function, needs no
+// second tile and no second barrier, and keeps the per-column products xt[x]*a0, xt[x]*a3 in registers.
 template <int S>
 __global__ void __launch_bounds__(kAugThreads) augment_kernel(const uint8_t* __restrict__ pool,
                                                               const int* __restrict__ index,
@@ -36,53 +43,76 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const uint8_t* __r
                                                               const double* __restrict__ sc,
                                                               const uint8_t* __restrict__ flip, int batch,
                                                               float* __restrict__ out) {
+    constexpr int QPR = S / 4;                   // quads (4 pixels) per row
+    constexpr int RSTEP = kAugWorkers / QPR;     // rows between two consecutive quads of one thread
+    constexpr int NQ = S * S / 4 / kAugWorkers;  // quads per thread per image
     __shared__ __align__(16) uint8_t src[S * S];
-    __shared__ __align__(16) uint8_t rotd[S * S];
     __shared__ float lut[256];
     __shared__ short xt[S], yt[S];
+    __shared__ int coef[8];
     const int tid = threadIdx.x;
+    const bool worker = tid < kAugWorkers;
     // ToTensor + Normalize of every possible 8-bit value, with IEEE division (no reciprocal shortcuts)
-    lut[tid] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(tid), 255.0f), 0.5f), 0.5f);
+    if (worker) lut[tid] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(tid), 255.0f), 0.5f), 0.5f);
+    const int qx = (tid % QPR) * 4, qy = tid / QPR;  // this worker's quad column / first row
     for (int img = blockIdx.x; img < batch; img += gridDim.x) {
-        const long long src_img = index ? index[img] : img;
-        const uint4* g = reinterpret_cast<const uint4*>(pool + src_img * (S * S));
-        for (int i = tid; i < S * S / 16; i += kAugThreads) reinterpret_cast<uint4*>(src)[i] = __ldg(g + i);
-        // coordinate tables of the scaling step: entry k is the start value advanced k times by `o += a` in double,
-        // exactly the sequence Pillow's serial loop goes through (thread k repeats the first k additions)
-        if (tid < 2 * S) {
-            const int k = tid % S, which = tid / S;  // 0: columns (a0, xo), 1: rows (a4, yo)
-            const double a = sc[img * 4 + 2 * which];
-            double o = sc[img * 4 + 2 * which + 1];
-            for (int j = 0; j < k; ++j) o += a;
-            int v = o < 0.0 ? -1 : static_cast<int>(o);
-            if (v >= S) v = -1;
-            (which ? yt : xt)[k] = static_cast<short>(v);
+        if (worker) {
+            const long long src_img = index ? index[img] : img;
+            const uint4* g = reinterpret_cast<const uint4*>(pool + src_img * (S * S));
+#pragma unroll
+            for (int i = 0; i < S * S / 16 / kAugWorkers; ++i)
+                reinterpret_cast<uint4*>(src)[tid + i * kAugWorkers] = __ldg(g + tid + i * kAugWorkers);
+        } else {
+            const int lane = tid - kAugWorkers;
+            if (lane < 2) {
+                // scaling coordinates: the start value advanced by `o += a` in double once per output column / row — the
+                // very sequence of roundings Pillow's serial loop produces; COORD(v) = v < 0 ? -1 : (int)v, -1 for v >= S
+                const double a = sc[img * 4 + 2 * lane];  // lane 0: columns (a0, xo), lane 1: rows (a4, yo)
+                double o = sc[img * 4 + 2 * lane + 1];
+                short* tab = lane ? yt : xt;
+                for (int k = 0; k < S; ++k) {
+                    int v = o < 0.0 ? -1 : static_cast<int>(o);
+                    if (v >= S) v = -1;
+                    tab[k] = static_cast<short>(v);
+                    o += a;
+                }
+            } else if (lane < 8) {
+                coef[lane - 2] = rot[img * 6 + lane - 2];
+            } else if (lane == 8) {
+                coef[6] = (flip && flip[img]) ? 1 : 0;
+            }
         }
-        const int a0 = rot[img * 6 + 0], a1 = rot[img * 6 + 1], a2 = rot[img * 6 + 2];
-        const int a3 = rot[img * 6 + 3], a4 = rot[img * 6 + 4], a5 = rot[img * 6 + 5];
-        const bool fl = flip && flip[img];
         __syncthreads();
-        for (int p = tid; p < S * S; p += kAugThreads) {
-            const int y = p / S, x = p % S;
-            const int xin = (a2 + y * a1 + x * a0) >> 16;
-            const int yin = (a5 + y * a4 + x * a3) >> 16;
-            const bool ok = xin >= 0 && xin < S && yin >= 0 && yin < S;
-            rotd[p] = ok ? src[yin * S + xin] : static_cast<uint8_t>(255);
-        }
-        __syncthreads();
-        float4* o4 = reinterpret_cast<float4*>(out + static_cast<long long>(img) * (S * S));
-        for (int q = tid; q < S * S / 4; q += kAugThreads) {
-            const int y = q / (S / 4), x = (q % (S / 4)) * 4;
-            const int yi = yt[y];
-            float v[4];
+        if (worker) {
+            // Pillow affine_fixed: source = ((a5 + y*a4 + x*a3) >> 16, (a2 + y*a1 + x*a0) >> 16), 32-bit integers
+            const int a0 = coef[0], a1 = coef[1], a2 = coef[2], a3 = coef[3], a4 = coef[4], a5 = coef[5];
+            const bool fl = coef[6] != 0;
+            int cx0[4], cx3[4];
+            bool xok[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int xi = xt[fl ? S - 1 - (x + j) : x + j];
-                v[j] = lut[(yi >= 0 && xi >= 0) ? rotd[yi * S + xi] : 255];
+                const int xi = xt[fl ? S - 1 - (qx + j) : qx + j];
+                xok[j] = xi >= 0;
+                cx0[j] = xi * a0;
+                cx3[j] = xi * a3;
             }
-            o4[q] = make_float4(v[0], v[1], v[2], v[3]);
+            float4* o4 = reinterpret_cast<float4*>(out + static_cast<long long>(img) * (S * S)) + tid;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const int yi = yt[qy + i * RSTEP];
+                const int bx = a2 + yi * a1, by = a5 + yi * a4;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned xin = static_cast<unsigned>((bx + cx0[j]) >> 16);
+                    const unsigned yin = static_cast<unsigned>((by + cx3[j]) >> 16);
+                    const bool ok = xok[j] && yi >= 0 && xin < S && yin < S;
+                    v[j] = ok ? lut[src[yin * S + xin]] : 1.0f;  // fill = 255 -> (255/255 - 0.5) / 0.5 = 1
+                }
+                o4[i * kAugWorkers] = make_float4(v[0], v[1], v[2], v[3]);
+            }
         }
-        __syncthreads();  // src / rotd / tables are rewritten by the next image
+        __syncthreads();  // src / tables / coefficients are rewritten by the next image
     }
 }
 
@@ -110,7 +140,7 @@ int augment_batch(const uint8_t* pool, const int* index, const int* rot, const d
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const int per_sm = size == 64 ? 8 : 4;  // 9 KB / 33 KB of shared memory per CTA
+    const int per_sm = 5;  // resident CTAs per SM (288 threads x 40 registers): one wave, every CTA strides over the batch
     int grid = sms * per_sm;
     if (grid > batch) grid = batch;
     note_launch();
@@ -142,7 +172,10 @@ void augment_params(const double* angles, const double* scales, int n, int size,
             r[0] = 0; r[1] = one; r[2] = one / 2; r[3] = -one; r[4] = 0; r[5] = size * one - one / 2;
         } else {
             const double a = -(ang * (M_PI / 180.0));  // -math.radians(angle)
-            double m[6] = {round15(std::cos(a)), round15(std::sin(a)), 0.0, round15(-std::sin(a)), round15(std::cos(a)), 0.0};
+            // round(cos, 15), round(sin, 15), round(-sin, 15), round(cos, 15): decimal rounding is symmetric, so two
+            // conversions serve the four entries (they dominate this function's time)
+            const double rc = round15(std::cos(a)), rs = round15(std::sin(a));
+            double m[6] = {rc, rs, 0.0, -rs, rc, 0.0};
             m[2] = m[0] * (-c0) + m[1] * (-c0) + m[2];
             m[5] = m[3] * (-c0) + m[4] * (-c0) + m[5];
             m[2] += c0;

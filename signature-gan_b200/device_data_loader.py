@@ -66,9 +66,21 @@ class DeviceSignatureLoader:
         n = self.pool.shape[0]
         order = (torch.randperm(n, device=self.device, generator=self._gen) if self.shuffle
                  else torch.arange(n, device=self.device)).to(torch.int32)
-        for b in range(len(self)):
-            idx = order[b * self.batch_size:(b + 1) * self.batch_size]
-            yield self.batch(idx)
+        nb = len(self)
+        if nb == 0:
+            return
+        sizes = [min(self.batch_size, n - b * self.batch_size) for b in range(nb)]
+        # the host side of batch b+1 (parameter sampling + sg_augment_params, which releases the GIL) runs on a helper
+        # thread while the consumer trains on batch b
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(self._host_tables, sizes[0])
+            for b in range(nb):
+                tables = pending.result()
+                if b + 1 < nb:
+                    pending = pool.submit(self._host_tables, sizes[b + 1])
+                idx = order[b * self.batch_size:b * self.batch_size + sizes[b]]
+                yield self._launch(idx, *tables)
 
     # -- one batch ------------------------------------------------------------------------------------
     def sample_params(self, n: int) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
@@ -88,27 +100,33 @@ class DeviceSignatureLoader:
         """Augmented batch of the pool images `index` (int32 CUDA tensor). angles / scales / flips override the
         sampled parameters (parity tests inject the values the reference's transforms drew)."""
         n = int(index.numel())
+        return self._launch(index, *self._host_tables(n, angles, scales, flips))
+
+    def _host_tables(self, n: int, angles=None, scales=None, flips=None) -> Tuple[torch.Tensor, int, int, bool]:
+        """Pinned staging block [rot_fixed int32 n*6 | scale_affine float64 n*4 | flip uint8 n] for one batch."""
         if angles is None and scales is None and flips is None:
             angles, scales, flips = self.sample_params(n)
         angles = np.ascontiguousarray(np.zeros(n) if angles is None else angles, dtype=np.float64)
         scales = np.ascontiguousarray(np.ones(n) if scales is None else scales, dtype=np.float64)
         if angles.shape != (n,) or scales.shape != (n,):
             raise ValueError("angles / scales must have one entry per image")
-        S = self.image_size
-        # one pinned staging block: [rot_fixed int32 n*6 | scale_affine float64 n*4 | flip uint8 n] -> one H2D copy
         rot_bytes, sc_bytes = n * 24, n * 32
         host = torch.empty(rot_bytes + sc_bytes + n, dtype=torch.uint8).pin_memory()
         base = host.data_ptr()
-        L.check(self.lib.sg_augment_params(angles.ctypes.data, scales.ctypes.data, n, S, base, base + rot_bytes),
-                "sg_augment_params")
+        L.check(self.lib.sg_augment_params(angles.ctypes.data, scales.ctypes.data, n, self.image_size, base,
+                                           base + rot_bytes), "sg_augment_params")
         if flips is not None:
             host[rot_bytes + sc_bytes:] = torch.as_tensor(np.ascontiguousarray(flips, dtype=np.uint8))
-        dev = host.to(self.device, non_blocking=True)
+        return host, rot_bytes, sc_bytes, flips is not None
+
+    def _launch(self, index: torch.Tensor, host: torch.Tensor, rot_bytes: int, sc_bytes: int, has_flip: bool) -> torch.Tensor:
+        n, S = int(index.numel()), self.image_size
+        dev = host.to(self.device, non_blocking=True)     # one H2D copy: 56 (57) bytes per image
         out = torch.empty(n, 1, S, S, dtype=torch.float32, device=self.device)
         index = index.to(device=self.device, dtype=torch.int32).contiguous()
         d0 = dev.data_ptr()
         L.check(self.lib.sg_augment_batch(L.ptr(self.pool), L.ptr(index), d0, d0 + rot_bytes,
-                                          d0 + rot_bytes + sc_bytes if flips is not None else None, n, S, L.ptr(out),
+                                          d0 + rot_bytes + sc_bytes if has_flip else None, n, S, L.ptr(out),
                                           L.current_stream(self.device)), "sg_augment_batch")
         # `dev` and `host` may be released now: both allocators are stream-ordered (the caching host allocator tracks the
         # pending non-blocking copy, the device block is only reused by work enqueued after the kernel on this stream)
