@@ -175,7 +175,7 @@ def run_reference(args, rank):
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -465,16 +465,29 @@ def run_ours(args, rank, local_rank, world):
                                     "sample": f"{steps_cpu} D+G steps of batch {args.cpu_batch} ({S}x{S}), torch CPU fp32, "
                                               f"{os.cpu_count()} logical cpus"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+RESULT_OUT = sys.stdout
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line. Libraries write to the C-level stdout behind Python's back (NCCL prints
+    its version banner there under NCCL_DEBUG=VERSION — setting NCCL_DEBUG_FILE did not stop it on the box), so the
+    process keeps a private duplicate of the original stdout for the result line and points fd 1 at stderr for
+    everything else."""
+    global RESULT_OUT
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    RESULT_OUT = os.fdopen(saved, "w")
+
+
 def main():
-    # stdout carries exactly one JSON line: NCCL's own messages (e.g. its version banner under NCCL_DEBUG=VERSION) go to
-    # stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    claim_stdout()
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -486,7 +499,7 @@ def main():
         # launched without torchrun: re-exec under the launcher so that there is one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=RESULT_OUT))   # the ranks write their line to OUR original stdout
     run_ours(args, rank, local_rank, world)
 
 
