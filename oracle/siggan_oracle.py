@@ -268,6 +268,52 @@ def d_backward_sn(cache: Dict[str, Tensor], dprob: Tensor, image_size: int = 64,
     return out
 
 
+def sn_trainable_names(sd: Dict[str, Tensor]) -> List[str]:
+    return [k for k in sd if k.endswith(".bias") or k.endswith(".weight_orig")]
+
+
+def d_step_sn(g_sd, d_sd, d_opt: "AdamState", real: Tensor, noise: Tensor, image_size: int = 64,
+              masks_real=None, masks_fake=None, label_smoothing: float = 0.9, lr: float = 2e-4,
+              b1: float = 0.5, b2: float = 0.999, apply_update: bool = True):
+    """vanilla…:180-252 with VanillaGAN(use_spectral_norm=True): D.train -> BOTH forwards run a power iteration (the
+    second starts from the buffers the first left), each backward uses its own forward's (u, v, sigma)."""
+    p_real, c_real, buf = d_forward_sn(d_sd, real, image_size, masks_real, train=True)
+    d_sd.update(buf)
+    fake, _, _ = g_forward(g_sd, noise, image_size, train=False)
+    p_fake, c_fake, buf = d_forward_sn(d_sd, fake, image_size, masks_fake, train=True)
+    d_sd.update(buf)
+    t_real = torch.full_like(p_real, label_smoothing)
+    loss_real, loss_fake = bce(p_real, t_real), bce(p_fake, torch.zeros_like(p_fake))
+    g_real = d_backward_sn(c_real, bce_grad(p_real, t_real), image_size, masks_real)
+    g_fake = d_backward_sn(c_fake, bce_grad(p_fake, torch.zeros_like(p_fake)), image_size, masks_fake)
+    grads = {k: g_real[k] + g_fake[k] for k in g_real}
+    if apply_update:
+        d_opt.apply(d_sd, grads, lr, b1, b2)
+    metrics = {
+        "d_loss": float(loss_real + loss_fake), "d_loss_real": float(loss_real), "d_loss_fake": float(loss_fake),
+        "d_real_acc": float((p_real > 0.5).float().mean()), "d_fake_acc": float((p_fake < 0.5).float().mean()),
+        "d_real_mean": float(p_real.mean()), "d_fake_mean": float(p_fake.mean()),
+    }
+    return metrics, grads
+
+
+def g_step_sn(g_sd, d_sd, g_opt: "AdamState", noise: Tensor, image_size: int = 64, lr: float = 2e-4,
+              b1: float = 0.5, b2: float = 0.999, apply_update: bool = True):
+    """vanilla…:254-306 with the SN discriminator in eval mode: no power iteration, sigma from the stored u, v."""
+    fake, gc, new_stats = g_forward(g_sd, noise, image_size, train=True)
+    p, dc, _ = d_forward_sn(d_sd, fake, image_size, None, train=False)
+    ones = torch.ones_like(p)
+    loss = bce(p, ones)
+    dg = d_backward(dc["__eff"], dc, bce_grad(p, ones), image_size, None, need_dx=True)
+    grads = g_backward(g_sd, gc, dg["__dx"], image_size, train=True)
+    grads.pop("__dz")
+    for k, v in new_stats.items():
+        g_sd[k] = v
+    if apply_update:
+        g_opt.apply(g_sd, grads, lr, b1, b2)
+    return {"g_loss": float(loss), "g_fake_mean": float(p.mean())}, grads
+
+
 def make_sn_state_dict(image_size: int = 64, seed: int = 0) -> Dict[str, Tensor]:
     """SN-variant state dict in the reference's key order: kaiming-scale weight_orig (the reference's DCGAN init
     does not reach weight_orig, disc…:212-239 initialises the derived `weight`), unit-norm u / v."""

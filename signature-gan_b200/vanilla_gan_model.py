@@ -254,8 +254,68 @@ class VanillaGAN(nn.Module):
         from data_parallel import average_gradients_
         average_gradients_(flat_grad)
 
+    # -- spectral-norm variant: the same two steps through the module path -----------------------------------
+    # sg_train_step runs the Discriminator on its raw parameters; with use_spectral_norm the layers must run on
+    # weight_orig / sigma with a power iteration per forward (disc…:61-62, 201-202), which the Discriminator module does
+    # (sg_spectral_norm_weight / _backward around sg_d_forward / sg_d_backward). The steps below are the reference's own
+    # statements (vanilla…:203-252, 273-306) on those modules; metrics stay on the device.
+    def _grad_allreduce(self, module: nn.Module) -> None:
+        import data_parallel as dp
+        if dp.world()[1] > 1:
+            flat = module._flat.flat_grad_if_contiguous()
+            for g in ([flat] if flat is not None else [p.grad for p in module.parameters()]):
+                dp.average_gradients_(g)
+
+    def _layered_discriminator_step(self, real_images: torch.Tensor, noise: Optional[torch.Tensor]) -> torch.Tensor:
+        D, G = self.discriminator, self.generator
+        D.train()
+        G.eval()
+        self._fused_ready()
+        dev = G._flat.flat.device
+        real = real_images.to(dev, non_blocking=True).contiguous().float()
+        B = real.shape[0]
+        noise = torch.randn(B, self.latent_dim, device=dev) if noise is None else noise.to(dev).contiguous().float()
+        self.d_optimizer.zero_grad()
+        masks = self.mask_override
+        D.mask_override = masks["real"] if masks is not None else None
+        real_preds = D(real)
+        d_loss_real = self.criterion(real_preds, self._get_labels(B, real=True, smooth=True))
+        with torch.no_grad():
+            fake = G(noise)
+        D.mask_override = masks["fake"] if masks is not None else None
+        fake_preds = D(fake)
+        D.mask_override = None
+        d_loss_fake = self.criterion(fake_preds, self._get_labels(B, real=False))
+        d_loss = d_loss_real + d_loss_fake
+        d_loss.backward()
+        self._grad_allreduce(D)
+        self.d_optimizer.step()
+        with torch.no_grad():
+            self._metrics[:7] = torch.stack([d_loss, d_loss_real, d_loss_fake, (real_preds > 0.5).float().mean(),
+                                             (fake_preds < 0.5).float().mean(), real_preds.mean(), fake_preds.mean()])
+        return self._metrics
+
+    def _layered_generator_step(self, batch_size: int, noise: Optional[torch.Tensor]) -> torch.Tensor:
+        D, G = self.discriminator, self.generator
+        G.train()
+        D.eval()
+        self._fused_ready()
+        dev = G._flat.flat.device
+        noise = torch.randn(batch_size, self.latent_dim, device=dev) if noise is None else noise.to(dev).contiguous().float()
+        self.g_optimizer.zero_grad()
+        fake_preds = D(G(noise))
+        g_loss = self.criterion(fake_preds, self._get_labels(noise.shape[0], real=True, smooth=False))
+        g_loss.backward()
+        self._grad_allreduce(G)
+        self.g_optimizer.step()
+        with torch.no_grad():
+            self._metrics[7:9] = torch.stack([g_loss, fake_preds.mean()])
+        return self._metrics
+
     def discriminator_step_async(self, real_images: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Enqueue one D step (reference vanilla…:180-252) without synchronising; metrics stay on the device."""
+        if self.use_spectral_norm:
+            return self._layered_discriminator_step(real_images, noise)
         self.discriminator.train()
         self.generator.eval()
         sctx = self._fused_ready()
@@ -291,6 +351,8 @@ class VanillaGAN(nn.Module):
 
     def generator_step_async(self, batch_size: int, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Enqueue one G step (reference vanilla…:254-306) without synchronising."""
+        if self.use_spectral_norm:
+            return self._layered_generator_step(batch_size, noise)
         self.generator.train()
         self.discriminator.eval()
         sctx = self._fused_ready()

@@ -58,6 +58,45 @@ def main(size: int = 64, B: int = 4):
     print(f"sn_{size}.pt: {len(out)} entries; prob={p1.detach().flatten().tolist()} loss={float(loss):.6f}")
 
 
+
+
+def make_sn_steps(size: int = 64, B: int = 4, steps: int = 2):
+    """The reference's VanillaGAN(use_spectral_norm=True) through train_discriminator_step / train_generator_step
+    (vanilla…:180-306) with injected noise and captured dropout masks -> tests/golden/sn_steps_64.pt."""
+    from vanilla_gan_model import VanillaGAN
+    g_sd, _ = O.make_state_dicts(size, 100, seed=6)
+    d_sd = O.make_sn_state_dict(size, seed=6)
+    gan = VanillaGAN(latent_dim=100, image_size=size, use_spectral_norm=True, device="cpu")
+    gan.generator.load_state_dict(g_sd)
+    gan.discriminator.load_state_dict(d_sd)
+    out = {"size": size, "B": B, "steps": steps, "metrics": [], "masks": []}
+    torch.manual_seed(55)
+    for s in range(steps):
+        real = O.synthetic_signatures(B, size, seed=400 + s)
+        nd, ng = O.hash_normal((B, 100), 500 + s), O.hash_normal((B, 100), 600 + s)
+        rec, hooks = capture_dropout(gan.discriminator)
+        md = gan.train_discriminator_step(real, noise=nd)
+        for h in hooks:
+            h.remove()
+        nblk = len(gan.discriminator.conv_blocks)
+        out["masks"].append({"real": [m.clone() for m in rec[:nblk]], "fake": [m.clone() for m in rec[nblk:]]})
+        for k, p in gan.discriminator.named_parameters():
+            out[f"s{s}.d_grad.{k}"] = probe(p.grad)
+            out[f"s{s}.d_param.{k}"] = probe(p)
+        for k, v in gan.discriminator.state_dict().items():
+            if k.endswith(("weight_u", "weight_v")):
+                out[f"s{s}.d_buf.{k}"] = v.clone()
+        mg = gan.train_generator_step(B, noise=ng)
+        for k, p in gan.generator.named_parameters():
+            out[f"s{s}.g_grad.{k}"] = probe(p.grad)
+            out[f"s{s}.g_param.{k}"] = probe(p)
+        md.update(mg)
+        out["metrics"].append(md)
+    torch.save(out, os.path.join(HERE, f"sn_steps_{size}.pt"))
+    print(f"sn_steps_{size}.pt: {len(out)} entries; metrics[0]={out['metrics'][0]}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     main()
+    make_sn_steps()

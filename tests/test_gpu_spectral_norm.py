@@ -122,3 +122,50 @@ def test_spectral_norm_trains_with_stock_adam():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vanilla_gan_with_spectral_norm_trains_like_the_reference(golden_dir, precision):
+    """VanillaGAN(use_spectral_norm=True) (vanilla…:70-103): train_discriminator_step / train_generator_step must run the
+    SN discriminator (power iteration per forward, weight_orig / sigma), not the raw-parameter fused step — checked
+    against the oracle's d_step_sn / g_step_sn and the metrics of the unmodified reference (sn_steps_64.pt)."""
+    from vanilla_gan_model import VanillaGAN
+    gold = torch.load(os.path.join(golden_dir, "sn_steps_64.pt"), weights_only=False)
+    size, B = gold["size"], gold["B"]
+    g_sd, _ = O.make_state_dicts(size, 100, seed=6)
+    d_sd = O.make_sn_state_dict(size, seed=6)
+    gan = VanillaGAN(latent_dim=100, image_size=size, use_spectral_norm=True, device="cuda")
+    gan.generator.set_precision(precision)
+    gan.discriminator.set_precision(precision)
+    gan.generator.load_state_dict(g_sd)
+    gan.discriminator.load_state_dict(d_sd)
+    assert gan.get_config()["use_spectral_norm"] is True
+    g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
+    d_opt = O.AdamState(d_sd, O.sn_trainable_names(d_sd))
+    for s in range(gold["steps"]):
+        real = O.synthetic_signatures(B, size, seed=400 + s)
+        nd, ng = O.hash_normal((B, 100), 500 + s), O.hash_normal((B, 100), 600 + s)
+        mk = gold["masks"][s]
+        gan.mask_override = mk
+        md = gan.train_discriminator_step(real.cuda(), noise=nd.cuda())
+        mg = gan.train_generator_step(B, noise=ng.cuda())
+        od, _ = O.d_step_sn(g_sd, d_sd, d_opt, real, nd, size, mk["real"], mk["fake"])
+        og, _ = O.g_step_sn(g_sd, d_sd, g_opt, ng, size)
+        mtol = 2e-4 if precision == "fp32" else 2e-2
+        for k, v in {**od, **og}.items():
+            got = {**md, **mg}[k]
+            assert abs(got - v) <= mtol * max(1.0, abs(v)) + (0.26 if k.endswith("acc") else 0), (s, k, got, v)
+            assert abs(got - gold["metrics"][s][k]) <= mtol * max(1.0, abs(v)) + (0.26 if k.endswith("acc") else 0), (s, k)
+        got_d = gan.discriminator.state_dict()
+        for k, v in d_sd.items():
+            kind = 1e-5 if k.endswith(("weight_u", "weight_v")) and precision == "fp32" else tol(precision, "param")
+            assert rel_err(got_d[k], v) <= max(kind, 1e-5), (s, k, rel_err(got_d[k], v))
+        got_g = gan.generator.state_dict()
+        for k in O.trainable_names(g_sd):
+            if k != "fc.0.bias":
+                assert rel_err(got_g[k], g_sd[k]) <= tol(precision, "param"), (s, k, rel_err(got_g[k], g_sd[k]))
+    # train_step (D step + G step) goes the same way and keeps the reference's keys
+    out = gan.train_step(O.synthetic_signatures(B, size, seed=3).cuda())
+    assert set(out) == {"d_loss", "d_loss_real", "d_loss_fake", "d_real_acc", "d_fake_acc", "d_real_mean", "d_fake_mean",
+                        "g_loss", "g_fake_mean"}
+    assert all(v == v for v in out.values())

@@ -152,3 +152,33 @@ def test_spectral_norm_variant_matches_reference(golden_dir):
     check_probe("eval.feat", ce["feat"], gold["eval.feat"])
     for k, v in buf3.items():
         assert torch.equal(v, sd3[k]), f"{k}: eval mode must not iterate"
+
+
+def test_spectral_norm_training_steps_match_reference(golden_dir):
+    """VanillaGAN(use_spectral_norm=True).train_discriminator_step / train_generator_step (vanilla…:180-306) of the
+    unmodified reference vs the oracle's d_step_sn / g_step_sn (tests/golden/sn_steps_64.pt)."""
+    gold = torch.load(os.path.join(golden_dir, "sn_steps_64.pt"), weights_only=False)
+    size, B = gold["size"], gold["B"]
+    g_sd, _ = O.make_state_dicts(size, 100, seed=6)
+    d_sd = O.make_sn_state_dict(size, seed=6)
+    g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
+    d_opt = O.AdamState(d_sd, O.sn_trainable_names(d_sd))
+    for s in range(gold["steps"]):
+        real = O.synthetic_signatures(B, size, seed=400 + s)
+        nd, ng = O.hash_normal((B, 100), 500 + s), O.hash_normal((B, 100), 600 + s)
+        mk = gold["masks"][s]
+        md, dgr = O.d_step_sn(g_sd, d_sd, d_opt, real, nd, size, mk["real"], mk["fake"])
+        for k in O.sn_trainable_names(d_sd):
+            check_probe(f"s{s}.d_grad.{k}", dgr[k], gold[f"s{s}.d_grad.{k}"], rtol=GTOL, atol=2e-8)
+            check_probe(f"s{s}.d_param.{k}", d_sd[k], gold[f"s{s}.d_param.{k}"])
+        for k in d_sd:
+            if k.endswith(("weight_u", "weight_v")):
+                assert torch.allclose(d_sd[k], gold[f"s{s}.d_buf.{k}"], rtol=RTOL, atol=1e-6), (s, k)
+        mg, ggr = O.g_step_sn(g_sd, d_sd, g_opt, ng, size)
+        for k in O.trainable_names(g_sd):
+            if k != "fc.0.bias":
+                check_probe(f"s{s}.g_grad.{k}", ggr[k], gold[f"s{s}.g_grad.{k}"], rtol=GTOL, atol=2e-8)
+                check_probe(f"s{s}.g_param.{k}", g_sd[k], gold[f"s{s}.g_param.{k}"])
+        md.update(mg)
+        for k, v in gold["metrics"][s].items():
+            assert abs(md[k] - v) <= 2e-4 * max(1.0, abs(v)), (s, k, md[k], v)
