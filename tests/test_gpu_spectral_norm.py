@@ -169,3 +169,57 @@ def test_vanilla_gan_with_spectral_norm_trains_like_the_reference(golden_dir, pr
     assert set(out) == {"d_loss", "d_loss_real", "d_loss_fake", "d_real_acc", "d_fake_acc", "d_real_mean", "d_fake_mean",
                         "g_loss", "g_fake_mean"}
     assert all(v == v for v in out.values())
+
+
+def test_ablation_trainer_ordering_with_external_generator():
+    """AblationGANTrainer.train_epoch (ablation…:397-467): both networks stay in train mode, ONE generator pass per
+    batch, the D step sees fake.detach(), the G loss re-runs D (dropout on, another power iteration) on the same fakes
+    against the smoothed label 0.9. The generator is the script's own torch module (ConfigurableGenerator,
+    ablation…:216-328); only D is ours — its image gradient must reach the external module through autograd."""
+    size, B = 64, 8
+    D, sd = _make(size, 7, "fp32")
+    D.train()
+    torch.manual_seed(0)
+    Gx = torch.nn.Sequential(torch.nn.Linear(100, size * size), torch.nn.Tanh()).cuda()   # stand-in external generator
+    d_opt = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    g_opt = torch.optim.Adam(Gx.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    real = O.synthetic_signatures(B, size, seed=12)
+    z = O.hash_normal((B, 100), 13).cuda()
+    m1, m2, m3 = (O.make_dropout_masks(B, size, seed=40 + i) for i in range(3))
+    bce = torch.nn.functional.binary_cross_entropy
+    fake = Gx(z).view(B, 1, size, size)
+    fake.retain_grad()
+    d_opt.zero_grad()
+    D.mask_override = m1
+    pr = D(real.cuda())
+    D.mask_override = m2
+    pf = D(fake.detach())
+    d_loss = bce(pr, torch.full_like(pr, 0.9)) + bce(pf, torch.zeros_like(pf))
+    d_loss.backward()
+    d_opt.step()
+    g_opt.zero_grad()
+    D.mask_override = m3
+    pg = D(fake)
+    g_loss = bce(pg, torch.full_like(pg, 0.9))
+    g_loss.backward()
+    before = [p.detach().clone() for p in Gx.parameters()]
+    g_opt.step()
+    # ---- oracle (float64) of the same sequence
+    sd64 = to64(sd)
+    opt = O.AdamState(sd64, O.sn_trainable_names(sd64))
+    fake64 = fake.detach().cpu().double()
+    d64 = [[m.double() for m in ms] for ms in (m1, m2, m3)]
+    p1, c1, buf = O.d_forward_sn(sd64, real.double(), size, d64[0], train=True)
+    sd64.update(buf)
+    p2, c2, buf = O.d_forward_sn(sd64, fake64, size, d64[1], train=True)
+    sd64.update(buf)
+    ga = O.d_backward_sn(c1, O.bce_grad(p1, torch.full_like(p1, 0.9)), size, d64[0])
+    gb = O.d_backward_sn(c2, O.bce_grad(p2, torch.zeros_like(p2)), size, d64[1])
+    ref_loss = float(O.bce(p1, torch.full_like(p1, 0.9)) + O.bce(p2, torch.zeros_like(p2)))
+    assert abs(float(d_loss) - ref_loss) < 1e-5
+    opt.apply(sd64, {k: ga[k] + gb[k] for k in ga}, 2e-4, 0.5, 0.999)
+    p3, c3, buf = O.d_forward_sn(sd64, fake64, size, d64[2], train=True)
+    g3 = O.d_backward_sn(c3, O.bce_grad(p3, torch.full_like(p3, 0.9)), size, d64[2], need_dx=True)
+    assert abs(float(g_loss) - float(O.bce(p3, torch.full_like(p3, 0.9)))) < 1e-5
+    assert rel_err(fake.grad, g3["__dx"]) <= 5e-4, rel_err(fake.grad, g3["__dx"])
+    assert all(not torch.equal(a, b) for a, b in zip(before, Gx.parameters()))      # the external module did learn
