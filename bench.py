@@ -179,6 +179,56 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# the unchanged reference trainer's loop over the drop-in modules (second figure)
+# ------------------------------------------------------------------------------------------------
+def trainer_style_numbers(gan, pool, B, dev, steps=10, warmup=3):
+    """GANTrainer._train_discriminator / _train_generator (train…:281-376) statement for statement — module calls,
+    criterion, loss.backward(), optimizer.step() and the 7 `.item()` reads per step — which is what
+    train_vanilla_gan_signatures.py executes when it imports this repo's modules (gradient clipping off, its default)."""
+    import torch
+    D, G, crit = gan.discriminator, gan.generator, gan.criterion
+    n_pool = pool.shape[0]
+
+    def one(real):
+        D.train()
+        G.eval()
+        gan.d_optimizer.zero_grad()
+        real_labels = torch.full((B, 1), gan.label_smoothing, device=dev)
+        real_preds = D(real)
+        d_loss_real = crit(real_preds, real_labels)
+        noise = torch.randn(B, gan.latent_dim, device=dev)
+        with torch.no_grad():
+            fake = G(noise)
+        fake_preds = D(fake)
+        d_loss_fake = crit(fake_preds, torch.zeros(B, 1, device=dev))
+        d_loss = d_loss_real + d_loss_fake
+        d_loss.backward()
+        gan.d_optimizer.step()
+        vals = [d_loss.item(), d_loss_real.item(), d_loss_fake.item(), real_preds.mean().item(), fake_preds.mean().item()]
+        G.train()
+        D.eval()
+        gan.g_optimizer.zero_grad()
+        noise = torch.randn(B, gan.latent_dim, device=dev)
+        fake_preds = D(G(noise))
+        g_loss = crit(fake_preds, torch.ones(B, 1, device=dev))
+        g_loss.backward()
+        gan.g_optimizer.step()
+        return vals + [g_loss.item(), fake_preds.mean().item()]
+
+    for i in range(warmup):
+        one(pool[i % n_pool])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        vals = one(pool[i % n_pool])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"images_per_s": B * steps / dt, "ms_per_step": dt / steps * 1e3, "steps": steps, "item_reads_per_step": 7,
+            "api": "module calls + criterion + backward + optimizer.step, as GANTrainer (train…:281-376) drives them",
+            "finite": all(v == v for v in vals)}
+
+
+# ------------------------------------------------------------------------------------------------
 # input pipeline: DeviceSignatureLoader (sg_augment_batch) next to the reference's PIL / torchvision transforms
 # ------------------------------------------------------------------------------------------------
 def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu):
@@ -454,6 +504,9 @@ def run_ours(args, rank, local_rank, world):
                                 "e2e_images_per_s_uint8_host": samp_e2e,
                                 "e2e_bytes": {"h2d": SB * 400, "d2h": SB * S * S},
                                 "e2e_api": "Generator.sample_uint8_to_host (8 chunks, double-buffered D2H)"}
+        # ---- the reference trainer's own loop over the modules (7 .item() per step) ------------------------
+        if rank == 0 and world == 1:
+            line["trainer_style"] = trainer_style_numbers(gan, pool, B, dev)
         # ---- input pipeline: augmentation kernel over a device-resident uint8 pool ------
         if rank == 0:
             line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1))
