@@ -155,6 +155,14 @@ int sg_augment_params(const double* host_angles, const double* host_scales, int 
 int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed, const double* scale_affine,
                      const uint8_t* flip, int batch, int image_size, float* out, void* stream);
 
+/* ---- evaluation: per-image ink statistics --------------------------------------------- */
+/* One pass over (n_images, 1, H, W) fp32 images for src/utils/metrics.py:118-174 calculate_stroke_density /
+ * calculate_foreground_ratio: per image, count_raw = #(x < threshold), count_rescaled = #((x + 1) / 2 < threshold)
+ * (float32, as torch evaluates it) and the minimum. The reference rescales when the minimum of the WHOLE batch is
+ * negative: the caller reduces `minimum` and picks the column. Integer counts: bit-exact. */
+int sg_ink_stats(const float* images, int n_images, int pixels_per_image, float threshold, int* count_raw,
+                 int* count_rescaled, float* minimum, void* stream);
+
 /* ---- synchronised BatchNorm for data-parallel runs ------------------------------- */
 /* With a callback set, every training-mode BatchNorm of the Generator (gen…:58,126) normalises with the statistics of
  * the GLOBAL batch: the per-channel sums (sum x, sum x^2 in forward; sum d, sum d*xhat in backward; 2*C floats) are

@@ -128,7 +128,7 @@ def augment(img_u8: np.ndarray, angle: float, scale: float, flip: bool = False) 
     """One image through the training pipeline with the sampled (angle, scale, flip). Returns float32 (S, S)."""
     size = img_u8.shape[0]
     r = rotate_nearest(img_u8, rotation_fixed(angle, size))
-    s = scale_nearest(r, scale_params(scale, size)) if scale != 1.0 or True else r
+    s = scale_nearest(r, scale_params(scale, size))     # RandomAffine runs even for scale == 1.0 (identity lookup)
     if flip:
         s = s[:, ::-1]
     return to_normalised(np.ascontiguousarray(s))
@@ -140,3 +140,32 @@ def parameter_tables(angles: Sequence[float], scales: Sequence[float], size: int
     rot = np.array([rotation_fixed(float(a), size) for a in angles], dtype=np.int32).reshape(-1, 6)
     sc = np.array([scale_params(float(s), size) for s in scales], dtype=np.float64).reshape(-1, 4)
     return rot, sc
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Ink statistics (src/utils/metrics.py:118-174 calculate_stroke_density / calculate_foreground_ratio), restated in numpy
+# --------------------------------------------------------------------------------------------------------------
+def ink_counts(images: np.ndarray, threshold: float = 0.5):
+    """images (N, 1, H, W) float32. Returns (count_raw, count_rescaled, minimum) per image, the three columns
+    sg_ink_stats produces: #(x < t), #((x + 1) / 2 < t) with float32 roundings, min(x)."""
+    x = images.astype(np.float32).reshape(images.shape[0], -1)
+    t = np.float32(threshold)
+    res = (x + np.float32(1.0)) / np.float32(2.0)
+    return (x < t).sum(axis=1).astype(np.int32), (res < t).sum(axis=1).astype(np.int32), x.min(axis=1)
+
+
+def ink_fraction(images: np.ndarray, threshold: float = 0.5) -> np.ndarray:
+    raw, res, mn = ink_counts(images, threshold)
+    counts = res if mn.min() < 0 else raw                       # `if images.min() < 0: images = (images + 1) / 2`
+    return counts.astype(np.float32) / np.float32(images.shape[2] * images.shape[3])
+
+
+def stroke_density(images: np.ndarray, threshold: float = 0.5):
+    d = ink_fraction(images, threshold)
+    return {"mean": float(np.mean(d)), "std": float(np.std(d)), "min": float(np.min(d)), "max": float(np.max(d))}
+
+
+def foreground_ratio(images: np.ndarray, threshold: float = 0.5):
+    r = ink_fraction(images, threshold)
+    return {"mean": float(np.mean(r)), "std": float(np.std(r)),
+            "percentiles": {k: float(np.percentile(r, int(k))) for k in ("25", "50", "75")}}

@@ -517,3 +517,14 @@ def synthetic_signatures(n: int, size: int = 64, seed: int = 1234) -> Tensor:
     ink = F.max_pool2d(ink, 3, 1, 1)
     ink = F.avg_pool2d(ink, 3, 1, 1)
     return (1.0 - 2.0 * ink).clamp(-1, 1)
+
+
+def metric_batches(size: int = 64, n: int = 24) -> Dict[str, Tensor]:
+    """Seeded image batches for the ink-statistics checks (shared by tests/golden/make_golden_metrics.py and the tests):
+    generator-range [-1, 1] images, their [0, 1] counterpart (no rescale branch), and one with exact zeros / values at
+    the rescale boundary."""
+    sig = synthetic_signatures(n, size, seed=31)
+    noise = hash_uniform((n, 1, size, size), 77) * 2.0 - 1.0
+    soft = (0.6 * sig + 0.4 * noise).clamp(-1, 1)
+    return {"signed": soft, "unit": (soft + 1.0) / 2.0,
+            "edge": torch.where(soft.abs() < 0.02, torch.zeros_like(soft), soft)}

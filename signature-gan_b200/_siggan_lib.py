@@ -67,6 +67,7 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_spectral_norm_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "sg_augment_params": (_I, [_P, _P, _I, _I, _P, _P]),
     "sg_augment_batch": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "sg_ink_stats": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "sg_set_sync_batchnorm": (_I, [_P, _P, _P, _I, _P, _LL]),
     "sg_train_step": (_I, [_P, C.POINTER(SgTrainState), _P, _P, _P, _I, _P, _P, _P, _I, _P]),
 }

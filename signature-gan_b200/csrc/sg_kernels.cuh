@@ -162,6 +162,10 @@ int augment_batch(const uint8_t* pool, const int* index, const int* rot, const d
                   int size, float* out, cudaStream_t s);
 void augment_params(const double* angles, const double* scales, int n, int size, int* rot, double* sc);  // host only
 
+// ---- per-image ink statistics (sg_metrics.cu): counts of x < t and of (x + 1) / 2 < t, and the minimum ------
+void ink_stats(const float* images, int n_images, int pixels, float threshold, int* count_raw, int* count_rescaled,
+               float* minimum, cudaStream_t s);
+
 int kernels_check(const char* what);  // cudaGetLastError -> 0 / -1 (message kept)
 
 }  // namespace sg

@@ -1056,6 +1056,17 @@ int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed
     return 0;
 }
 
+int sg_ink_stats(const float* images, int n_images, int pixels_per_image, float threshold, int* count_raw,
+                 int* count_rescaled, float* minimum, void* stream) {
+    if (!images || !count_raw || !count_rescaled || !minimum || n_images < 1 || pixels_per_image < 4 ||
+        (pixels_per_image & 3) || (reinterpret_cast<uintptr_t>(images) & 15))
+        return fail("sg_ink_stats: bad argument (pixels per image must be a multiple of 4, images 16-byte aligned)");
+    sg::ink_stats(images, n_images, pixels_per_image, threshold, count_raw, count_rescaled, minimum,
+                  static_cast<cudaStream_t>(stream));
+    SG_KCHECK("sg_ink_stats");
+    return 0;
+}
+
 int sg_set_sync_batchnorm(sg_ctx* c, sg_allreduce_fn fn, void* user, int world_size, float* buf, long long buf_floats) {
     if (!c) return fail("sg_set_sync_batchnorm: null ctx");
     if (fn && (world_size < 1 || !buf || buf_floats < 4)) return fail("sg_set_sync_batchnorm: bad argument");
