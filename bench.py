@@ -231,7 +231,7 @@ def trainer_style_numbers(gan, pool, B, dev, steps=10, warmup=3):
 # ------------------------------------------------------------------------------------------------
 # input pipeline: DeviceSignatureLoader (sg_augment_batch) next to the reference's PIL / torchvision transforms
 # ------------------------------------------------------------------------------------------------
-def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu):
+def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu, gan=None):
     """Augmented batches of B images from an 8-bit pool in HBM: kernel alone (CUDA events; 1 byte read + 4 bytes
     written per pixel against the measured HBM peak) and through the loader (host parameter sampling +
     sg_augment_params + one 56 B/image upload + kernel). CPU side: the reference's own transform stack
@@ -277,7 +277,22 @@ def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu):
         ld.batch(idx)
     torch.cuda.synchronize()
     loader_ips = B * reps / (time.perf_counter() - t0)
-    res = {"kernel": "sg_augment_batch", "batch": B, "ms_per_batch": ms, "images_per_s_kernel": B / (ms * 1e-3),
+    # training fed by the loader: epochs over the pool (shuffled, augmented), each batch straight into the fused step
+    train_ips = None
+    if gan is not None:
+        ld2 = DeviceSignatureLoader(imgs, batch_size=B, device=dev, seed=6)
+        for real in ld2:
+            gan.train_step_async(real)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seen = 0
+        for _ in range(3):
+            for real in ld2:
+                gan.train_step_async(real)
+                seen += real.shape[0]
+        torch.cuda.synchronize()
+        train_ips = seen / (time.perf_counter() - t0)
+    res = {"kernel": "sg_augment_batch", "batch": B, "train_images_per_s_fed_by_loader": train_ips, "ms_per_batch": ms, "images_per_s_kernel": B / (ms * 1e-3),
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                         "bytes_per_image": 5 * S * S, "l2": "256 MB flush between launches"},
            "images_per_s_loader": loader_ips,
@@ -509,7 +524,8 @@ def run_ours(args, rank, local_rank, world):
             line["trainer_style"] = trainer_style_numbers(gan, pool, B, dev)
         # ---- input pipeline: augmentation kernel over a device-resident uint8 pool ------
         if rank == 0:
-            line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1))
+            line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1),
+                                                             gan=gan if world == 1 else None)
         # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------
         if rank == 0 and world == 1:
             steps_cpu = 12
