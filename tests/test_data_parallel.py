@@ -86,3 +86,65 @@ def test_shard_range_covers_everything():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [e - b for b, e in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _syncbn_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    """The algebra sg_set_sync_batchnorm implements in CUDA, restated with the oracle's BatchNorm on two gloo ranks:
+    all-reduce the [2][C] rows (sum x, sum x^2 | sum d, sum d*xhat), finalize with rows x world_size; BatchNorm weight /
+    bias gradients stay local and are averaged with the bucket. Each rank's upstream gradient is that of ITS mean loss
+    (world_size x the global-loss gradient of its samples), as in the data-parallel step."""
+    for sub in ("oracle", "signature-gan_b200"):
+        sys.path.insert(0, os.path.join(ROOT, sub))
+    import siggan_oracle as O
+    from data_parallel import average_gradients_, shard_range
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        B, C, H = 12, 16, 8
+        y = O.hash_normal((B, C, H, H), 5).double() * 1.7 + 0.3
+        d = O.hash_normal((B, C, H, H), 6).double()                 # d(global mean loss) / d(bn output)
+        sd = {"bn.weight": O.hash_normal((C,), 7, 1.0, 0.1).double(), "bn.bias": O.hash_normal((C,), 8).double(),
+              "bn.running_mean": torch.zeros(C, dtype=torch.float64), "bn.running_var": torch.ones(C, dtype=torch.float64),
+              "bn.num_batches_tracked": torch.tensor(0)}
+        stats = {}
+        out_ref, xhat_ref, rstd_ref = O._bn_forward(y, sd, "bn", True, stats)
+        dy_ref, dgamma_ref, dbeta_ref = O._bn_backward(d, xhat_ref, rstd_ref, sd["bn.weight"], True)
+        lo, hi = shard_range(B, rank, world)
+        yl, dl = y[lo:hi], d[lo:hi] * world
+        rows = (hi - lo) * H * H
+        # ---- forward: one [2][C] row per rank, summed over ranks, finalized with the global row count
+        row = torch.stack([yl.sum(dim=(0, 2, 3)), (yl * yl).sum(dim=(0, 2, 3))])
+        dist.all_reduce(row)
+        n = rows * world
+        mean = row[0] / n
+        var = (row[1] / n - mean * mean).clamp_min(0)
+        rstd = torch.rsqrt(var + O.BN_EPS)
+        xhat = (yl - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+        out = xhat * sd["bn.weight"].view(1, -1, 1, 1) + sd["bn.bias"].view(1, -1, 1, 1)
+        assert torch.allclose(out, out_ref[lo:hi], rtol=1e-10, atol=1e-10)
+        run_var = 0.9 * sd["bn.running_var"] + 0.1 * var * n / (n - 1)
+        assert torch.allclose(run_var, stats["bn.running_var"], rtol=1e-10, atol=1e-12)
+        assert torch.allclose(0.1 * mean, stats["bn.running_mean"], rtol=1e-10, atol=1e-12)
+        # ---- backward: local dgamma / dbeta (averaged like the rest of the bucket), global k2 / k3 for the data gradient
+        brow = torch.stack([dl.sum(dim=(0, 2, 3)), (dl * xhat).sum(dim=(0, 2, 3))])
+        dbeta, dgamma = brow[0].clone(), brow[1].clone()
+        dist.all_reduce(brow)
+        k1 = (sd["bn.weight"] * rstd).view(1, -1, 1, 1)
+        dy = k1 * (dl - (brow[0] / n).view(1, -1, 1, 1) - xhat * (brow[1] / n).view(1, -1, 1, 1))
+        assert torch.allclose(dy, world * dy_ref[lo:hi], rtol=1e-9, atol=1e-10)
+        bucket = torch.cat([dgamma, dbeta])
+        average_gradients_(bucket)
+        assert torch.allclose(bucket, torch.cat([dgamma_ref, dbeta_ref]), rtol=1e-9, atol=1e-10)
+        # ---- and local statistics would NOT have given the global result (what SyncBN is for)
+        lm = yl.mean(dim=(0, 2, 3))
+        assert (lm - mean).abs().max() > 1e-3
+        open(os.path.join(out_dir, f"sbn{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sync_batchnorm_algebra(tmp_path):
+    world = 2
+    mp.spawn(_syncbn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"sbn{r}").exists() for r in range(world))
