@@ -21,7 +21,7 @@ import torch
 
 import _siggan_lib as L
 
-IMAGE_EXTENSIONS = (".png", ".jpg", ".jpeg", ".bmp", ".tif", ".tiff")   # data_loader_signatures.py:35
+SUPPORTED_EXTENSIONS = (".png", ".jpg", ".jpeg", ".bmp", ".tiff")        # data_loader_signatures.py:38
 
 
 class DeviceSignatureLoader:
@@ -133,13 +133,28 @@ class DeviceSignatureLoader:
         return out
 
     # -- construction from a directory, like create_data_loader(data_dir, ...) ---------------------------
+    @staticmethod
+    def load_directory_uint8(data_dir: Union[str, Path], image_size: int = 64,
+                             extensions: Tuple[str, ...] = SUPPORTED_EXTENSIONS) -> torch.Tensor:
+        """(N, S, S) uint8 pool from the image files directly inside `data_dir` (same discovery rule as
+        SignatureDataset._collect_image_paths, data_loader_signatures.py:88-103: listed extensions in lower and upper
+        case, sorted). Each file goes once through what SignatureDataset.__getitem__ + the first transform do per
+        access: Image.open(...).convert('L') and transforms.Resize((S, S)) (= PIL bilinear resize)."""
+        from PIL import Image
+        root = Path(data_dir)
+        if not root.exists():
+            raise ValueError(f"Directory does not exist: {data_dir}")
+        paths = set()
+        for ext in extensions:
+            paths.update(root.glob(f"*{ext}"))
+            paths.update(root.glob(f"*{ext.upper()}"))
+        paths = sorted(paths)
+        if not paths:
+            raise ValueError(f"No images found in {data_dir}")
+        imgs = [np.asarray(Image.open(p).convert("L").resize((image_size, image_size), Image.BILINEAR)) for p in paths]
+        return torch.from_numpy(np.stack(imgs))
+
     @classmethod
     def from_directory(cls, data_dir: Union[str, Path], image_size: int = 64, **kwargs) -> "DeviceSignatureLoader":
-        """Decode + grayscale + resize every image ONCE on the host (PIL, as `SignatureDataset.__getitem__` does per
-        access: Image.open(...).convert('L'), transforms.Resize), then keep the uint8 pool in HBM."""
-        from PIL import Image
-        paths = sorted(p for p in Path(data_dir).rglob("*") if p.suffix.lower() in IMAGE_EXTENSIONS)
-        if not paths:
-            raise ValueError(f"No valid images found in {data_dir}")
-        imgs = [np.asarray(Image.open(p).convert("L").resize((image_size, image_size), Image.BILINEAR)) for p in paths]
-        return cls(torch.from_numpy(np.stack(imgs)), **kwargs)
+        """Decode + grayscale + resize every image ONCE on the host, then keep the uint8 pool in HBM."""
+        return cls(cls.load_directory_uint8(data_dir, image_size), **kwargs)

@@ -77,3 +77,34 @@ def test_loader_refuses_cpu():
         DeviceSignatureLoader(imgs.float(), device="cpu")
     with pytest.raises(ValueError):
         DeviceSignatureLoader(torch.zeros(4, 32, 32, dtype=torch.uint8), device="cpu")
+
+
+def test_directory_pool_equals_reference_decode_and_resize(tmp_path):
+    """DeviceSignatureLoader.load_directory_uint8 == per file Image.open(...).convert('L') + transforms.Resize((S, S))
+    (data_loader_signatures.py:120-135, 176-177), with SignatureDataset's discovery rule (:88-103)."""
+    from PIL import Image
+    from torchvision import transforms
+    from device_data_loader import DeviceSignatureLoader
+    rng = np.random.default_rng(4)
+    names = ["b.png", "a.PNG", "c.jpg", "d.bmp", "skip.txt", "e.gif"]
+    for i, name in enumerate(names):
+        arr = (rng.random((90 + 7 * i, 150 - 11 * i, 3)) * 255).astype(np.uint8)
+        if name.endswith((".txt", ".gif")):
+            (tmp_path / name).write_bytes(b"not an image the loader should look at")
+        else:
+            Image.fromarray(arr).save(tmp_path / name)
+    (tmp_path / "sub").mkdir()
+    Image.fromarray(np.zeros((20, 20), np.uint8)).save(tmp_path / "sub" / "nested.png")     # not recursive
+    for size in (64, 128):
+        pool = DeviceSignatureLoader.load_directory_uint8(tmp_path, size)
+        expect = sorted(p for p in tmp_path.iterdir() if p.suffix.lower() in (".png", ".jpg", ".bmp"))
+        assert pool.shape == (len(expect), size, size) and pool.dtype == torch.uint8
+        for k, p in enumerate(expect):
+            ref = transforms.Resize((size, size))(Image.open(p).convert("L"))
+            assert np.array_equal(pool[k].numpy(), np.asarray(ref)), p.name
+    with pytest.raises(ValueError, match="does not exist"):
+        DeviceSignatureLoader.load_directory_uint8(tmp_path / "missing")
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(ValueError, match="No images"):
+        DeviceSignatureLoader.load_directory_uint8(empty)
