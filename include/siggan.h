@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
 enum { SG_PREC_BF16 = 0, SG_PREC_FP32 = 1 };
 enum { SG_NET_G = 0, SG_NET_D = 1 };
@@ -127,6 +127,8 @@ typedef struct sg_train_state {
     uint64_t seed; uint64_t offset;                /* dropout RNG counter (ignored when masks given) */
     const float* masks_real; const float* masks_fake; /* optional injected masks (parity tests) */
     int world_size;                                /* >1: caller all-reduces the gradient buckets between phases */
+    float grad_scale;                              /* the Adam phases multiply the bucket by this (1/world_size when the
+                                                      caller SUMs over ranks; 0 or 1 = gradients used as they are) */
 } sg_train_state;
 
 /* metrics_out (device, 12 floats): d_loss, d_loss_real, d_loss_fake, d_real_acc, d_fake_acc, d_real_mean,

@@ -31,7 +31,7 @@ class SgTrainState(C.Structure):
                 ("g_lr", C.c_float), ("d_lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("label_smoothing", C.c_float), ("dropout_p", C.c_float),
                 ("seed", C.c_uint64), ("offset", C.c_uint64), ("masks_real", C.c_void_p),
-                ("masks_fake", C.c_void_p), ("world_size", C.c_int)]
+                ("masks_fake", C.c_void_p), ("world_size", C.c_int), ("grad_scale", C.c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/siggan.h declares (tests check this).

@@ -56,6 +56,7 @@ struct WgradArgs {
     int plain;            // 1: no taps, fmap[0] is a 2-D [pixels][Nf] map (Generator fc weight gradient)
     int tpc;              // filter taps stacked along N per CTA (1, 2 or 4)
     float* partial;  // [splits][16][Mc][Nf]
+    float* bias_partial;  // optional [splits][Mc]: sum over pixels of the coarse tensor (fused bias gradient)
 };
 
 // Tensor-map builders (host). Return 0 on success.
@@ -81,8 +82,11 @@ int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout);
 
 // dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
 // `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.
+// dbias (optional, Mc floats): sum over pixels of `coarse` — the bias gradient of a Conv2d whose output gradient is
+// `coarse` — computed by the same kernel (one more product with an all-ones operand); fat layers only.
 int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
-                 float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream);
+                 float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream,
+                 float* dbias = nullptr);
 size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf);
 
 // Generator fc weight gradient (plain MN-major GEMM over the batch), un-permuting rows into dW (F, latent).

@@ -70,6 +70,84 @@ void pack_classifier(const float* w, float* wp, int C, cudaStream_t s) {
     pack_classifier_kernel<<<blocks_for(C * 16, 256), 256, 0, s>>>(w, wp, C);
 }
 
+// One launch for all weight packs of a network (table in the parameter bank). w16 segments are transposed through
+// shared memory in 32 x 32 x 16 tiles so that both packed layouts are written in 64-byte runs; the fc / classifier
+// permutations are small elementwise sections (4096 elements per block).
+__global__ void __launch_bounds__(256) pack_plan_kernel(const __grid_constant__ PackPlan plan) {
+    __shared__ bf16 tile[32 * 32 * 16 + 64];
+    int sidx = 0;
+    while (sidx + 1 < plan.nseg && static_cast<int>(blockIdx.x) >= plan.seg[sidx + 1].tile0) ++sidx;
+    const PackSeg& sg_ = plan.seg[sidx];
+    const int t_local = blockIdx.x - sg_.tile0;
+    const int tid = threadIdx.x;
+    if (sg_.kind == 0) {
+        const int A = sg_.A, B = sg_.B;
+        const int bt = B / 32;
+        const int a0 = (t_local / bt) * 32, b0 = (t_local % bt) * 32;
+        // load: for each a, the 32 b's x 16 taps are 512 contiguous floats
+        for (int e = tid; e < 32 * 512; e += 256) {
+            const int a = e >> 9, r = e & 511;
+            tile[a * 512 + r] = __float2bfloat16(sg_.src[(static_cast<long>(a0 + a) * B + b0) * 16 + r]);
+        }
+        __syncthreads();
+        if (sg_.ab) {  // [a][t][b]: 32 b's contiguous
+            for (int e = tid; e < 32 * 16 * 32; e += 256) {
+                const int b = e & 31, t = (e >> 5) & 15, a = e >> 9;
+                sg_.ab[(static_cast<long>(a0 + a) * 16 + t) * B + b0 + b] = tile[a * 512 + b * 16 + t];
+            }
+        }
+        if (sg_.ba) {  // [b][t][a]: 32 a's contiguous
+            for (int e = tid; e < 32 * 16 * 32; e += 256) {
+                const int a = e & 31, t = (e >> 5) & 15, b = e >> 9;
+                sg_.ba[(static_cast<long>(b0 + b) * 16 + t) * A + a0 + a] = tile[a * 512 + b * 16 + t];
+            }
+        }
+    } else if (sg_.kind == 1) {  // generator fc: rows permuted NCHW feature -> NHWC column, K padded
+        const int C0 = sg_.A, latent = sg_.B, Kp = sg_.Kp;
+        const long total = static_cast<long>(C0) * 16 * Kp;
+        for (long i = static_cast<long>(t_local) * 4096 + tid; i < total && i < static_cast<long>(t_local + 1) * 4096; i += 256) {
+            const int k = static_cast<int>(i % Kp);
+            const int j = static_cast<int>(i / Kp);
+            const int f = (j % C0) * 16 + j / C0;
+            sg_.ab[i] = __float2bfloat16(k < latent ? sg_.src[static_cast<long>(f) * latent + k] : 0.f);
+            if (k == 0) sg_.fdst[j] = sg_.src2[f];
+        }
+    } else {  // classifier weight: NCHW -> NHWC order, fp32
+        const int C = sg_.A, F = C * 16;
+        for (int j = t_local * 4096 + tid; j < F && j < (t_local + 1) * 4096; j += 256)
+            sg_.fdst[j] = sg_.src[(j % C) * 16 + j / C];
+    }
+}
+int pack_plan_add_w16(PackPlan& p, const float* src, bf16* ab, bf16* ba, int A, int B) {
+    if (p.nseg >= 8 || A % 32 || B % 32) return -1;
+    PackSeg& s = p.seg[p.nseg++];
+    s = PackSeg{};
+    s.src = src; s.ab = ab; s.ba = ba; s.A = A; s.B = B; s.kind = 0; s.tile0 = p.total_tiles;
+    p.total_tiles += (A / 32) * (B / 32);
+    return 0;
+}
+int pack_plan_add_fc(PackPlan& p, const float* W, const float* bias, bf16* Wp, float* biasp, int C0, int latent, int Kp) {
+    if (p.nseg >= 8) return -1;
+    PackSeg& s = p.seg[p.nseg++];
+    s = PackSeg{};
+    s.src = W; s.src2 = bias; s.ab = Wp; s.fdst = biasp; s.A = C0; s.B = latent; s.Kp = Kp; s.kind = 1; s.tile0 = p.total_tiles;
+    p.total_tiles += static_cast<int>((static_cast<long>(C0) * 16 * Kp + 4095) / 4096);
+    return 0;
+}
+int pack_plan_add_classifier(PackPlan& p, const float* w, float* wp, int C) {
+    if (p.nseg >= 8) return -1;
+    PackSeg& s = p.seg[p.nseg++];
+    s = PackSeg{};
+    s.src = w; s.fdst = wp; s.A = C; s.kind = 2; s.tile0 = p.total_tiles;
+    p.total_tiles += (C * 16 + 4095) / 4096;
+    return 0;
+}
+void pack_plan_launch(const PackPlan& p, cudaStream_t s) {
+    if (p.total_tiles <= 0) return;
+    note_launch();
+    pack_plan_kernel<<<p.total_tiles, 256, 0, s>>>(p);
+}
+
 template <typename T>
 __global__ void cast_pad_z_kernel(const float* __restrict__ z, T* __restrict__ zp, int B, int latent, int Kp) {
     const long total = static_cast<long>(B) * Kp;
@@ -841,6 +919,21 @@ void dropout_masks(uint64_t seed, uint64_t offset, long n, float p, float* out, 
     note_launch();
     dropout_masks_kernel<<<blocks_for(n, 256), 256, 0, s>>>(seed, offset, n, p, out);
 }
+__global__ void dropout_masks_dev_kernel(uint64_t seed, const unsigned long long* __restrict__ offset_ptr, long n, float p,
+                                         float* __restrict__ out) {
+    const float keep = 1.f / (1.f - p);
+    const uint64_t offset = *offset_ptr;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const uint64_t h = splitmix64(splitmix64(seed) ^ (offset + static_cast<uint64_t>(i)));
+        const float u = static_cast<float>(h >> 40) * (1.0f / 16777216.0f);
+        out[i] = u >= p ? keep : 0.f;
+    }
+}
+void dropout_masks_dev(uint64_t seed, const unsigned long long* offset_ptr, long n, float p, float* out, cudaStream_t s) {
+    note_launch();
+    dropout_masks_dev_kernel<<<blocks_for(n, 256), 256, 0, s>>>(seed, offset_ptr, n, p, out);
+}
 
 // ------------------------------------------------------------------------------------------------
 // BCE on probabilities
@@ -955,6 +1048,57 @@ void adam_step(float* p, const float* g, float* m, float* v, long n, float lr, f
     note_launch();
     adam_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, b1, b2, eps, static_cast<float>(lr / bc1),
                                                    static_cast<float>(1.0 / std::sqrt(bc2)));
+}
+
+// Device-resident step counters (the fused training step is captured in CUDA graphs, so nothing that changes from step
+// to step may be a kernel argument): step_prep advances the Adam step of one network, derives its bias-correction
+// scalars with the same double-precision formulas adam_step() uses on the host, and advances the dropout counter.
+__global__ void step_prep_kernel(StepCounters* __restrict__ c, int which, float lr, float b1, float b2,
+                                 unsigned long long dropout_advance) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long step;
+    if (which == 0) step = ++c->g_step; else step = ++c->d_step;
+    const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(step));
+    float* o = which == 0 ? c->adam_g : c->adam_d;
+    o[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    o[1] = static_cast<float>(1.0 / sqrt(bc2));
+    c->dropout_offset += dropout_advance;
+}
+void step_prep(StepCounters* c, int which, float lr, float b1, float b2, unsigned long long dropout_advance, cudaStream_t s) {
+    note_launch();
+    step_prep_kernel<<<1, 32, 0, s>>>(c, which, lr, b1, b2, dropout_advance);
+}
+__global__ void step_set_kernel(StepCounters* __restrict__ c, int field, long long value) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (field == 0) c->g_step = value;
+    else if (field == 1) c->d_step = value;
+    else c->dropout_offset = static_cast<unsigned long long>(value);
+}
+void step_set(StepCounters* c, int field, long long value, cudaStream_t s) {
+    note_launch();
+    step_set_kernel<<<1, 32, 0, s>>>(c, field, value);
+}
+// grad_scale: 1 / world_size when the bucket holds the SUM over data-parallel ranks
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long n, float b1, float b2, float eps,
+                                const float* __restrict__ scal, float grad_scale) {
+    const float step_size = scal[0], inv_bc2_sqrt = scal[1];
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+void adam_step_dev(float* p, const float* g, float* m, float* v, long n, float b1, float b2, float eps, const float* scal,
+                   float grad_scale, cudaStream_t s) {
+    note_launch();
+    adam_dev_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, b1, b2, eps, scal, grad_scale);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -37,6 +37,25 @@ void pack_fc(const float* W, const float* bias, bf16* Wp, float* biasp, int C0, 
 // Classifier weight (1, C*16) NCHW order -> NHWC order fp32
 void pack_classifier(const float* w, float* wp, int C, cudaStream_t s);
 
+// All packs of one network in ONE launch (<= 8 segments). kind 0: pack_w16, 1: pack_fc, 2: pack_classifier.
+struct PackSeg {
+    const float* src;
+    const float* src2;  // fc bias
+    bf16* ab;           // w16: [A][16][B]; fc: Wp
+    bf16* ba;           // w16: [B][16][A]
+    float* fdst;        // fc: permuted bias; classifier: permuted weight
+    int A, B, Kp, kind, tile0;
+};
+struct PackPlan {
+    PackSeg seg[8];
+    int nseg = 0;
+    int total_tiles = 0;
+};
+int pack_plan_add_w16(PackPlan& p, const float* src, bf16* ab, bf16* ba, int A, int B);
+int pack_plan_add_fc(PackPlan& p, const float* W, const float* bias, bf16* Wp, float* biasp, int C0, int latent, int Kp);
+int pack_plan_add_classifier(PackPlan& p, const float* w, float* wp, int C);
+void pack_plan_launch(const PackPlan& p, cudaStream_t s);
+
 // ---- generator side --------------------------------------------------------------------------
 template <typename T>
 void cast_pad_z(const float* z, T* zp, int B, int latent, int Kp, cudaStream_t s);
@@ -127,6 +146,19 @@ void g_loss_metrics(const float* prob, int B, float* metrics, float* dlogit, cud
 // ---- optimizer -------------------------------------------------------------------------------
 void adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, long step,
                cudaStream_t s);
+
+// Device-resident per-step state of the fused training step (see step_prep_kernel).
+struct StepCounters {
+    long long g_step, d_step;
+    unsigned long long dropout_offset;
+    float adam_g[2], adam_d[2];  // {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)}
+};
+void step_prep(StepCounters* c, int which /* 0 = G, 1 = D */, float lr, float b1, float b2,
+               unsigned long long dropout_advance, cudaStream_t s);
+void step_set(StepCounters* c, int field /* 0 g_step, 1 d_step, 2 dropout_offset */, long long value, cudaStream_t s);
+void adam_step_dev(float* p, const float* g, float* m, float* v, long n, float b1, float b2, float eps, const float* scal,
+                   float grad_scale, cudaStream_t s);
+void dropout_masks_dev(uint64_t seed, const unsigned long long* offset_ptr, long n, float p, float* out, cudaStream_t s);
 
 // ---- direct convolutions (validation mode / fallback). Weights are the fp32 master tensors in PyTorch
 // layout, addressed as w[o*so + i*si + ky*4 + kx] where o = output channel of THIS op, i = input channel.

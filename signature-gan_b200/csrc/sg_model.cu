@@ -62,11 +62,15 @@ struct TensorInfo {
     }
 };
 
+// Bumped whenever a library-owned buffer moves: captured CUDA graphs hold the old addresses and must be rebuilt.
+static unsigned long long g_alloc_epoch = 0;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
+        ++g_alloc_epoch;
         if (p) cudaFree(p);  // implicit device sync: in-flight users are done before the old block goes away
         p = nullptr;
         cap = 0;
@@ -146,6 +150,22 @@ struct DWs {
     size_t bytes;
 };
 
+// One captured phase of the fused training step. The key holds everything the captured launches bake in.
+struct GraphKey {
+    int phase, B, flags;
+    const void* ptr[10];
+    float f[8];
+    unsigned long long seed;
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0, n_launches = 0;
+    bool bad = false;
+    unsigned long long epoch = 0, last = 0;
+};
+
 }  // namespace
 
 struct sg_ctx {
@@ -164,6 +184,8 @@ struct sg_ctx {
     float *fc_biasp, *cls_wp;
     DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
     const float* d_pack_src = nullptr;  // parameter buffer the Discriminator packs were last built from
+    const float* g_pack_src = nullptr;  // same for the Generator (several modules may share one context)
+    int device = 0;                     // CUDA device ordinal this context was created on
     // SyncBN (sg_set_sync_batchnorm): per-channel BatchNorm sums are all-reduced over the ranks through the caller's callback
     sg_allreduce_fn sync_fn = nullptr;
     void* sync_user = nullptr;
@@ -174,6 +196,15 @@ struct sg_ctx {
     float *dlogit, *k1, *k2, *k3;
     int scratch_batch = 0;
     Profiler prof;
+    // fused training step: device-resident step counters + CUDA graphs of the phases (see sg_train_step)
+    DevBuf counters_buf;
+    sg::StepCounters* counters = nullptr;
+    long long mirror_g_step = -1, mirror_d_step = -1;     // host mirror of the device counters (-1 = unknown)
+    unsigned long long mirror_drop = ~0ull;
+    bool mirror_drop_known = false;
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_tick = 0;
+    cudaStream_t cap_stream = nullptr;
 };
 
 namespace {
@@ -311,24 +342,32 @@ int sync_bn_bwd_coefficients(sg_ctx* c, const float* partial, int chunks, long r
 // weight packs
 // ------------------------------------------------------------------------------------------------
 int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
+    c->g_pack_src = params;
     if (c->cfg.precision != SG_PREC_BF16) return 0;
     PROF("g.pack", 0, 10.0 * c->g_count);
-    sg::pack_fc(params + c->gt[c->g_fc_w].offset, params + c->gt[c->g_fc_b].offset, c->fc_Wp, c->fc_biasp, c->gch[0],
-                c->cfg.latent_dim, c->Kp, s);
+    sg::PackPlan plan;
+    int rc = sg::pack_plan_add_fc(plan, params + c->gt[c->g_fc_w].offset, params + c->gt[c->g_fc_b].offset, c->fc_Wp,
+                                  c->fc_biasp, c->gch[0], c->cfg.latent_dim, c->Kp);
     for (int i = 0; i < c->L; ++i)  // W (Cin, Cout, 4, 4): forward pack [Cout][16][Cin] = BA, dgrad pack [Cin][16][Cout] = AB
-        sg::pack_w16(params + c->gt[c->g_up_w[i]].offset, c->g_packB[i], c->g_packF[i], c->gch[i], c->gch[i + 1], s);
+        rc |= sg::pack_plan_add_w16(plan, params + c->gt[c->g_up_w[i]].offset, c->g_packB[i], c->g_packF[i], c->gch[i],
+                                    c->gch[i + 1]);
+    if (rc) return fail("pack_generator: pack plan overflow");
+    sg::pack_plan_launch(plan, s);
     SG_KCHECK("pack_generator");
     return 0;
 }
 int pack_discriminator(sg_ctx* c, const float* params, cudaStream_t s) {
     PROF("d.pack", 0, 10.0 * c->d_count);
     c->d_pack_src = params;
-    sg::pack_classifier(params + c->dt[c->d_cls_w].offset, c->cls_wp, c->dch[c->ND], s);
+    sg::PackPlan plan;
+    int rc = sg::pack_plan_add_classifier(plan, params + c->dt[c->d_cls_w].offset, c->cls_wp, c->dch[c->ND]);
     if (c->cfg.precision == SG_PREC_BF16) {
         for (int i = 1; i < c->ND; ++i)  // W (Cout, Cin, 4, 4): forward pack [Cout][16][Cin] = AB, dgrad pack = BA
-            sg::pack_w16(params + c->dt[c->d_conv_w[i]].offset, c->d_packF[i], c->d_packB[i], c->dch[i + 1], c->dch[i],
-                         s);
+            rc |= sg::pack_plan_add_w16(plan, params + c->dt[c->d_conv_w[i]].offset, c->d_packF[i], c->d_packB[i],
+                                        c->dch[i + 1], c->dch[i]);
     }
+    if (rc) return fail("pack_discriminator: pack plan overflow");
+    sg::pack_plan_launch(plan, s);
     SG_KCHECK("pack_discriminator");
     return 0;
 }
@@ -364,7 +403,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     const bool fused_eval = !train && !save;  // fold running-stat BN + ReLU into the producing GEMM's epilogue
     SG_TRY(pack_generator(c, params, s));
     const double es = c->es;
-    {
+    if (z) {  // z == nullptr: the caller already cast the latents into the workspace (fused step, outside its graph)
         PROF("g.cast_z", 0, B * (4.0 * latent + es * c->Kp));
         sg::cast_pad_z<T>(z, reinterpret_cast<T*>(w.zp), B, latent, c->Kp, s);
     }
@@ -710,17 +749,21 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
             float* dW = grads + c->dt[c->d_conv_w[i]].offset;
             {
             PROF((nm + ".wgrad").c_str(), cflops, es * ((double)rows * Cout + 4.0 * rows * Cin));
+            // bf16: the bias gradient (column sums of dy) comes out of the weight-gradient kernel (all-ones operand)
             if (kTC)
                 SG_UMMA(sg::launch_wgrad(reinterpret_cast<const bf16*>(cur), reinterpret_cast<const bf16*>(w.a[i - 1]), B,
-                                         oh, oh, Cout, Cin, wpart, c->wpart.cap / 4, dW, 0, s));
+                                         oh, oh, Cout, Cin, wpart, c->wpart.cap / 4, dW, 0, s,
+                                         grads + c->dt[c->d_conv_b[i]].offset));
             else
                 sg::wgrad_direct<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.a[i - 1]), dW, B, oh,
                                     oh, Cout, Cin, s);
             }
-            PROF((nm + ".dbias").c_str(), 0, es * (double)rows * Cout);
-            const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr, nullptr,
-                                                 rows, Cout, cpart, s);
-            sg::col_finalize(cpart, chunks, Cout, 0, grads + c->dt[c->d_conv_b[i]].offset, nullptr, s);
+            if (!kTC) {
+                PROF((nm + ".dbias").c_str(), 0, es * (double)rows * Cout);
+                const int chunks = sg::col_reduce<T>(0, reinterpret_cast<const T*>(cur), nullptr, nullptr, nullptr,
+                                                     nullptr, rows, Cout, cpart, s);
+                sg::col_finalize(cpart, chunks, Cout, 0, grads + c->dt[c->d_conv_b[i]].offset, nullptr, s);
+            }
         }
         // data gradient = transposed conv of dy, gated by the previous block's LeakyReLU' and dropout mask
         const float* mk = masks ? masks + mask_offset(c, B, i - 1) : nullptr;
@@ -765,10 +808,238 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     return 0;
 }
 
+// Every entry point runs on the context's device, whatever the caller's current device is (kernel launches, scratch
+// allocation and tensor-map encoding all go to the current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Context-less entry points run on the device that owns their first device pointer.
+struct PtrDeviceGuard : DeviceGuard {
+    static int device_of(const void* p) {
+        cudaPointerAttributes a;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+        cudaGetLastError();
+        return cur;
+    }
+    explicit PtrDeviceGuard(const void* p) : DeviceGuard(device_of(p)) {}
+};
+
 #define DISPATCH_T(ctx, fn, ...) \
     ((ctx)->cfg.precision == SG_PREC_BF16 ? fn<bf16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 }  // namespace
+
+// ---- fused training step ------------------------------------------------------------------------
+// Everything that changes from step to step lives in device memory (Adam step counts, dropout counter) or is staged
+// by a few launches OUTSIDE the captured region (real batch -> x2, latents -> workspace, injected masks), so that each
+// phase is ONE cudaGraphLaunch: ~110 kernel launches per step otherwise leave 0.7-0.85 ms of gaps between kernels.
+static bool graphs_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SIGGAN_GRAPH");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
+template <typename T>
+static int cast_latents_t(sg_ctx* c, const float* z, void* ws, int B, cudaStream_t s) {
+    GWs w = carve_g(c, ws, B);
+    PROF("g.cast_z", 0, B * (4.0 * c->cfg.latent_dim + (double)c->es * c->Kp));
+    sg::cast_pad_z<T>(z, reinterpret_cast<T*>(w.zp), B, c->cfg.latent_dim, c->Kp, s);
+    return 0;
+}
+
+static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d_grads, float* g_grads, float* metrics,
+                            int phase, bool masks_injected, cudaStream_t s) {
+    const size_t img = (size_t)B * c->S * c->S;
+    float* x2 = static_cast<float*>(c->x2.p);
+    const bool dropout = st->dropout_p > 0.f;
+    const float gscale = st->grad_scale > 0.f ? st->grad_scale : 1.f;
+    if (phase == 12) {
+        const float* masks = dropout ? static_cast<const float*>(c->masks2.p) : nullptr;
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s, 2));
+    }
+    if (phase == 1 || phase == 11) {
+        // ---- D step (train…:281-337): D.train(), G.eval(); one 2B batch [real | G(noise)] since D has no batch coupling
+        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, nullptr, B, 0, c->gws_tmp.p, x2 + img,
+                          nullptr, false, s));
+        const float* masks = nullptr;
+        if (dropout) {
+            float* m2 = static_cast<float*>(c->masks2.p);
+            if (!masks_injected)
+                sg::dropout_masks_dev(st->seed, &c->counters->dropout_offset, sg_d_mask_count(c, 2 * B), st->dropout_p, m2, s);
+            masks = m2;
+        }
+        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s));
+        DWs w = carve_d(c, c->d_ws.p, 2 * B);
+        sg::d_loss_metrics(w.prob, B, st->label_smoothing, metrics, c->dlogit, s);
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s,
+                          phase == 11 ? 1 : 0));
+    }
+    if (phase == 2) {
+        PROF("adam.d", 0, 28.0 * c->d_count);
+        sg::step_prep(c->counters, 1, st->d_lr, st->beta1, st->beta2,
+                      dropout ? (unsigned long long)sg_d_mask_count(c, 2 * B) : 0ull, s);
+        sg::adam_step_dev(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->beta1, st->beta2, st->eps,
+                          c->counters->adam_d, gscale, s);
+    }
+    if (phase == 3) {
+        // ---- G step (train…:339-376): G.train() (batch-stat BN), D.eval() (no dropout), labels = 1
+        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, nullptr, B, 1, c->g_ws.p, nullptr, nullptr,
+                          true, s));
+        const float* fake = carve_g(c, c->g_ws.p, B).out;  // D reads the generated images where G left them
+        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, fake, B, nullptr, c->d_ws.p, nullptr, nullptr, s));
+        DWs w = carve_d(c, c->d_ws.p, B);
+        sg::g_loss_metrics(w.prob, B, metrics, c->dlogit, s);
+        float* dximg = static_cast<float*>(c->dximg.p);
+        // weight gradients of D are not needed here (the reference's autograd computes and discards them)
+        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, fake, c->d_ws.p, nullptr, c->dlogit, B, nullptr, dximg, s));
+        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, dximg, B, 1, g_grads, nullptr, s));
+    }
+    if (phase == 4) {
+        PROF("adam.g", 0, 28.0 * c->g_count);
+        sg::step_prep(c->counters, 0, st->g_lr, st->beta1, st->beta2, 0ull, s);
+        sg::adam_step_dev(st->g_params, g_grads, st->g_exp_avg, st->g_exp_avg_sq, c->g_count, st->beta1, st->beta2, st->eps,
+                          c->counters->adam_g, gscale, s);
+    }
+    SG_KCHECK("sg_train_step");
+    return 0;
+}
+
+static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
+                       int B, float* d_grads, float* g_grads, float* metrics, int phase, cudaStream_t s) {
+    const size_t img = (size_t)B * c->S * c->S;
+    const bool dropout = st->dropout_p > 0.f;
+    const bool masks_injected = dropout && st->masks_real && st->masks_fake;
+    // ---- per-step inputs and counters: plain launches on the caller's stream, outside any graph -------------------
+    if (phase == 1 || phase == 11) {
+        if (!real || !noise_d || !d_grads) return fail("sg_train_step: D phase needs real, noise_d and d_grads");
+        float* x2 = static_cast<float*>(c->x2.p);
+        cudaError_t e = cudaMemcpyAsync(x2, real, img * 4, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail("sg_train_step: copy of real batch failed: %s", cudaGetErrorString(e));
+        SG_TRY(DISPATCH_T(c, cast_latents_t, c, noise_d, c->gws_tmp.p, B, s));
+        if (dropout) {
+            float* m2 = static_cast<float*>(c->masks2.p);
+            if (masks_injected) {
+                for (int i = 0; i < c->ND; ++i) {
+                    const size_t n = (size_t)B * c->dch[i + 1];
+                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i), st->masks_real + mask_offset(c, B, i), n * 4,
+                                    cudaMemcpyDeviceToDevice, s);
+                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i) + n, st->masks_fake + mask_offset(c, B, i), n * 4,
+                                    cudaMemcpyDeviceToDevice, s);
+                }
+            } else if (!c->mirror_drop_known || c->mirror_drop != st->offset) {
+                sg::step_set(c->counters, 2, (long long)st->offset, s);
+                c->mirror_drop = st->offset;
+                c->mirror_drop_known = true;
+            }
+        }
+    } else if (phase == 12) {
+        if (!d_grads) return fail("sg_train_step: D phase needs d_grads");
+    } else if (phase == 2) {
+        if (!d_grads) return fail("sg_train_step: D update needs d_grads");
+        if (c->mirror_d_step != st->d_step) sg::step_set(c->counters, 1, st->d_step, s);
+        c->mirror_d_step = st->d_step + 1;
+        if (dropout && c->mirror_drop_known) c->mirror_drop += (unsigned long long)sg_d_mask_count(c, 2 * B);
+    } else if (phase == 3) {
+        if (!noise_g || !g_grads) return fail("sg_train_step: G phase needs noise_g and g_grads");
+        SG_TRY(DISPATCH_T(c, cast_latents_t, c, noise_g, c->g_ws.p, B, s));
+    } else if (phase == 4) {
+        if (!g_grads) return fail("sg_train_step: G update needs g_grads");
+        if (c->mirror_g_step != st->g_step) sg::step_set(c->counters, 0, st->g_step, s);
+        c->mirror_g_step = st->g_step + 1;
+    } else {
+        return fail("sg_train_step: unknown phase %d", phase);
+    }
+    SG_KCHECK("sg_train_step(inputs)");
+    const bool use_graph = graphs_enabled() && !c->prof.on && !sync_bn_on(c);
+    if (!use_graph) return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.phase = phase;
+    key.B = B;
+    key.flags = (masks_injected ? 1 : 0) | (dropout ? 2 : 0);
+    const void* ptrs[10] = {st->g_params, st->g_running_stats, st->g_exp_avg, st->g_exp_avg_sq, st->d_params,
+                            st->d_exp_avg, st->d_exp_avg_sq, d_grads, g_grads, metrics};
+    memcpy(key.ptr, ptrs, sizeof(ptrs));
+    const float fl[8] = {st->g_lr, st->d_lr, st->beta1, st->beta2, st->eps, st->label_smoothing, st->dropout_p, st->grad_scale};
+    memcpy(key.f, fl, sizeof(fl));
+    key.seed = st->seed;
+    GraphEntry* ent = nullptr;
+    for (GraphEntry& g : c->graphs)
+        if (g.key == key) ent = &g;
+    if (!ent) {
+        if (c->graphs.size() >= 24) {  // evict the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < c->graphs.size(); ++i)
+                if (c->graphs[i].last < c->graphs[lru].last) lru = i;
+            if (c->graphs[lru].exec) cudaGraphExecDestroy(c->graphs[lru].exec);
+            c->graphs.erase(c->graphs.begin() + lru);
+        }
+        c->graphs.emplace_back();
+        ent = &c->graphs.back();
+        ent->key = key;
+    }
+    ent->last = ++c->graph_tick;
+    if (ent->exec && ent->epoch != g_alloc_epoch) {  // a library buffer moved since the capture
+        cudaGraphExecDestroy(ent->exec);
+        ent->exec = nullptr;
+        ent->seen = 0;
+    }
+    if (ent->bad || ent->seen == 0) {
+        // first sight of this configuration: run it eagerly (loads modules, sets kernel attributes, sizes buffers)
+        ent->seen = 1;
+        return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+    }
+    if (!ent->exec) {
+        if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+            return fail("sg_train_step: cannot create the capture stream");
+        cudaError_t e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ent->bad = true;
+            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+        }
+        const unsigned long long launches0 = sg::g_launches;
+        const int rc = train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, c->cap_stream);
+        ent->n_launches = static_cast<int>(sg::g_launches - launches0);
+        sg::g_launches = launches0;  // counted per graph launch below
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamEndCapture(c->cap_stream, &graph);
+        if (rc != 0 || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ent->bad = true;
+            if (rc != 0) return rc;
+            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+        }
+        e = cudaGraphInstantiate(&ent->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ent->exec = nullptr;
+            ent->bad = true;
+            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+        }
+        ent->epoch = g_alloc_epoch;
+    }
+    cudaError_t e = cudaGraphLaunch(ent->exec, s);
+    if (e != cudaSuccess) return fail("sg_train_step: cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+    sg::g_launches += static_cast<unsigned long long>(ent->n_launches);
+    return 0;
+}
 
 // ================================================================================================
 // extern "C"
@@ -820,6 +1091,7 @@ int sg_create(const sg_config* cfg, sg_ctx** out) {
     }
     sg_ctx* c = new sg_ctx();
     c->cfg = *cfg;
+    cudaGetDevice(&c->device);
     c->S = cfg->image_size;
     c->es = cfg->precision == SG_PREC_BF16 ? 2 : 4;
     c->Kp = (cfg->latent_dim + 63) / 64 * 64;
@@ -923,6 +1195,11 @@ int sg_create(const sg_config* cfg, sg_ctx** out) {
 
 void sg_destroy(sg_ctx* c) {
     if (!c) return;
+    DeviceGuard guard(c->device);
+    for (GraphEntry& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    c->counters_buf.release();
     DevBuf* bufs[] = {&c->packs, &c->bufA, &c->bufB, &c->dpre, &c->wpart, &c->cpart, &c->small,
                       &c->g_ws,  &c->d_ws, &c->x2,   &c->masks2, &c->dximg, &c->gws_tmp};
     for (DevBuf* b : bufs) b->release();
@@ -960,6 +1237,7 @@ int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, i
     if (!ws && !out_image && !out_u8) return fail("sg_g_forward: no output requested");
     if (bn_batch_stats && batch < 2)
         return fail("sg_g_forward: training-mode BatchNorm needs more than 1 value per channel (batch=%d)", batch);
+    DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SG_TRY(ensure_scratch(c, batch));
     bool save = ws != nullptr;
@@ -978,14 +1256,19 @@ int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, i
 int sg_g_backward(sg_ctx* c, const float* params, const void* ws, const float* grad_image, int batch,
                   int bn_batch_stats, float* grads_out, float* dz_out, void* stream) {
     if (!c || !params || !ws || !grad_image || !grads_out || batch < 1) return fail("sg_g_backward: bad argument");
+    DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SG_TRY(ensure_scratch(c, batch));
+    // the packs are context-global and belong to the latest forward: another Generator sharing this context (a second
+    // VanillaGAN, an EMA copy, an ablation model) may have run in between
+    if (c->g_pack_src != params) SG_TRY(pack_generator(c, params, s));
     return DISPATCH_T(c, g_backward_t, c, params, ws, grad_image, batch, bn_batch_stats, grads_out, dz_out, s);
 }
 
 int sg_d_forward(sg_ctx* c, const float* params, const float* x, int batch, const float* masks, void* ws,
                  float* prob_out, float* features_out, void* stream) {
     if (!c || !params || !x || batch < 1) return fail("sg_d_forward: bad argument");
+    DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SG_TRY(ensure_scratch(c, batch));
     if (!ws) {
@@ -998,6 +1281,7 @@ int sg_d_forward(sg_ctx* c, const float* params, const float* x, int batch, cons
 int sg_d_backward(sg_ctx* c, const float* params, const float* x, const void* ws, const float* masks,
                   const float* grad_prob, int batch, float* grads_out, float* dx_out, void* stream) {
     if (!c || !params || !x || !ws || !grad_prob || batch < 1) return fail("sg_d_backward: bad argument");
+    DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SG_TRY(ensure_scratch(c, batch));
     DWs w = carve_d(c, const_cast<void*>(ws), batch);
@@ -1010,12 +1294,14 @@ int sg_d_backward(sg_ctx* c, const float* params, const float* x, const void* ws
 
 int sg_dropout_masks(sg_ctx* c, uint64_t seed, uint64_t offset, int batch, float p, float* masks_out, void* stream) {
     if (!c || !masks_out || batch < 1 || !(p >= 0.f && p < 1.f)) return fail("sg_dropout_masks: bad argument");
+    DeviceGuard guard(c->device);
     sg::dropout_masks(seed, offset, sg_d_mask_count(c, batch), p, masks_out, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_dropout_masks");
     return 0;
 }
 
 int sg_bce_forward(const float* prob, const float* target, int n, float* loss_out, void* stream) {
+    PtrDeviceGuard guard(prob);
     if (!prob || !target || !loss_out || n < 1) return fail("sg_bce_forward: bad argument");
     sg::bce_forward(prob, target, n, loss_out, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_bce_forward");
@@ -1023,6 +1309,7 @@ int sg_bce_forward(const float* prob, const float* target, int n, float* loss_ou
 }
 int sg_bce_backward(const float* prob, const float* target, int n, const float* grad_loss, float* dprob_out,
                     void* stream) {
+    PtrDeviceGuard guard(prob);
     if (!prob || !target || !grad_loss || !dprob_out || n < 1) return fail("sg_bce_backward: bad argument");
     sg::bce_backward(prob, target, n, grad_loss, dprob_out, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_bce_backward");
@@ -1031,6 +1318,7 @@ int sg_bce_backward(const float* prob, const float* target, int n, const float* 
 
 int sg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                  float beta1, float beta2, float eps, long long step, void* stream) {
+    PtrDeviceGuard guard(params);
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail("sg_adam_step: bad argument");
     sg::adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
     SG_KCHECK("sg_adam_step");
@@ -1046,6 +1334,7 @@ int sg_augment_params(const double* host_angles, const double* host_scales, int 
 }
 int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed, const double* scale_affine,
                      const uint8_t* flip, int batch, int image_size, float* out, void* stream) {
+    PtrDeviceGuard guard(pool);
     if (!pool || !rot_fixed || !scale_affine || !out || batch < 1) return fail("sg_augment_batch: bad argument");
     if (image_size != 64 && image_size != 128)
         return fail("sg_augment_batch: image_size must be 64 or 128, got %d", image_size);
@@ -1058,6 +1347,7 @@ int sg_augment_batch(const uint8_t* pool, const int* index, const int* rot_fixed
 
 int sg_ink_stats(const float* images, int n_images, int pixels_per_image, float threshold, int* count_raw,
                  int* count_rescaled, float* minimum, void* stream) {
+    PtrDeviceGuard guard(images);
     if (!images || !count_raw || !count_rescaled || !minimum || n_images < 1 || pixels_per_image < 4 ||
         (pixels_per_image & 3) || (reinterpret_cast<uintptr_t>(images) & 15))
         return fail("sg_ink_stats: bad argument (pixels per image must be a multiple of 4, images 16-byte aligned)");
@@ -1080,6 +1370,7 @@ int sg_set_sync_batchnorm(sg_ctx* c, sg_allreduce_fn fn, void* user, int world_s
 
 int sg_spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, int cols, int power_iterations,
                             float eps, float* w_out, float* sigma_out, float* scratch, void* stream) {
+    PtrDeviceGuard guard(w_orig);
     if (!w_orig || !u || !v || !w_out || !sigma_out || !scratch || rows < 1 || cols < 1 || power_iterations < 0 ||
         !(eps > 0.f))
         return fail("sg_spectral_norm_weight: bad argument");
@@ -1090,6 +1381,7 @@ int sg_spectral_norm_weight(const float* w_orig, float* u, float* v, int rows, i
 }
 int sg_spectral_norm_backward(const float* w_eff, const float* u, const float* v, const float* sigma, int rows,
                               int cols, float* grad, float* scratch, void* stream) {
+    PtrDeviceGuard guard(w_eff);
     if (!w_eff || !u || !v || !sigma || !grad || !scratch || rows < 1 || cols < 1)
         return fail("sg_spectral_norm_backward: bad argument");
     sg::spectral_norm_backward(w_eff, u, v, sigma, rows, cols, grad, scratch, static_cast<cudaStream_t>(stream));
@@ -1100,7 +1392,9 @@ int sg_spectral_norm_backward(const float* w_eff, const float* u, const float* v
 int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
                   int B, float* d_grads, float* g_grads, float* metrics, int phase, void* stream) {
     if (!c || !st || !metrics || B < 2) return fail("sg_train_step: bad argument");
+    DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // ---- library-owned buffers (never grown inside a captured region) --------------------------------------------
     SG_TRY(ensure_scratch(c, 2 * B));
     const size_t img = (size_t)B * c->S * c->S;
     SG_TRY(c->x2.ensure(2 * img * 4));
@@ -1108,70 +1402,18 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
     SG_TRY(c->g_ws.ensure(sg_g_workspace_bytes(c, B)));
     SG_TRY(c->gws_tmp.ensure(sg_g_workspace_bytes(c, B)));
     SG_TRY(c->dximg.ensure(img * 4));
-    float* x2 = static_cast<float*>(c->x2.p);
-    const bool dropout = st->dropout_p > 0.f;
-    if (phase == 12) {
-        if (!d_grads) return fail("sg_train_step: D phase needs d_grads");
-        const float* masks = dropout ? static_cast<const float*>(c->masks2.p) : nullptr;
-        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s, 2));
+    if (st->dropout_p > 0.f) SG_TRY(c->masks2.ensure((size_t)sg_d_mask_count(c, 2 * B) * 4));
+    if (!c->counters) {
+        SG_TRY(c->counters_buf.ensure(sizeof(sg::StepCounters)));
+        c->counters = static_cast<sg::StepCounters*>(c->counters_buf.p);
+        cudaMemsetAsync(c->counters, 0, sizeof(sg::StepCounters), s);
     }
-    if (phase == 0 || phase == 1 || phase == 11) {
-        if (!real || !noise_d || !d_grads) return fail("sg_train_step: D phase needs real, noise_d and d_grads");
-        // ---- D step (train…:281-337): D.train(), G.eval(); one 2B batch [real | G(noise)] since D has no batch coupling
-        cudaError_t e = cudaMemcpyAsync(x2, real, img * 4, cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return fail("sg_train_step: copy of real batch failed: %s", cudaGetErrorString(e));
-        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, noise_d, B, 0, c->gws_tmp.p, x2 + img,
-                          nullptr, false, s));
-        const float* masks = nullptr;
-        if (dropout) {
-            SG_TRY(c->masks2.ensure((size_t)sg_d_mask_count(c, 2 * B) * 4));
-            float* m2 = static_cast<float*>(c->masks2.p);
-            if (st->masks_real && st->masks_fake) {
-                for (int i = 0; i < c->ND; ++i) {
-                    const size_t n = (size_t)B * c->dch[i + 1];
-                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i), st->masks_real + mask_offset(c, B, i), n * 4,
-                                    cudaMemcpyDeviceToDevice, s);
-                    cudaMemcpyAsync(m2 + mask_offset(c, 2 * B, i) + n, st->masks_fake + mask_offset(c, B, i), n * 4,
-                                    cudaMemcpyDeviceToDevice, s);
-                }
-            } else {
-                sg::dropout_masks(st->seed, st->offset, sg_d_mask_count(c, 2 * B), st->dropout_p, m2, s);
-            }
-            masks = m2;
-        }
-        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s));
-        DWs w = carve_d(c, c->d_ws.p, 2 * B);
-        sg::d_loss_metrics(w.prob, B, st->label_smoothing, metrics, c->dlogit, s);
-        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s,
-                          phase == 11 ? 1 : 0));
+    if (phase == 0) {
+        static const int seq[4] = {1, 2, 3, 4};
+        for (int ph : seq) SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, ph, s));
+        return 0;
     }
-    if (phase == 0 || phase == 2) {
-        if (!d_grads) return fail("sg_train_step: D update needs d_grads");
-        PROF("adam.d", 0, 28.0 * c->d_count);
-        sg::adam_step(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->d_lr, st->beta1, st->beta2,
-                      st->eps, st->d_step + 1, s);
-    }
-    if (phase == 0 || phase == 3) {
-        if (!noise_g || !g_grads) return fail("sg_train_step: G phase needs noise_g and g_grads");
-        // ---- G step (train…:339-376): G.train() (batch-stat BN), D.eval() (no dropout), labels = 1
-        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, noise_g, B, 1, c->g_ws.p, x2, nullptr,
-                          true, s));
-        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, B, nullptr, c->d_ws.p, nullptr, nullptr, s));
-        DWs w = carve_d(c, c->d_ws.p, B);
-        sg::g_loss_metrics(w.prob, B, metrics, c->dlogit, s);
-        float* dximg = static_cast<float*>(c->dximg.p);
-        // weight gradients of D are not needed here (the reference's autograd computes and discards them)
-        SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, nullptr, c->dlogit, B, nullptr, dximg, s));
-        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, dximg, B, 1, g_grads, nullptr, s));
-    }
-    if (phase == 0 || phase == 4) {
-        if (!g_grads) return fail("sg_train_step: G update needs g_grads");
-        PROF("adam.g", 0, 28.0 * c->g_count);
-        sg::adam_step(st->g_params, g_grads, st->g_exp_avg, st->g_exp_avg_sq, c->g_count, st->g_lr, st->beta1, st->beta2,
-                      st->eps, st->g_step + 1, s);
-    }
-    SG_KCHECK("sg_train_step");
-    return 0;
+    return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, phase, s);
 }
 
 }  // extern "C"

@@ -27,7 +27,8 @@
 
 namespace sg {
 
-void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream);
+void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream,
+                  const float* bias_partial = nullptr, float* dbias = nullptr);
 
 namespace {
 

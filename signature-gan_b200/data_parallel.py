@@ -23,30 +23,43 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def _mean_op(group=None):
+    """NCCL averages inside the collective (ncclAvg: no extra kernel); gloo has no AVG, there it is SUM + one scale."""
+    try:
+        if dist.get_backend(group) == "nccl":
+            return dist.ReduceOp.AVG, False
+    except Exception:
+        pass
+    return dist.ReduceOp.SUM, True
+
+
 def average_gradients_(flat_grad: torch.Tensor, group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
     """In place: flat_grad <- mean over ranks of flat_grad. A no-op for a single process."""
     if not (dist.is_available() and dist.is_initialized()):
         return flat_grad
     n = dist.get_world_size(group)
     if n > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-        flat_grad.mul_(1.0 / n)
+        op, scale = _mean_op(group)
+        dist.all_reduce(flat_grad, op=op, group=group)
+        if scale:
+            flat_grad.mul_(1.0 / n)
     return flat_grad
 
 
 def all_reduce_start(part: torch.Tensor, group: Optional["dist.ProcessGroup"] = None):
-    """Start summing `part` (a contiguous slice of a gradient bucket) over ranks without blocking the caller's stream:
+    """Start averaging `part` (a contiguous slice of a gradient bucket) over ranks without blocking the caller's stream:
     NCCL runs the collective on its own stream after the work already enqueued on the current stream, so kernels
     enqueued afterwards (the rest of the backward pass) overlap it. Returns a work handle for all_reduce_finish."""
-    return dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return dist.all_reduce(part, op=_mean_op(group)[0], group=group, async_op=True)
 
 
 def all_reduce_finish(works, flat_grad: torch.Tensor, group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
-    """Make the current stream wait for the started reductions, then turn the summed bucket into the mean."""
+    """Make the current stream wait for the started reductions; the bucket then holds the mean over ranks."""
     for w in works:
         if w is not None:
             w.wait()
-    flat_grad.mul_(1.0 / dist.get_world_size(group))
+    if _mean_op(group)[1]:
+        flat_grad.mul_(1.0 / dist.get_world_size(group))
     return flat_grad
 
 
