@@ -7,8 +7,9 @@
 One "step" = one full adversarial training step (D step + G step, vanilla_gan_model.VanillaGAN.train_step) over a
 batch of 4096 synthetic 64x64 signatures per GPU (BASELINE.json configs[2]); weak scaling over data-parallel ranks
 with an NCCL all-reduce of the flat D and G gradient buckets. Rank 0 prints ONE JSON line.
-`--impl reference` times the CPU implementation of the same step (the oracle port of the reference's algorithm, torch
-CPU fp32, all host threads) on a bounded sample (batch 64 per step, the reference's own default configuration).
+`--impl reference` times the reference's own CPU implementation of the same step (the unmodified reference modules
+from oracle/_ref — see oracle/make_ref.py — torch CPU fp32, all host threads) on a bounded sample (batch 64 per step,
+the reference's own default configuration).
 """
 import argparse
 import json
@@ -40,6 +41,7 @@ def parse():
     ap.add_argument("--sampling-batch", type=int, default=16384)
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / cpu baseline / per-op profile")
+    ap.add_argument("--cpu-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--sync-bn", action="store_true", help="N > 1: global-batch BatchNorm statistics (sg_set_sync_batchnorm)")
     return ap.parse_args()
 
@@ -136,32 +138,103 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's D step + G step (torch CPU fp32, all host threads)
+# CPU arm: the UNMODIFIED reference (oracle/_ref, built by oracle/make_ref.py) on the host cores — its own
+# VanillaGAN(device='cpu').train_step / .generate (vanilla…:308-371), torch CPU fp32, all host threads. Falls back to
+# the oracle port of the same algorithm (kind "port") only when oracle/_ref is absent.
 # ------------------------------------------------------------------------------------------------
-def cpu_train_imgs_per_s(size, batch, steps, warmup):
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _import_reference():
+    """The reference's vanilla_gan_model from oracle/_ref/src (first on sys.path so that its own generator_ /
+    discriminator_ modules resolve to the reference's, not to this repo's drop-ins). None when the copy is absent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import make_ref
+        ref_src = make_ref.src_dir()
+    except Exception:
+        return None
+    if "vanilla_gan_model" in sys.modules:      # this process already holds the drop-in modules: cannot mix
+        return None
+    sys.path.insert(0, ref_src)
+    import vanilla_gan_model as R
+    assert os.path.realpath(R.__file__).startswith(os.path.realpath(ref_src)), R.__file__
+    return R
+
+
+def cpu_reference_numbers(size, batch, steps, warmup, sampling=True):
+    """Runs in a process of its own (see cpu_baseline_subprocess): times the reference on the host CPU."""
     import torch
+    threads = host_threads()
+    torch.set_num_threads(threads)        # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
+    R = _import_reference()
+    out = {"cores": threads, "torch_threads": torch.get_num_threads()}
+    real = synthetic_signatures(4 * batch, size, "cpu", seed=1234).view(4, batch, 1, size, size)
+    if R is not None:
+        torch.manual_seed(0)
+        gan = R.VanillaGAN(latent_dim=100, image_size=size, device="cpu")
+        for i in range(warmup):
+            gan.train_step(real[i % 4])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            m = gan.train_step(real[i % 4])
+        dt = time.perf_counter() - t0
+        out.update({"kind": "reference", "train_images_per_s": batch * steps / dt, "s_per_step": dt / steps,
+                    "last": {k: float(v) for k, v in m.items()},
+                    "sample": f"{steps} VanillaGAN(device='cpu').train_step calls of the unmodified reference "
+                              f"(oracle/_ref), batch {batch} ({size}x{size}), {warmup} warm-up, torch CPU fp32, "
+                              f"{threads} threads"})
+        if sampling:
+            gan.generate(64)
+            t0 = time.perf_counter()
+            n_s, reps = 1024, 5
+            for _ in range(reps):
+                gan.generate(n_s)
+            dt = time.perf_counter() - t0
+            out["sampling"] = {"value": n_s * reps / dt, "unit": "images/s", "cores": threads, "kind": "reference",
+                               "sample": f"{reps} x VanillaGAN(device='cpu').generate({n_s}) of the unmodified "
+                                         f"reference, {size}x{size}, torch CPU fp32"}
+        return out
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import siggan_oracle as O
     g_sd, d_sd = O.make_state_dicts(size, 100, seed=0)
     g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
     d_opt = O.AdamState(d_sd, O.trainable_names(d_sd))
-    real = O.synthetic_signatures(batch, size, seed=1234)
     t0 = None
     for i in range(warmup + steps):
         if i == warmup:
             t0 = time.perf_counter()
         masks_r, masks_f = O.make_dropout_masks(batch, size, 2 * i), O.make_dropout_masks(batch, size, 2 * i + 1)
-        O.d_step(g_sd, d_sd, d_opt, real, torch.randn(batch, 100), size, masks_r, masks_f)
+        O.d_step(g_sd, d_sd, d_opt, real[i % 4], torch.randn(batch, 100), size, masks_r, masks_f)
         O.g_step(g_sd, d_sd, g_opt, torch.randn(batch, 100), size)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    out.update({"kind": "port", "train_images_per_s": batch * steps / dt, "s_per_step": dt / steps,
+                "sample": f"{steps} D+G steps of the oracle port (oracle/_ref absent), batch {batch} ({size}x{size}), "
+                          f"torch CPU fp32, {threads} threads"})
+    return out
+
+
+def cpu_baseline_subprocess(size, batch, steps, warmup, sampling=True):
+    """The GPU arm's process has this repo's drop-in modules loaded under the reference's module names, so the CPU
+    baseline runs in a child process (`bench.py --cpu-child`), which prints one JSON object."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", "--size", str(size), "--cpu-batch", str(batch),
+           "--steps", str(steps), "--warmup", str(warmup)] + ([] if sampling else ["--no-extras"])
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError("cpu baseline child failed: " + r.stderr.decode()[-400:])
+    return json.loads(r.stdout.decode().strip().splitlines()[-1])
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    ips, spp, threads = cpu_train_imgs_per_s(args.size, args.cpu_batch, args.steps, args.warmup)
-    sample = f"{args.steps} steps of batch {args.cpu_batch} ({args.size}x{args.size}) on the host CPU, {args.warmup} warm-up"
+    r = cpu_reference_numbers(args.size, args.cpu_batch, args.steps, args.warmup, sampling=False)
+    ips, spp = r["train_images_per_s"], r["s_per_step"]
     line = {
         "impl": "reference", "metric": "training images/sec (G+D step)", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3,
@@ -169,9 +242,10 @@ def run_reference(args, rank):
         "config": {"workload": f"train_step_{args.size}x{args.size}_b{args.batch}_per_gpu",
                    "global_batch": args.gpus * args.batch, "image_size": args.size, "latent_dim": 100,
                    "parallelism": f"dp{args.gpus}", "n_critic": 1, "cpu_sample_batch": args.cpu_batch,
-                   "note": "the reference is pure PyTorch: its CPU implementation of the step (oracle port of the same "
-                           "algorithm, torch CPU fp32, all host threads) timed on a bounded sample of the workload"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+                   "note": "the reference's own CPU implementation of the step (unmodified modules from oracle/_ref, "
+                           "torch CPU fp32, all host threads) timed on a bounded sample of the workload: batch "
+                           f"{args.cpu_batch} per step, the reference's default configuration"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -526,13 +600,16 @@ def run_ours(args, rank, local_rank, world):
         if rank == 0:
             line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1),
                                                              gan=gan if world == 1 else None)
-        # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------
+        # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference on the host cores, bounded sample ----
         if rank == 0 and world == 1:
-            steps_cpu = 12
-            ips, spp, threads = cpu_train_imgs_per_s(S, args.cpu_batch, steps_cpu, 2)
-            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": f"{steps_cpu} D+G steps of batch {args.cpu_batch} ({S}x{S}), torch CPU fp32, "
-                                              f"{os.cpu_count()} logical cpus"}
+            try:
+                r = cpu_baseline_subprocess(S, args.cpu_batch, 12, 2, sampling=True)
+                line["cpu_baseline"] = {"value": r["train_images_per_s"], "unit": "images/s", "cores": r["cores"],
+                                        "kind": r["kind"], "sample": r["sample"]}
+                if "sampling" in r and "sampling" in line:
+                    line["sampling"]["cpu_baseline"] = r["sampling"]
+            except Exception as e:
+                line["cpu_baseline"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
@@ -561,6 +638,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.cpu_child:
+        print(json.dumps(cpu_reference_numbers(args.size, args.cpu_batch, args.steps, args.warmup,
+                                               sampling=not args.no_extras)), file=RESULT_OUT, flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -84,6 +84,29 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
     return 0;
 }
 
+// Generic tiled map over bf16 elements: dims / box innermost first, strides_bytes[i] = stride of dimension i + 1.
+int make_map_tiled(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SG_FAIL("cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i + 1 < rank) gstr[i] = strides_bytes[i];
+    }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SG_FAIL("cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r);
+    return 0;
+}
+
 // ----------------------------------------------------------------------------
 // Forward / dgrad implicit GEMM — persistent, warp-specialised
 //
@@ -630,8 +653,32 @@ static bool conv2_enabled() {  // SIGGAN_CONV2=0 keeps every layer on the one-CT
     return v;
 }
 
+// sg_convs2_thin.cu
+bool convs2_thin_supported(int inH, int inW, int Cin, int Cout);
+size_t convs2_thin_scratch_bytes();
+int launch_convs2_thin(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
+                       __nv_bfloat16* out, const __nv_bfloat16* gate, float slope, void* scratch, cudaStream_t stream);
+static void* thin_scratch() {  // stacked weights of the thin stride-2 kernel, one buffer per device
+    static void* buf[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return nullptr;
+    if (!buf[dev] && cudaMalloc(&buf[dev], convs2_thin_scratch_bytes()) != cudaSuccess) buf[dev] = nullptr;
+    return buf[dev];
+}
+
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
+    if (mode == kConvS2 && convs2_thin_supported(inH, inW, Cin, Cout) && !a.bias && !a.scale && !a.mask &&
+        !a.stats_partial && a.act == kActNone && a.ldo == Cout) {
+        // thin fine-grid tensors (generator's last block, data gradient): pixel-pair rows + col2im epilogue
+        void* scratch = thin_scratch();
+        if (!scratch) SG_FAIL("convs2_thin: cannot allocate the weight scratch");
+        if (launch_convs2_thin(in, w_packed, nimg, inH, inW, static_cast<__nv_bfloat16*>(a.out), a.gate, a.slope, scratch,
+                               stream))
+            SG_FAIL("convs2_thin launch failed: %s (%s)", cudaGetErrorString(cudaGetLastError()), umma_last_error());
+        return 0;
+    }
     if (mode != kPlain && !a.stats_partial && a.ldo == Cout && conv2_enabled() &&
         conv2_supported(mode, inH, inW, Cin, Cout)) {
         // CTA-pair kernel with shared shifted-input tiles (D conv1 forward, D conv1 / conv2 data gradients)
@@ -736,7 +783,9 @@ constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epil
 // Fused bias gradient (Discriminator conv blocks, disc…:51-58): dbias[m] = sum_pix coarse[pix][m] is one more product of
 // the staged coarse tile, with a constant all-ones B operand (16 pixel rows x 128 bytes of bf16 1.0 — all ones, so
 // neither the swizzle nor the MN-major atom layout matters) accumulated into 16 extra TMEM columns by the CTAs of the
-// first tap group. It replaces a separate column-reduction pass over dy (0.22 ms per step at B = 4096).
+// CTAs (tile_m, y, split), y = 0..ny-1, for the K steps `it % ny == y` — spread over all tap groups, because the extra
+// product re-reads the 4 KB A operand (~32 clk against the 128 clk of a 256-column product) and a launch is as slow as
+// its slowest CTA. It replaces a separate column-reduction pass over dy (0.22 ms per step at B = 4096).
 constexpr int kOnesBytes = 2048;
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -769,7 +818,8 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
     const int tile_m = blockIdx.x;
     const int n_tiles = (args.Nf + BN - 1) / BN;
     const int taps = args.plain ? 1 : 16;
-    const bool do_bias = args.bias_partial != nullptr && blockIdx.y == 0;
+    const bool do_bias = args.bias_partial != nullptr;
+    const int ny = gridDim.y, by = blockIdx.y;
     const uint32_t tmem_cols = do_bias ? Cfg::kTmemColsBias : Cfg::kTmemCols;
     if (do_bias) {
         for (int i = threadIdx.x; i < kOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
@@ -871,13 +921,13 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
                     const uint64_t db = make_smem_desc(b_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
                     umma_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
                 }
-                if (do_bias) {
+                if (do_bias && it % ny == by) {
                     constexpr uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 1);
                     const uint64_t d1 = make_smem_desc(smem_u32(ones), Cfg::kAtomBytes, 1024, kLayoutSW128);
 #pragma unroll
                     for (int k = 0; k < kWgK / 16; ++k) {
                         const uint64_t da = make_smem_desc(a_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
-                        umma_bf16_ss(tmem_base + BN, da, d1, idesc_b, (it | k) != 0);
+                        umma_bf16_ss(tmem_base + BN, da, d1, idesc_b, (it != by) || k != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -898,12 +948,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_umma_kernel(const __grid_con
         if (do_bias) {
             uint32_t v[32];
             float b = 0.f;
-            if (num_k > 0) {
+            if (num_k > by) {  // this CTA issued at least one bias product (K step `by`)
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN, v);
                 tmem_ld_wait();
                 b = __uint_as_float(v[0]);
             }
-            if (m < args.Mc) args.bias_partial[static_cast<size_t>(split) * args.Mc + m] = b;
+            if (m < args.Mc) args.bias_partial[(static_cast<size_t>(split) * ny + by) * args.Mc + m] = b;
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -964,7 +1014,8 @@ __global__ void __launch_bounds__(kWgThreads) wgrad2_umma_kernel(const __grid_co
     const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const bool do_bias = args.bias_partial != nullptr && blockIdx.y == 0;
+    const bool do_bias = args.bias_partial != nullptr;
+    const int ny = gridDim.y, by = blockIdx.y;
     const uint32_t tmem_cols = do_bias ? Cfg::kTmemColsBias : Cfg::kTmemCols;
     if (do_bias) {  // both CTAs of the pair: each provides its half of the (all-ones) B operand
         for (int i = threadIdx.x; i < kOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
@@ -1062,13 +1113,13 @@ __global__ void __launch_bounds__(kWgThreads) wgrad2_umma_kernel(const __grid_co
                         const uint64_t db = make_smem_desc(b_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
                         umma2_bf16_ss(tmem_base, da, db, idesc, (it | k) != 0);
                     }
-                    if (do_bias) {
+                    if (do_bias && it % ny == by) {
                         constexpr uint32_t idesc_b = make_idesc_bf16(256, 16, 1, 1);
                         const uint64_t d1 = make_smem_desc(smem_u32(ones), Cfg::kAtomBytes, 1024, kLayoutSW128);
 #pragma unroll
                         for (int k = 0; k < kWgK / 16; ++k) {
                             const uint64_t da = make_smem_desc(a_addr + k * 2048, Cfg::kAtomBytes, 1024, kLayoutSW128);
-                            umma2_bf16_ss(tmem_base + BN, da, d1, idesc_b, (it | k) != 0);
+                            umma2_bf16_ss(tmem_base + BN, da, d1, idesc_b, (it != by) || k != 0);
                         }
                     }
                     umma2_commit(&empty_bar[s]);
@@ -1090,12 +1141,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad2_umma_kernel(const __grid_co
         if (do_bias) {
             uint32_t v[32];
             float b = 0.f;
-            if (num_k > 0) {
+            if (num_k > by) {
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN, v);
                 tmem_ld_wait();
                 b = __uint_as_float(v[0]);
             }
-            if (m < args.Mc) args.bias_partial[static_cast<size_t>(split) * args.Mc + m] = b;
+            if (m < args.Mc) args.bias_partial[(static_cast<size_t>(split) * ny + by) * args.Mc + m] = b;
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -1127,12 +1178,13 @@ __global__ void __launch_bounds__(kWgThreads) wgrad2_umma_kernel(const __grid_co
 
 // partial [S][16][M][N] -> dW [M][N][16]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int S, int M, int N,
-                                    int accumulate, const float* __restrict__ bias_partial, float* __restrict__ dbias) {
+                                    int accumulate, const float* __restrict__ bias_partial, float* __restrict__ dbias,
+                                    int SB) {
     const long total = static_cast<long>(M) * N * 16;
-    if (dbias && blockIdx.x == 0) {  // fused bias gradient: [S][M] partial sums
+    if (dbias && blockIdx.x == gridDim.x - 1) {  // fused bias gradient: [SB][M] partial sums
         for (int m = threadIdx.x; m < M; m += blockDim.x) {
             float acc = 0.f;
-            for (int s = 0; s < S; ++s) acc += bias_partial[static_cast<size_t>(s) * M + m];
+            for (int s = 0; s < SB; ++s) acc += bias_partial[static_cast<size_t>(s) * M + m];
             dbias[m] = acc;
         }
     }
@@ -1151,12 +1203,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 }
 
 void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream,
-                  const float* bias_partial, float* dbias) {
+                  const float* bias_partial, float* dbias, int SB) {
     const long total = static_cast<long>(M) * N * 16;
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     note_launch();
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, S, M, N, accumulate, bias_partial, dbias);
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, S, M, N, accumulate, bias_partial, dbias, SB);
 }
 
 // sg_wgrad_thin.cu
@@ -1164,6 +1216,12 @@ bool wgrad_thin_supported(int cH, int cW, int Mc, int Nf);
 int wgrad_thin_ctas(int nimg, int cH, int cW);
 int launch_wgrad_thin(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc, int Nf,
                       float* partial, float* dW, int accumulate, cudaStream_t stream);
+
+// sg_wgrad_pair.cu
+bool wgrad_pair_supported(int cH, int cW, int Mc, int Nf);
+int wgrad_pair_ctas(int nimg, int cH);
+int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, float* partial,
+                      float* dW, int accumulate, cudaStream_t stream);
 
 static bool wgrad_pairs(int Mc, int Nf);
 // Split-K factor: the launch is base * s CTAs (or CTA pairs) of one tile each on `slots` resident CTAs (pairs). Pick
@@ -1207,7 +1265,7 @@ size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf) {
     const int BN = wgrad_bn(Nf);
     const int s = wgrad_splits(k_tiles, (Mc + 127) / 128, (Nf + BN - 1) / BN, 16 / wgrad_tpc(Nf), wgrad_pairs(Mc, Nf), BN,
                                64.0 * Mc * Nf);
-    return static_cast<size_t>(s) * 16 * Mc * Nf + static_cast<size_t>(s) * Mc;  // + fused bias-gradient partials
+    return static_cast<size_t>(s) * 16 * Mc * Nf + static_cast<size_t>(s) * 16 * Mc;  // + fused bias-gradient partials
 }
 
 template <int BN>
@@ -1231,6 +1289,14 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
                  float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream, float* dbias) {
     if (!is_pow2(cH) || !is_pow2(cW) || cW > kWgK) SG_FAIL("wgrad: coarse grid %dx%d unsupported", cH, cW);
     if (Mc % 8 != 0 || Nf % 8 != 0) SG_FAIL("wgrad: channels must be multiples of 8 (Mc=%d Nf=%d)", Mc, Nf);
+    if (wgrad_pair_supported(cH, cW, Mc, Nf)) {  // generator's last block: pixel-pair formulation on tcgen05
+        if (dbias) SG_FAIL("wgrad: the pair kernel has no fused bias gradient");
+        if (static_cast<size_t>(wgrad_pair_ctas(nimg, cH)) * 16 * Mc * Nf > partial_floats)
+            SG_FAIL("wgrad: partial workspace too small");
+        if (launch_wgrad_pair(coarse, fine, nimg, cH, cW, partial, dW, accumulate, stream))
+            SG_FAIL("wgrad_pair launch failed: %s (%s)", cudaGetErrorString(cudaGetLastError()), umma_last_error());
+        return 0;
+    }
     if (wgrad_thin_supported(cH, cW, Mc, Nf)) {  // thin layers: every pixel row staged once, mma.sync + ldmatrix
         if (wgrad_partial_floats(nimg, cH, cW, Mc, Nf) > partial_floats) SG_FAIL("wgrad: partial workspace too small");
         if (dbias) SG_FAIL("wgrad: the thin kernel has no fused bias gradient");
@@ -1253,7 +1319,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     a.splits = wgrad_splits(a.k_tiles, m_tiles, n_tiles, 16 / a.tpc, wgrad_pairs(Mc, Nf), BN, 64.0 * Mc * Nf);
     a.partial = partial;
     const size_t w_floats = static_cast<size_t>(a.splits) * 16 * Mc * Nf;
-    if (w_floats + (dbias ? static_cast<size_t>(a.splits) * Mc : 0) > partial_floats)
+    if (w_floats + (dbias ? static_cast<size_t>(a.splits) * 16 * Mc : 0) > partial_floats)
         SG_FAIL("wgrad: partial workspace too small");
     a.bias_partial = dbias ? partial + w_floats : nullptr;
     if (make_map_2d(&a.cmap, coarse, Mc, pix, Mc, 64, kWgK)) return -1;
@@ -1295,7 +1361,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     else
         rc = launch_wg<64>(a, grid, stream);
     if (rc) return rc;
-    wgrad_reduce(partial, dW, a.splits, Mc, Nf, accumulate, stream, a.bias_partial, dbias);
+    wgrad_reduce(partial, dW, a.splits, Mc, Nf, accumulate, stream, a.bias_partial, dbias, a.splits * static_cast<int>(grid.y));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) SG_FAIL("wgrad_reduce launch: %s", cudaGetErrorString(e));
     return 0;

@@ -74,7 +74,10 @@ void pack_classifier(const float* w, float* wp, int C, cudaStream_t s) {
 // shared memory in 32 x 32 x 16 tiles so that both packed layouts are written in 64-byte runs; the fc / classifier
 // permutations are small elementwise sections (4096 elements per block).
 __global__ void __launch_bounds__(256) pack_plan_kernel(const __grid_constant__ PackPlan plan) {
-    __shared__ bf16 tile[32 * 32 * 16 + 64];
+    // w16 tile: 16 a x 32 b x 16 taps, rows of (b, tap) padded by one 4-byte word against bank conflicts of the
+    // transposed reads
+    constexpr int kRow = 32 * 16 + 2;
+    __shared__ bf16 tile[16 * kRow];
     int sidx = 0;
     while (sidx + 1 < plan.nseg && static_cast<int>(blockIdx.x) >= plan.seg[sidx + 1].tile0) ++sidx;
     const PackSeg& sg_ = plan.seg[sidx];
@@ -83,23 +86,32 @@ __global__ void __launch_bounds__(256) pack_plan_kernel(const __grid_constant__ 
     if (sg_.kind == 0) {
         const int A = sg_.A, B = sg_.B;
         const int bt = B / 32;
-        const int a0 = (t_local / bt) * 32, b0 = (t_local % bt) * 32;
+        const int a0 = (t_local / bt) * 16, b0 = (t_local % bt) * 32;
         // load: for each a, the 32 b's x 16 taps are 512 contiguous floats
-        for (int e = tid; e < 32 * 512; e += 256) {
-            const int a = e >> 9, r = e & 511;
-            tile[a * 512 + r] = __float2bfloat16(sg_.src[(static_cast<long>(a0 + a) * B + b0) * 16 + r]);
+        for (int e = tid; e < 16 * 128; e += 256) {
+            const int a = e >> 7, r4 = (e & 127) * 4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(sg_.src + (static_cast<long>(a0 + a) * B + b0) * 16 + r4));
+            __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&tile[a * kRow + r4]);
+            d[0] = __floats2bfloat162_rn(v.x, v.y);
+            d[1] = __floats2bfloat162_rn(v.z, v.w);
         }
         __syncthreads();
-        if (sg_.ab) {  // [a][t][b]: 32 b's contiguous
-            for (int e = tid; e < 32 * 16 * 32; e += 256) {
-                const int b = e & 31, t = (e >> 5) & 15, a = e >> 9;
-                sg_.ab[(static_cast<long>(a0 + a) * 16 + t) * B + b0 + b] = tile[a * 512 + b * 16 + t];
+        if (sg_.ab) {  // [a][t][b]: 32 b's contiguous, written as bf16 pairs
+            for (int e = tid; e < 16 * 16 * 16; e += 256) {
+                const int b2 = (e & 15) * 2, t = (e >> 4) & 15, a = e >> 8;
+                __nv_bfloat162 v;
+                v.x = tile[a * kRow + b2 * 16 + t];
+                v.y = tile[a * kRow + (b2 + 1) * 16 + t];
+                *reinterpret_cast<__nv_bfloat162*>(&sg_.ab[(static_cast<long>(a0 + a) * 16 + t) * B + b0 + b2]) = v;
             }
         }
-        if (sg_.ba) {  // [b][t][a]: 32 a's contiguous
-            for (int e = tid; e < 32 * 16 * 32; e += 256) {
-                const int a = e & 31, t = (e >> 5) & 15, b = e >> 9;
-                sg_.ba[(static_cast<long>(b0 + b) * 16 + t) * A + a0 + a] = tile[a * 512 + b * 16 + t];
+        if (sg_.ba) {  // [b][t][a]: 16 a's contiguous
+            for (int e = tid; e < 32 * 16 * 8; e += 256) {
+                const int a2 = (e & 7) * 2, t = (e >> 3) & 15, b = e >> 7;
+                __nv_bfloat162 v;
+                v.x = tile[a2 * kRow + b * 16 + t];
+                v.y = tile[(a2 + 1) * kRow + b * 16 + t];
+                *reinterpret_cast<__nv_bfloat162*>(&sg_.ba[(static_cast<long>(b0 + b) * 16 + t) * A + a0 + a2]) = v;
             }
         }
     } else if (sg_.kind == 1) {  // generator fc: rows permuted NCHW feature -> NHWC column, K padded
@@ -123,7 +135,7 @@ int pack_plan_add_w16(PackPlan& p, const float* src, bf16* ab, bf16* ba, int A, 
     PackSeg& s = p.seg[p.nseg++];
     s = PackSeg{};
     s.src = src; s.ab = ab; s.ba = ba; s.A = A; s.B = B; s.kind = 0; s.tile0 = p.total_tiles;
-    p.total_tiles += (A / 32) * (B / 32);
+    p.total_tiles += (A / 16) * (B / 32);
     return 0;
 }
 int pack_plan_add_fc(PackPlan& p, const float* W, const float* bias, bf16* Wp, float* biasp, int C0, int latent, int Kp) {

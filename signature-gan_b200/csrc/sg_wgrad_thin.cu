@@ -28,7 +28,7 @@
 namespace sg {
 
 void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream,
-                  const float* bias_partial = nullptr, float* dbias = nullptr);
+                  const float* bias_partial = nullptr, float* dbias = nullptr, int SB = 0);
 
 namespace {
 

@@ -199,7 +199,12 @@ static int test_conv(const char* name, sg::ConvMode mode, int N, int H, int W, i
     a.ldo = Cout;
     float *bias = nullptr, *mask = nullptr;
     Dev gate;
-    if (epi) {
+    if (epi == 3) {  // ReLU gate only (Generator data gradients)
+        gate.init(out_n, 1.0f);
+        a.gate = gate.d;
+        a.slope = 0.f;
+        for (size_t i = 0; i < out_n; ++i) ref[i] *= gate.h[i] > 0 ? 1.f : 0.f;
+    } else if (epi) {
         std::vector<float> hb(Cout), hm((size_t)N * Cout);
         for (auto& v : hb) v = frand() * 0.5f;
         for (auto& v : hm) v = frand() > -0.5f ? 4.f / 3.f : 0.f;
@@ -588,6 +593,8 @@ int main(int argc, char** argv) {
     RUN(test_wgrad("wgrad 8x8x8 256|128", 8, 8, 8, 256, 128));
     RUN(test_wgrad("wgrad 2x32x32 32|32 (thin)", 2, 32, 32, 32, 32));
     RUN(test_wgrad("wgrad 3x16x16 64|32 (thin)", 3, 16, 16, 64, 32));
+    RUN(test_wgrad("wgrad 1x32x32 32|32 (pair)", 1, 32, 32, 32, 32));
+    RUN(test_wgrad("wgrad 70x32x32 32|32 (pair, 560 t)", 70, 32, 32, 32, 32));
     RUN(test_wgrad("wgrad 5x4x4 256|128 (tail)", 5, 4, 4, 256, 128));
     // CTA-pair kernels (sg_conv2_umma.cu): D conv1 forward and the D conv1 / conv2 data-gradient shapes, with tails
     RUN(test_conv("conv2 S2 3x32x32x64->128 +epi", sg::kConvS2, 3, 32, 32, 64, 128, true));
@@ -600,6 +607,10 @@ int main(int argc, char** argv) {
     RUN(test_conv("conv2 T4 3x32x32x128->64 +epi", sg::kConvT, 3, 32, 32, 128, 64, true));
     RUN(test_conv("conv2 T2 7x8x8x256->128 +epi", sg::kConvT, 7, 8, 8, 256, 128, true));
     RUN(test_conv("conv2 T2 341x8x8x256->128", sg::kConvT, 341, 8, 8, 256, 128, true));
+    // pixel-pair stride-2 kernel with col2im epilogue (sg_convs2_thin.cu): generator's last block, data gradient
+    RUN(test_conv("convS2 thin 1x64x64x32->32", sg::kConvS2, 1, 64, 64, 32, 32, false));
+    RUN(test_conv("convS2 thin 5x64x64x32->32 +gate", sg::kConvS2, 5, 64, 64, 32, 32, 3));
+    RUN(test_conv("convS2 thin 100x64x64x32->32 +gate (800 t)", sg::kConvS2, 100, 64, 64, 32, 32, 3));
     RUN(test_gfinal("gfinal 5x64 train", 5, 64, true, false));
     RUN(test_gfinal("gfinal 3x64 eval", 3, 64, false, false));
     RUN(test_gfinal("gfinal 3x128 train", 3, 128, true, false));
@@ -614,6 +625,8 @@ int main(int argc, char** argv) {
         perf_conv("G up1 128->64 @8x8", sg::kConvT, B, 8, 8, 128, 64);
         perf_conv("G up2 64->32 @16x16", sg::kConvT, B, 16, 16, 64, 32);
         perf_conv("G up3 32->32 @32x32", sg::kConvT, B, 32, 32, 32, 32);
+        perf_conv("G up3 dgrad 32->32 @64x64 +gate", sg::kConvS2, B, 64, 64, 32, 32, 3);
+        perf_conv("G up2 dgrad 32->64 @32x32 +gate", sg::kConvS2, B, 32, 32, 32, 64, 3);
         perf_conv("D dgrad c3 512->256 @4x4", sg::kConvT, B, 4, 4, 512, 256);
         perf_conv("D dgrad c2 256->128 @8x8", sg::kConvT, B, 8, 8, 256, 128);
         perf_conv("D dgrad c1 128->64 @16x16", sg::kConvT, B, 16, 16, 128, 64);
