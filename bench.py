@@ -540,6 +540,10 @@ def run_ours(args, rank, local_rank, world):
                                 "traffic_source": traffic_src, "ms_per_launch": a[0] / a[3], "share_of_step": a[0] / tot,
                                 "peak_source": pk["source"]}
         line["ops_ms_per_step"] = {k: round(a[0] / prof_steps, 4) for k, a in ops}
+        # per op: achieved TFLOP/s on its algorithmic flops and GB/s on its algorithmic bytes
+        line["ops_detail"] = {k: {"tflops": round(a[1] / (a[0] * 1e-3) / 1e12, 1) if a[1] else None,
+                                  "gbs": round(a[2] / (a[0] * 1e-3) / 1e9, 0) if a[2] else None,
+                                  "launches_per_step": a[3] / prof_steps} for k, a in ops if a[0] > 0}
         line["ops_total_ms_per_step"] = tot / prof_steps
         tens = sum(a[0] for k, a in tensor_ops)
         tfl = sum(a[1] for k, a in tensor_ops)

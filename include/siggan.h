@@ -91,6 +91,21 @@ int sg_d_forward(sg_ctx* ctx, const float* params, const float* x, int batch, co
 /* grads_out NULL => skip weight gradients; dx_out NULL => skip the image gradient. */
 int sg_d_backward(sg_ctx* ctx, const float* params, const float* x, const void* ws, const float* masks,
                   const float* grad_prob, int batch, float* grads_out, float* dx_out, void* stream);
+/* ---- one layer of a backward pass (parity tests: tests/test_gpu_layers.py feeds each layer the oracle's exact upstream
+ * gradient). These run the same launchers as sg_d_backward / sg_g_backward on ONE unit of the chain; `ws` must come from
+ * the matching forward. Activation-shaped tensors are NHWC in the context's activation type (bf16, or fp32 in
+ * validation mode). Only the gradient entries of the unit's own parameters are written to grads_out.
+ * Discriminator units: layer = number of conv blocks -> classifier (dz_in = d loss / d probability, fp32 (batch));
+ * layer 1.. -> conv block `layer`; layer 0 -> first block (dx_out = image gradient, fp32). dz_in / dz_prev_out = gradient
+ * w.r.t. the block's convolution output, i.e. after the LeakyReLU derivative and the dropout mask (disc…:51-75). */
+int sg_d_backward_layer(sg_ctx* ctx, const float* params, const float* x, const void* ws, const float* masks, int layer,
+                        const void* dz_in, int batch, float* grads_out, void* dz_prev_out, float* dx_out, void* stream);
+/* Generator units: level = number of upsample blocks - 1 -> final Conv3x3 + tanh and the last block together (d_in =
+ * d loss / d image, fp32); 0 <= level below that -> upsample block `level`; -1 -> the fc stage. d_in / d_prev_out =
+ * gradient w.r.t. the stage's BatchNorm output with the ReLU derivative applied (gen…:58-60, 126-127). */
+int sg_g_backward_layer(sg_ctx* ctx, const float* params, const void* ws, int level, const void* d_in, int batch,
+                        int bn_batch_stats, float* grads_out, void* d_prev_out, void* stream);
+
 /* Fills masks with {0, 1/(1-p)} from a counter-based generator (seed, offset). */
 int sg_dropout_masks(sg_ctx* ctx, uint64_t seed, uint64_t offset, int batch, float p, float* masks_out, void* stream);
 

@@ -9,8 +9,7 @@ the CUDA path have an independent checker. Only `tests/`, `__graft_entry__.smoke
 Pinning: the reference ships no golden vectors or value-asserting tests, so the
 oracle is pinned against outputs of the reference itself, produced in the build container by
 `tests/golden/make_golden.py` (which imports /root/reference/src unmodified) and committed under
-`tests/golden/`. `tests/test_oracle_golden.py` checks the oracle against them; where the reference
-tree is mounted, `tests/test_oracle_vs_reference.py` additionally runs both side by side.
+`tests/golden/`. `tests/test_oracle_golden.py` checks the oracle against them.
 
 Parameters travel as a dict keyed exactly like the reference's `state_dict()`:
   G: fc.0.{weight,bias} fc.1.{weight,bias,running_mean,running_var,num_batches_tracked}
@@ -116,8 +115,10 @@ def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: boo
 
 
 def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, image_size: int = 64,
-               train: bool = True) -> Dict[str, Tensor]:
-    """Gradients of every Generator parameter given d(loss)/d(image)."""
+               train: bool = True, taps: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    """Gradients of every Generator parameter given d(loss)/d(image). `taps` (optional dict) receives the upstream
+    gradient of every stage: `up{i}.dbn` / `fc.dbn` = gradient w.r.t. the stage's BatchNorm output with ReLU' applied
+    (what the per-layer parity tests feed to one stage of the CUDA backward)."""
     ch = g_channels(image_size)
     g: Dict[str, Tensor] = {}
     dpre = dout * (1.0 - cache["out"] ** 2)                                   # tanh'
@@ -129,6 +130,8 @@ def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, im
     for i in reversed(range(len(ch) - 1)):
         p = f"upsample_blocks.{i}.block"
         dbn = da * (cache[f"up{i}.a"] > 0)                                    # ReLU'
+        if taps is not None:
+            taps[f"up{i}.dbn"] = dbn
         dy, dgam, dbet = _bn_backward(dbn, cache[f"up{i}.xhat"], cache[f"up{i}.rstd"], sd[p + ".1.weight"], train)
         g[p + ".1.weight"], g[p + ".1.bias"] = dgam, dbet
         w = sd[p + ".0.weight"]                                               # (Cin, Cout, 4, 4)
@@ -137,6 +140,8 @@ def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, im
         g[p + ".0.weight"] = torch.nn.grad.conv2d_weight(dy, w.shape, x, stride=2, padding=1)
         da = F.conv2d(dy, w, None, stride=2, padding=1)                       # data gradient of ConvT
     dfc = da.reshape(da.shape[0], -1) * (cache["fc.a"] > 0)
+    if taps is not None:
+        taps["fc.dbn"] = dfc
     dy, dgam, dbet = _bn_backward(dfc, cache["fc.xhat"], cache["fc.rstd"], sd["fc.1.weight"], train)
     g["fc.1.weight"], g["fc.1.bias"] = dgam, dbet
     g["fc.0.weight"] = dy.t() @ cache["z"]
@@ -170,7 +175,10 @@ def d_forward(sd: Dict[str, Tensor], x: Tensor, image_size: int = 64,
 
 
 def d_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dprob: Tensor, image_size: int = 64,
-               masks: Optional[List[Tensor]] = None, need_dx: bool = False):
+               masks: Optional[List[Tensor]] = None, need_dx: bool = False,
+               taps: Optional[Dict[str, Tensor]] = None):
+    """`taps` (optional dict) receives `c{i}.dy`, the gradient w.r.t. block i's convolution output (after LeakyReLU'
+    and the dropout mask) — the upstream gradient the per-layer parity tests feed to one block of the CUDA backward."""
     ch = d_channels(image_size, cache["c0.in"].shape[1])
     g: Dict[str, Tensor] = {}
     p = cache["prob"]
@@ -185,6 +193,8 @@ def d_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dprob: Tensor, i
             da = da * masks[i].view(masks[i].shape[0], -1, 1, 1)
         # LeakyReLU(inplace) backward keys on the sign of its output; dropped channels carry zero gradient anyway.
         dy = da * torch.where(a > 0, torch.ones_like(a), torch.full_like(a, LEAKY_SLOPE))
+        if taps is not None:
+            taps[f"c{i}.dy"] = dy
         w = sd[name + ".weight"]
         xin = cache[f"c{i}.in"]
         g[name + ".weight"] = torch.nn.grad.conv2d_weight(xin, w.shape, dy, stride=2, padding=1)

@@ -59,6 +59,8 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_g_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "sg_d_forward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "sg_d_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "sg_d_backward_layer": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "sg_g_backward_layer": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "sg_dropout_masks": (_I, [_P, _U64, _U64, _I, _F, _P, _P]),
     "sg_bce_forward": (_I, [_P, _P, _I, _P, _P]),
     "sg_bce_backward": (_I, [_P, _P, _I, _P, _P, _P]),

@@ -537,9 +537,15 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     return 0;
 }
 
+// only_level = kAllLevels: the whole backward. Otherwise ONE unit of it (sg_g_backward_layer, parity tests): level
+// L-1 = final Conv3x3 + tanh together with the last block (input: grad_image), 0 <= level < L-1 = that block and -1 = the
+// fc stage (input `inject`: the ReLU'-masked gradient w.r.t. the stage's BatchNorm output, NHWC, T); the masked gradient
+// handed to the stage below is copied to d_prev_out.
+constexpr int kAllLevels = -100;
 template <typename T>
 int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float* grad_image, int B, int train,
-                 float* grads, float* dz, cudaStream_t s) {
+                 float* grads, float* dz, cudaStream_t s, int only_level = kAllLevels, const void* inject = nullptr,
+                 void* d_prev_out = nullptr) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     GWs w = carve_g(c, const_cast<void*>(ws_ptr), B);
     float* cpart = static_cast<float*>(c->cpart.p);
@@ -548,13 +554,22 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
     char* nxt = static_cast<char*>(c->bufB.p);
     const int L = c->L;
     const double es = c->es;
+    const bool single = only_level != kAllLevels;
+    const int lvl_hi = single ? only_level : L - 1, lvl_lo = single ? (only_level < 0 ? 0 : only_level) : 0;
+    if (single && only_level != L - 1) {
+        const int C = only_level < 0 ? c->gch[0] * 16 : c->gch[only_level + 1];
+        const size_t px = only_level < 0 ? 1 : static_cast<size_t>(g_spatial(c, only_level)) * g_spatial(c, only_level);
+        cudaMemcpyAsync(cur, inject, static_cast<size_t>(B) * px * C * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    }
+    const bool run_final = !single || only_level == L - 1;
+    const bool run_fc = !single || only_level < 0;
     // One pass over the last block's pre-BatchNorm output: d/d(bn output), final-conv dW/dbias, and the
     // BatchNorm-backward reductions of the last block (so that block needs no separate reduction pass below).
     float* part_bn = cpart + static_cast<size_t>(sg::kMaxChunks) * (9 * c->gch[L] + 1);
     int last_chunks = 0;
     // bf16 with batch statistics: pass 1 = reductions only, pass 2 (below) recomputes d and applies BatchNorm backward
     const bool two_pass = kTC && train && sg::final_conv_bwd_two_pass(c->S, c->gch[L]);
-    {
+    if (run_final) {
     PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L],
          (double)B * c->S * c->S * (8.0 + (two_pass ? 1.0 : 2.0) * es * c->gch[L]));
     last_chunks = sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.y[L - 1]), w.scale[L], w.shift[L],
@@ -562,7 +577,7 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
                                         grads + c->gt[c->g_final_w].offset, grads + c->gt[c->g_final_b].offset, cpart,
                                         part_bn, B, c->S, c->gch[L], s);
     }
-    for (int i = L - 1; i >= 0; --i) {
+    for (int i = (only_level < 0 && single) ? -1 : lvl_hi; i >= lvl_lo; --i) {
         const int oh = g_spatial(c, i), ih = oh / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
         const long rows = static_cast<long>(B) * oh * oh;
         const BNInfo& bn = c->bn[i + 1];
@@ -622,6 +637,15 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
         char* t = cur;
         cur = nxt;
         nxt = t;
+    }
+    if (single && only_level >= 0 && d_prev_out) {
+        const int Cp = c->gch[only_level];
+        const size_t px = static_cast<size_t>(g_spatial(c, only_level) / 2) * (g_spatial(c, only_level) / 2);
+        cudaMemcpyAsync(d_prev_out, cur, static_cast<size_t>(B) * px * Cp * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    }
+    if (!run_fc) {
+        SG_KCHECK("g_backward");
+        return 0;
     }
     // ---- fc: BatchNorm1d backward, weight / bias gradients
     const int F0 = c->gch[0] * 16, latent = c->cfg.latent_dim;
@@ -712,9 +736,14 @@ int d_forward_t(sg_ctx* c, const float* params, const float* x, int B, const flo
 // dlogit: d(loss)/d(logit) per sample (already includes sigmoid').
 // stage 0: whole backward; 1: classifier + last conv block only (the tail of the gradient bucket is final afterwards);
 // 2: the remaining blocks (continues from the scratch buffers stage 1 left).
+// only_layer >= 0 (sg_d_backward_layer, parity tests): ONE unit of the backward — ND = the classifier (input dlogit), 1..ND-1
+// = that conv block, 0 = the first block (weight gradient + image gradient); `inject` = the gradient w.r.t. the block's
+// convolution output (after LeakyReLU' and the dropout mask), NHWC, T; the same quantity of the block below is copied to
+// dz_prev_out.
 template <typename T>
 int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_ptr, const float* masks,
-                 const float* dlogit, int B, float* grads, float* dx, cudaStream_t s, int stage = 0) {
+                 const float* dlogit, int B, float* grads, float* dx, cudaStream_t s, int stage = 0, int only_layer = -1,
+                 const void* inject = nullptr, void* dz_prev_out = nullptr) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     DWs w = carve_d(c, const_cast<void*>(ws_ptr), B);
     const float slope = c->cfg.leaky_slope;
@@ -724,12 +753,18 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     char* nxt = static_cast<char*>(c->bufB.p);
     const int last = c->ND - 1, Cl = c->dch[c->ND];
     const double es = c->es;
+    const bool single = only_layer >= 0;
+    auto act_bytes = [&](int layer) {
+        return static_cast<size_t>(B) * d_spatial(c, layer) * d_spatial(c, layer) * c->dch[layer + 1] * sizeof(T);
+    };
+    if (single && only_layer < c->ND)
+        cudaMemcpyAsync(cur, inject, act_bytes(only_layer), cudaMemcpyDeviceToDevice, s);
     if (stage == 2) {  // stage 1 processed block `last` and swapped the scratch buffers once
         char* t = cur;
         cur = nxt;
         nxt = t;
     }
-    if (stage != 2) {
+    if (single ? only_layer == c->ND : stage != 2) {
     PROF("d.cls_bwd", 4.0 * B * Cl * 16, 3.0 * es * B * Cl * 16.0);
     if (grads) {
         const int chunks = sg::col_reduce<T>(2, reinterpret_cast<const T*>(w.a[last]), nullptr, nullptr, nullptr, dlogit,
@@ -740,7 +775,14 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     sg::classifier_bwd_dy<T>(dlogit, c->cls_wp, masks ? masks + mask_offset(c, B, last) : nullptr,
                              reinterpret_cast<const T*>(w.a[last]), slope, reinterpret_cast<T*>(cur), B, Cl, s);
     }
-    for (int i = (stage == 2 ? last - 1 : last); i >= (stage == 1 ? last : 1); --i) {
+    if (single && only_layer == c->ND) {
+        if (dz_prev_out) cudaMemcpyAsync(dz_prev_out, cur, act_bytes(last), cudaMemcpyDeviceToDevice, s);
+        SG_KCHECK("d_backward");
+        return 0;
+    }
+    const int i_hi = single ? only_layer : (stage == 2 ? last - 1 : last);
+    const int i_lo = single ? (only_layer > 0 ? only_layer : 1 << 30) : (stage == 1 ? last : 1);
+    for (int i = i_hi; i >= i_lo; --i) {
         const int oh = d_spatial(c, i), Cin = c->dch[i], Cout = c->dch[i + 1];
         const long rows = static_cast<long>(B) * oh * oh;
         const std::string nm = "d.c" + std::to_string(i);
@@ -790,6 +832,11 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
         nxt = t;
     }
     const int o0 = c->S / 2;
+    if (single && only_layer > 0) {
+        if (dz_prev_out) cudaMemcpyAsync(dz_prev_out, cur, act_bytes(only_layer - 1), cudaMemcpyDeviceToDevice, s);
+        SG_KCHECK("d_backward");
+        return 0;
+    }
     if (stage == 1) {
         SG_KCHECK("d_backward");
         return 0;
@@ -1290,6 +1337,37 @@ int sg_d_backward(sg_ctx* c, const float* params, const float* x, const void* ws
     // spectral-norm variant hands every forward its own weight_orig / sigma buffer) packs its own again
     if (c->d_pack_src != params) SG_TRY(pack_discriminator(c, params, s));
     return DISPATCH_T(c, d_backward_t, c, params, x, ws, masks, c->dlogit, batch, grads_out, dx_out, s);
+}
+
+int sg_d_backward_layer(sg_ctx* c, const float* params, const float* x, const void* ws, const float* masks, int layer,
+                        const void* dz_in, int batch, float* grads_out, void* dz_prev_out, float* dx_out, void* stream) {
+    if (!c || !params || !x || !ws || !dz_in || !grads_out || batch < 1 || layer < 0 || layer > c->ND)
+        return fail("sg_d_backward_layer: bad argument");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    const float* dlogit = nullptr;
+    if (layer == c->ND) {  // dz_in = d(loss)/d(probability), as for sg_d_backward
+        DWs w = carve_d(c, const_cast<void*>(ws), batch);
+        sg::sigmoid_bwd(w.prob, static_cast<const float*>(dz_in), c->dlogit, batch, s);
+        dlogit = c->dlogit;
+    }
+    if (c->d_pack_src != params) SG_TRY(pack_discriminator(c, params, s));
+    return DISPATCH_T(c, d_backward_t, c, params, x, ws, masks, dlogit, batch, grads_out, dx_out, s, 0, layer, dz_in,
+                      dz_prev_out);
+}
+
+int sg_g_backward_layer(sg_ctx* c, const float* params, const void* ws, int level, const void* d_in, int batch,
+                        int bn_batch_stats, float* grads_out, void* d_prev_out, void* stream) {
+    if (!c || !params || !ws || !d_in || !grads_out || batch < 1 || level < -1 || level >= c->L)
+        return fail("sg_g_backward_layer: bad argument");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SG_TRY(ensure_scratch(c, batch));
+    if (c->g_pack_src != params) SG_TRY(pack_generator(c, params, s));
+    const bool top = level == c->L - 1;
+    return DISPATCH_T(c, g_backward_t, c, params, ws, top ? static_cast<const float*>(d_in) : nullptr, batch,
+                      bn_batch_stats, grads_out, nullptr, s, level, top ? nullptr : d_in, d_prev_out);
 }
 
 int sg_dropout_masks(sg_ctx* c, uint64_t seed, uint64_t offset, int batch, float p, float* masks_out, void* stream) {

@@ -73,5 +73,15 @@ def make_gan(size: int, seed: int, precision: str, device="cuda"):
     return gan, g_sd, d_sd
 
 
-def nchw(t_nhwc_like: torch.Tensor) -> torch.Tensor:
-    return t_nhwc_like
+def to_nhwc(t: torch.Tensor, precision: str) -> torch.Tensor:
+    """Oracle activation (NCHW or (B, F) fp32, CPU) -> the library's layout: NHWC in the context's activation type."""
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    if t.dim() == 4:
+        t = t.permute(0, 2, 3, 1)
+    return t.contiguous().to(device="cuda", dtype=dt)
+
+
+def from_nhwc(t: torch.Tensor, shape_nchw) -> torch.Tensor:
+    """Library activation buffer (flat, NHWC) -> NCHW fp32 on the CPU."""
+    B, C, H, W = shape_nchw
+    return t.reshape(B, H, W, C).permute(0, 3, 1, 2).float().cpu()

@@ -1,0 +1,173 @@
+"""Per-layer isolated backward parity (BASELINE.json north_star: per-layer gradients within 1e-2 under bf16, 1e-5 in the
+fp32 validation mode).
+
+Every unit of the two backward chains — the classifier and each conv block of the Discriminator (disc…:18-81, 196-207),
+the final Conv3x3 + tanh with the last upsample block, each other upsample block and the fc stage of the Generator
+(gen…:17-66, 124-163) — is run ALONE through the C ABI (sg_d_backward_layer / sg_g_backward_layer: the same launchers
+the full backward uses) on the CPU oracle's exact upstream gradient, and its parameter gradients and the gradient it
+hands to the unit below are compared with the oracle's for that unit. Unlike the chained tests of test_gpu_parity.py no
+error is inherited from the units above, so the stated per-layer tolerance applies as it is.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import _siggan_lib as L
+import siggan_oracle as O
+from _util import from_nhwc, make_gan, rel_err, to64, to_nhwc
+
+pytestmark = pytest.mark.gpu
+
+# north_star: 1e-2 relative (bf16 operands), 1e-5 (fp32 validation mode) per layer. The fp32 figures are taken against
+# the float64 oracle; a gradient that is a sum of ~1e5..1e6 signed fp32 terms carries the fp32 CPU oracle's own
+# cancellation noise too, so the bound is max(1e-5, 4 x the fp32 oracle's own distance to float64) — the measured
+# distances are printed by `pytest -s`.
+TOL = {"bf16": 1e-2, "fp32": 1e-5}
+
+
+def _limit(precision, ref32, ref64):
+    if precision == "bf16":
+        return TOL["bf16"]
+    return max(TOL["fp32"], 4 * rel_err(ref32, ref64))
+
+
+def _cmp(name, precision, got, ref32, ref64, errs, floor=1e-7):
+    e = rel_err(got, ref64, floor)
+    lim = _limit(precision, ref32, ref64)
+    errs[name] = (e, lim)
+    assert e <= lim, f"{name}: relative error {e:.3e} > {lim:.1e} ({precision})"
+
+
+def _grads_by_name(ctx, net, flat):
+    return {name: flat[off:off + torch.Size(shape).numel()].view(shape).float().cpu()
+            for name, off, shape in ctx.tensor_table(net)}
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("size,B", [(64, 16), (128, 8)])
+def test_discriminator_layers_backward(precision, size, B):
+    gan, _, d_sd = make_gan(size, 2, precision)
+    D = gan.discriminator
+    D._prepare(torch.device("cuda", torch.cuda.current_device()))
+    ctx, lib, fp = D._ctx, D._ctx.lib, D._flat
+    x = O.synthetic_signatures(B, size, seed=6)
+    masks = O.make_dropout_masks(B, size, seed=4)
+    # oracle: forward + backward with the per-block upstream gradients, in fp32 and in float64
+    prob32, c32 = O.d_forward(d_sd, x, size, masks)
+    dprob32 = O.bce_grad(prob32, torch.full_like(prob32, 0.9))
+    taps32 = {}
+    g32 = O.d_backward(d_sd, c32, dprob32, size, masks, need_dx=True, taps=taps32)
+    sd64 = to64(d_sd)
+    m64 = [m.double() for m in masks]
+    prob64, c64 = O.d_forward(sd64, x.double(), size, m64)
+    taps64 = {}
+    g64 = O.d_backward(sd64, c64, dprob32.double(), size, m64, need_dx=True, taps=taps64)
+    # CUDA forward (saves the activations the backward units read)
+    xs = x.cuda()
+    mflat = torch.cat([m.reshape(-1) for m in masks]).cuda().contiguous()
+    ws = torch.empty(int(lib.sg_d_workspace_bytes(ctx.handle, B)), dtype=torch.uint8, device="cuda")
+    st = L.current_stream(xs.device)
+    L.check(lib.sg_d_forward(ctx.handle, L.ptr(fp.flat), L.ptr(xs), B, L.ptr(mflat), L.ptr(ws), None, None, st), "d fwd")
+    nd = len(O.d_channels(size)) - 1
+    errs = {}
+    grads = torch.zeros_like(fp.flat)
+    act_dt = torch.bfloat16 if precision == "bf16" else torch.float32
+
+    def shape_of(i):
+        return tuple(c32[f"c{i}.a"].shape)
+
+    # ---- classifier: input d(loss)/d(prob)
+    dz_prev = torch.empty(torch.Size(shape_of(nd - 1)).numel(), dtype=act_dt, device="cuda")
+    dprob = dprob32.cuda().contiguous()
+    L.check(lib.sg_d_backward_layer(ctx.handle, L.ptr(fp.flat), L.ptr(xs), L.ptr(ws), L.ptr(mflat), nd, L.ptr(dprob), B,
+                                    L.ptr(grads), L.ptr(dz_prev), None, st), "d layer cls")
+    got = _grads_by_name(ctx, L.SG_NET_D, grads)
+    for k in ("classifier.0.weight", "classifier.0.bias"):
+        _cmp(k, precision, got[k], g32[k], g64[k], errs)
+    _cmp(f"c{nd - 1}.dy", precision, from_nhwc(dz_prev, shape_of(nd - 1)), taps32[f"c{nd - 1}.dy"], taps64[f"c{nd - 1}.dy"], errs)
+    # ---- conv blocks, each fed the ORACLE's upstream gradient
+    for i in range(nd - 1, -1, -1):
+        dz_in = to_nhwc(taps32[f"c{i}.dy"], precision)
+        grads.zero_()
+        dz_prev = torch.empty(torch.Size(shape_of(i - 1)).numel(), dtype=act_dt, device="cuda") if i > 0 else None
+        dx = torch.empty_like(xs) if i == 0 else None
+        L.check(lib.sg_d_backward_layer(ctx.handle, L.ptr(fp.flat), L.ptr(xs), L.ptr(ws), L.ptr(mflat), i, L.ptr(dz_in), B,
+                                        L.ptr(grads), L.ptr(dz_prev), L.ptr(dx), st), f"d layer {i}")
+        got = _grads_by_name(ctx, L.SG_NET_D, grads)
+        for suffix in ("weight", "bias"):
+            k = f"conv_blocks.{i}.block.0.{suffix}"
+            _cmp(k, precision, got[k], g32[k], g64[k], errs)
+        if i > 0:
+            _cmp(f"c{i - 1}.dy", precision, from_nhwc(dz_prev, shape_of(i - 1)), taps32[f"c{i - 1}.dy"],
+                 taps64[f"c{i - 1}.dy"], errs)
+        else:
+            _cmp("dx", precision, dx.cpu(), g32["__dx"], g64["__dx"], errs)
+    print(f"\nD per-layer backward {precision} {size}x{size} B={B}:",
+          {k: f"{e:.1e}/{lim:.0e}" for k, (e, lim) in errs.items()})
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("size,B", [(64, 16), (128, 8)])
+def test_generator_layers_backward(precision, size, B):
+    gan, g_sd, _ = make_gan(size, 2, precision)
+    G = gan.generator
+    G._prepare(torch.device("cuda", torch.cuda.current_device()))
+    ctx, lib, fp = G._ctx, G._ctx.lib, G._flat
+    z = O.hash_normal((B, 100), 13)
+    dout = O.hash_normal((B, 1, size, size), 17) * 1e-3      # d(loss)/d(image): the scale a batch-mean loss produces
+    img32, c32, _ = O.g_forward(g_sd, z, size, train=True)
+    taps32 = {}
+    g32 = O.g_backward(g_sd, c32, dout, size, train=True, taps=taps32)
+    sd64 = to64(g_sd)
+    img64, c64, _ = O.g_forward(sd64, z.double(), size, train=True)
+    taps64 = {}
+    g64 = O.g_backward(sd64, c64, dout.double(), size, train=True, taps=taps64)
+    # CUDA training-mode forward: saves raw conv outputs, BatchNorm statistics, activations
+    zs = z.cuda()
+    ws = torch.empty(int(lib.sg_g_workspace_bytes(ctx.handle, B)), dtype=torch.uint8, device="cuda")
+    st = L.current_stream(zs.device)
+    stats = fp.stats.clone()
+    L.check(lib.sg_g_forward(ctx.handle, L.ptr(fp.flat), L.ptr(stats), L.ptr(zs), B, 1, L.ptr(ws), None, None, st), "g fwd")
+    nl = len(O.g_channels(size)) - 1
+    act_dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    grads = torch.zeros_like(fp.flat)
+    errs = {}
+
+    def in_shape(i):      # input activation of upsample block i (= output of the stage below)
+        return tuple(c32[f"up{i}.in"].shape)
+
+    def stage_params(i):
+        if i < 0:
+            return ["fc.0.weight", "fc.1.weight", "fc.1.bias"]      # fc.0.bias: mathematically zero (bias before BatchNorm)
+        p = f"upsample_blocks.{i}.block"
+        names = [p + ".0.weight", p + ".1.weight", p + ".1.bias"]
+        return names + (["final_conv.0.weight", "final_conv.0.bias"] if i == nl - 1 else [])
+
+    for i in range(nl - 1, -2, -1):
+        if i == nl - 1:
+            d_in = dout.cuda().contiguous()
+        elif i >= 0:
+            d_in = to_nhwc(taps32[f"up{i}.dbn"], precision)
+        else:
+            # fc stage: (B, C0*16) in NCHW feature order -> the library's NHWC (B, 4, 4, C0) order
+            C0 = O.g_channels(size)[0]
+            d_in = to_nhwc(taps32["fc.dbn"].view(B, C0, 4, 4), precision)
+        grads.zero_()
+        d_prev = None
+        if i >= 0:
+            d_prev = torch.empty(torch.Size(in_shape(i)).numel(), dtype=act_dt, device="cuda")
+        L.check(lib.sg_g_backward_layer(ctx.handle, L.ptr(fp.flat), L.ptr(ws), i, L.ptr(d_in), B, 1, L.ptr(grads),
+                                        L.ptr(d_prev), st), f"g level {i}")
+        got = _grads_by_name(ctx, L.SG_NET_G, grads)
+        for k in stage_params(i):
+            _cmp(k, precision, got[k], g32[k], g64[k], errs)
+        if i >= 0:
+            below = f"up{i - 1}.dbn" if i > 0 else "fc.dbn"
+            r32, r64 = taps32[below], taps64[below]
+            if i == 0:
+                C0 = O.g_channels(size)[0]
+                r32, r64 = r32.view(B, C0, 4, 4), r64.view(B, C0, 4, 4)
+            _cmp(below, precision, from_nhwc(d_prev, in_shape(i)), r32, r64, errs)
+    print(f"\nG per-layer backward {precision} {size}x{size} B={B}:",
+          {k: f"{e:.1e}/{lim:.0e}" for k, (e, lim) in errs.items()})

@@ -280,6 +280,45 @@ def test_full_batch_properties():
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
 
 
+def test_benchmark_batch_step_against_oracle():
+    """The benchmarked configuration itself (64x64, B = 4096 per GPU, bf16: BASELINE.json configs[2]) against the CPU
+    oracle: one D step and one G step of the fused path, gradients and metrics. Split-K factors, CTA-pair weight
+    gradients and tile schedules are functions of the batch, so the small-batch parity tests do not cover them.
+    (~1 minute of CPU time for the oracle at this size.)"""
+    B, size = 4096, 64
+    gan, g_sd, d_sd = make_gan(size, 4, "bf16")
+    real = O.synthetic_signatures(B, size, seed=21)
+    nd, ng = O.hash_normal((B, 100), 31), O.hash_normal((B, 100), 32)
+    mk_r, mk_f = O.make_dropout_masks(B, size, 41), O.make_dropout_masks(B, size, 42)
+    gan.mask_override = {"real": mk_r, "fake": mk_f}
+    md = gan.train_discriminator_step(real.cuda(), noise=nd.cuda())
+    d_got = {k: p.grad.detach().float().cpu().clone() for k, p in gan.discriminator.named_parameters()}
+    mg = gan.train_generator_step(B, noise=ng.cuda())
+    g_got = {k: p.grad.detach().float().cpu().clone() for k, p in gan.generator.named_parameters()}
+    torch.cuda.synchronize()
+    g_opt = O.AdamState(g_sd, O.trainable_names(g_sd))
+    d_opt = O.AdamState(d_sd, O.trainable_names(d_sd))
+    od, d_ref, _ = O.d_step(g_sd, d_sd, d_opt, real, nd, size, mk_r, mk_f)
+    og, g_ref, _ = O.g_step(g_sd, d_sd, g_opt, ng, size)
+    for k, v in {**od, **og}.items():
+        got = {**md, **mg}[k]
+        assert abs(got - v) <= 1e-2 * max(1.0, abs(v)) + (0.02 if k.endswith("acc") else 0), (k, got, v)
+    errs = {}
+    for k, ref in d_ref.items():      # chained tolerances of tests/_util.py (errors accumulate down the backward chain)
+        errs[k] = rel_err(d_got[k], ref)
+        assert errs[k] <= tol("bf16", "grad_d") * (2 if k.endswith("bias") else 1), f"D grad {k}: {errs[k]:.3e}"
+    num = den = 0.0
+    for k, ref in g_ref.items():
+        if k == "fc.0.bias":          # mathematically zero (bias in front of BatchNorm)
+            continue
+        errs[k] = rel_err(g_got[k], ref)
+        assert errs[k] <= tol("bf16", "grad_g"), f"G grad {k}: {errs[k]:.3e}"
+        num += ((g_got[k].double() - ref.double()) ** 2).sum().item()
+        den += (ref.double() ** 2).sum().item()
+    assert (num / den) ** 0.5 <= tol("bf16", "grad_g_all"), f"G gradient vector: {(num / den) ** 0.5:.3e}"
+    print("\nB=4096 step vs oracle:", {k: f"{e:.1e}" for k, e in errs.items()}, "G vector", f"{(num / den) ** 0.5:.1e}")
+
+
 def test_edge_cases():
     gan, g_sd, d_sd = make_gan(64, 1, "bf16")
     G, D = gan.generator, gan.discriminator
