@@ -91,6 +91,13 @@ int sg_d_forward(sg_ctx* ctx, const float* params, const float* x, int batch, co
 /* grads_out NULL => skip weight gradients; dx_out NULL => skip the image gradient. */
 int sg_d_backward(sg_ctx* ctx, const float* params, const float* x, const void* ws, const float* masks,
                   const float* grad_prob, int batch, float* grads_out, float* dx_out, void* stream);
+/* Byte offset of one saved tensor inside a forward workspace (parity tests read per-layer activations there and
+ * replace them by the oracle's before running a single backward unit), or -1. Generator kinds: 0 padded latents,
+ * 1 fc output before BatchNorm, 2 fc activation, 3 block `index` ConvT output before BatchNorm, 4 block `index`
+ * activation, 5 image (fp32), 6 / 7 / 8 / 9 BatchNorm `index` mean / rstd / scale / shift (fp32; index 0 = fc, in NHWC
+ * column order). Discriminator kinds: 0 block `index` activation, 1 probabilities (fp32). */
+long long sg_ws_offset(const sg_ctx* ctx, int net, int batch, int kind, int index);
+
 /* ---- one layer of a backward pass (parity tests: tests/test_gpu_layers.py feeds each layer the oracle's exact upstream
  * gradient). These run the same launchers as sg_d_backward / sg_g_backward on ONE unit of the chain; `ws` must come from
  * the matching forward. Activation-shaped tensors are NHWC in the context's activation type (bf16, or fp32 in

@@ -59,6 +59,7 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_g_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "sg_d_forward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "sg_d_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "sg_ws_offset": (_LL, [_P, _I, _I, _I, _I]),
     "sg_d_backward_layer": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "sg_g_backward_layer": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "sg_dropout_masks": (_I, [_P, _U64, _U64, _I, _F, _P, _P]),
@@ -117,6 +118,42 @@ def precision_from_env() -> int:
     if v in ("fp32", "float32", "validate", "1"):
         return SG_PREC_FP32
     raise ValueError(f"SIGGAN_PRECISION must be bf16 or fp32, got {v!r}")
+
+
+class DropoutStream:
+    """The ONE counter-based Dropout2d mask stream of this process (sg_dropout_masks / sg_train_step hash (seed, offset +
+    index)): shared by the Discriminator module path and the fused training step, so the two never replay each other's
+    masks; the seed is torch's initial seed mixed with the data-parallel rank, so replicas that share a seed still
+    draw different masks; `state_dict()` goes into checkpoints so that a resumed run continues the stream."""
+
+    def __init__(self) -> None:
+        self.offset = 0
+
+    @staticmethod
+    def seed() -> int:
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:
+            rank = 0
+        return (torch.initial_seed() ^ (rank * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+
+    def advance(self, n: int) -> int:
+        """Returns the offset of the next `n` mask values and moves past them."""
+        o = self.offset
+        self.offset += int(n)
+        return o
+
+    def state_dict(self) -> dict:
+        return {"offset": int(self.offset)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.offset = int(sd.get("offset", 0))
+
+
+DROPOUT = DropoutStream()
 
 
 class Context:

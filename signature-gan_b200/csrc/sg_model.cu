@@ -1278,6 +1278,34 @@ long long sg_d_mask_count(const sg_ctx* c, int batch) { return mask_offset(c, ba
 long long sg_d_grad_tail_offset(const sg_ctx* c) { return c->dt[c->d_conv_w[c->ND - 1]].offset; }
 long long sg_d_feature_count(const sg_ctx* c) { return (long long)c->dch[c->ND] * 16; }
 
+long long sg_ws_offset(const sg_ctx* c, int net, int batch, int kind, int index) {
+    if (!c || batch < 1) return -1;
+    char base[1];  // carve relative to a dummy base: only differences are used
+    if (net == SG_NET_G) {
+        GWs w = carve_g(c, base, batch);
+        if (index < 0 || index > c->L) return -1;
+        const char* p = nullptr;
+        switch (kind) {
+            case 0: p = w.zp; break;
+            case 1: p = w.fc_y; break;
+            case 2: p = w.fc_a; break;
+            case 3: p = index < c->L ? w.y[index] : nullptr; break;
+            case 4: p = index < c->L ? w.a[index] : nullptr; break;
+            case 5: p = reinterpret_cast<const char*>(w.out); break;
+            case 6: p = reinterpret_cast<const char*>(w.mean[index]); break;
+            case 7: p = reinterpret_cast<const char*>(w.rstd[index]); break;
+            case 8: p = reinterpret_cast<const char*>(w.scale[index]); break;
+            case 9: p = reinterpret_cast<const char*>(w.shift[index]); break;
+            default: break;
+        }
+        return p ? static_cast<long long>(p - base) : -1;
+    }
+    DWs w = carve_d(c, base, batch);
+    if (kind == 0 && index >= 0 && index < c->ND) return static_cast<long long>(w.a[index] - base);
+    if (kind == 1) return static_cast<long long>(reinterpret_cast<const char*>(w.prob) - base);
+    return -1;
+}
+
 int sg_g_forward(sg_ctx* c, const float* params, float* stats, const float* z, int batch, int bn_batch_stats, void* ws,
                  float* out_image, uint8_t* out_u8, void* stream) {
     if (!c || !params || !stats || !z || batch < 1) return fail("sg_g_forward: bad argument");

@@ -41,9 +41,6 @@ class DownsampleBlock(nn.Module):
         raise RuntimeError("DownsampleBlock is a parameter holder in siggan_b200; run it through Discriminator.forward")
 
 
-_mask_counter = [0]
-
-
 class _SpectralWeights:
     """Effective weights of one forward of the spectral-norm variant: flat copy of the parameters with every
     weight divided by its sigma, plus the (u, v, sigma) that forward used (torch SpectralNorm.compute_weight)."""
@@ -203,9 +200,8 @@ class Discriminator(nn.Module):
                 raise RuntimeError(f"mask_override has {flat.numel()} elements, expected {n}")
             return flat.contiguous()
         masks = torch.empty(n, dtype=torch.float32, device=device)
-        L.check(sctx.lib.sg_dropout_masks(sctx.handle, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, _mask_counter[0], B,
+        L.check(sctx.lib.sg_dropout_masks(sctx.handle, L.DROPOUT.seed(), L.DROPOUT.advance(n), B,
                                           float(self.dropout), L.ptr(masks), L.current_stream(device)), "sg_dropout_masks")
-        _mask_counter[0] += n
         return masks
 
     def _check_input(self, x: torch.Tensor) -> torch.device:

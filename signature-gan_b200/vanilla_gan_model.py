@@ -187,7 +187,7 @@ class VanillaGAN(nn.Module):
         self.d_losses: list = []
         self.g_losses: list = []
         self._metrics: Optional[torch.Tensor] = None
-        self._dropout_offset = 0
+        self._d_loss_hist: Optional[torch.Tensor] = None
         #: parity hook for the fused step: dict(real=[...], fake=[...]) of (B, C_i) keep-scale tensors
         self.mask_override: Optional[Dict[str, list]] = None
         self.to(self._device)
@@ -195,6 +195,15 @@ class VanillaGAN(nn.Module):
     @property
     def device(self) -> torch.device:
         return self._device
+
+    # The Dropout2d mask stream is process-wide (shared with the Discriminator module path, _siggan_lib.DROPOUT).
+    @property
+    def _dropout_offset(self) -> int:
+        return L.DROPOUT.offset
+
+    @_dropout_offset.setter
+    def _dropout_offset(self, value: int) -> None:
+        L.DROPOUT.offset = int(value)
 
     def to(self, device: Union[str, torch.device]) -> "VanillaGAN":  # reference vanilla…:136-150
         if isinstance(device, str):
@@ -235,8 +244,8 @@ class VanillaGAN(nn.Module):
         st.g_lr, st.d_lr, st.beta1, st.beta2, st.eps = glr, dlr, b1, b2, eps
         st.label_smoothing = float(self.label_smoothing)
         st.dropout_p = float(d.dropout)
-        st.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        st.offset = self._dropout_offset
+        st.seed = L.DROPOUT.seed()
+        st.offset = L.DROPOUT.offset
         if masks is not None:
             st.masks_real, st.masks_fake = L.ptr(masks["real"]), L.ptr(masks["fake"])
         st.world_size = 1
@@ -346,7 +355,8 @@ class VanillaGAN(nn.Module):
         L.check(sctx.lib.sg_train_step(*args, 2, stream), "sg_train_step(D update)")
         self.d_optimizer.advance()
         self.discriminator._flat.expose(dgrads)
-        self._dropout_offset += int(sctx.lib.sg_d_mask_count(sctx.handle, 2 * B))
+        if st.dropout_p > 0:
+            L.DROPOUT.advance(int(sctx.lib.sg_d_mask_count(sctx.handle, 2 * B)))
         return self._metrics
 
     def generator_step_async(self, batch_size: int, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -389,17 +399,31 @@ class VanillaGAN(nn.Module):
         return out
 
     def train_step_async(self, real_images: torch.Tensor, n_critic: int = 1) -> torch.Tensor:
-        """D step(s) + G step enqueued back to back; returns the 12-float device metrics tensor (no host sync)."""
-        for _ in range(n_critic):
-            self.discriminator_step_async(real_images)
+        """D step(s) + G step enqueued back to back; returns the 12-float device metrics tensor (no host sync). With
+        n_critic > 1 the loss of every critic step is kept in `self._d_loss_hist` (device, n_critic floats)."""
+        if n_critic > 1:
+            dev = self.generator.fc[0].weight.device
+            if self._d_loss_hist is None or self._d_loss_hist.numel() != n_critic or self._d_loss_hist.device != dev:
+                self._d_loss_hist = torch.zeros(n_critic, dtype=torch.float32, device=dev)
+        for i in range(n_critic):
+            m = self.discriminator_step_async(real_images)
+            if n_critic > 1:
+                self._d_loss_hist[i:i + 1].copy_(m[0:1])
         return self.generator_step_async(real_images.size(0))
 
     def train_step(self, real_images: torch.Tensor, n_critic: int = 1) -> Dict[str, float]:
-        """reference vanilla…:308-336; one device->host read for all returned floats."""
-        m = self.train_step_async(real_images, n_critic).tolist()
+        """reference vanilla…:308-336; one device->host read for all returned floats. Every critic step's own loss
+        goes into `d_losses` (the reference appends per train_discriminator_step call, vanilla…:241)."""
+        metrics = self.train_step_async(real_images, n_critic)
+        if n_critic > 1:
+            both = torch.cat([metrics, self._d_loss_hist]).tolist()
+            m, per_step = both[:12], both[12:]
+        else:
+            m = metrics.tolist()
+            per_step = [m[0]]
         out = dict(zip(_METRIC_KEYS_D, m[:7]))
         out.update(zip(_METRIC_KEYS_G, m[7:9]))
-        self.d_losses.extend([out["d_loss"]] * n_critic)
+        self.d_losses.extend(per_step)
         self.global_step += n_critic
         self.g_losses.append(out["g_loss"])
         return out
@@ -450,6 +474,7 @@ class VanillaGAN(nn.Module):
             ckpt["d_optimizer_state_dict"] = self.d_optimizer.state_dict()
         if save_history:
             ckpt["d_losses"], ckpt["g_losses"] = self.d_losses, self.g_losses
+        ckpt["dropout_stream"] = L.DROPOUT.state_dict()   # extra key (ignored by the reference's loader): resume continues the masks
         torch.save(ckpt, f"{path}.pt")
         with open(f"{path}_config.json", "w") as f:
             json.dump(self.get_config(), f, indent=2)
@@ -470,6 +495,8 @@ class VanillaGAN(nn.Module):
         if load_optimizer and "g_optimizer_state_dict" in ckpt:
             self.g_optimizer.load_state_dict(ckpt["g_optimizer_state_dict"])
             self.d_optimizer.load_state_dict(ckpt["d_optimizer_state_dict"])
+        if "dropout_stream" in ckpt:
+            L.DROPOUT.load_state_dict(ckpt["dropout_stream"])
         if load_history and "d_losses" in ckpt:
             self.d_losses = ckpt.get("d_losses", [])
             self.g_losses = ckpt.get("g_losses", [])

@@ -39,6 +39,14 @@ def _cmp(name, precision, got, ref32, ref64, errs, floor=1e-7):
     assert e <= lim, f"{name}: relative error {e:.3e} > {lim:.1e} ({precision})"
 
 
+def _put(ctx, ws, net, B, kind, index, value):
+    """Overwrite one saved tensor of a forward workspace with `value` (already in the library's layout / dtype)."""
+    off = int(ctx.lib.sg_ws_offset(ctx.handle, net, B, kind, index))
+    assert off >= 0, (net, kind, index)
+    raw = value.contiguous().view(torch.uint8).reshape(-1)
+    ws[off:off + raw.numel()].copy_(raw)
+
+
 def _grads_by_name(ctx, net, flat):
     return {name: flat[off:off + torch.Size(shape).numel()].view(shape).float().cpu()
             for name, off, shape in ctx.tensor_table(net)}
@@ -70,6 +78,11 @@ def test_discriminator_layers_backward(precision, size, B):
     st = L.current_stream(xs.device)
     L.check(lib.sg_d_forward(ctx.handle, L.ptr(fp.flat), L.ptr(xs), B, L.ptr(mflat), L.ptr(ws), None, None, st), "d fwd")
     nd = len(O.d_channels(size)) - 1
+    # isolate the units: every saved activation becomes the ORACLE's (rounded to the activation type), so that a unit's
+    # result does not inherit the forward chain's rounding (near-zero activations whose LeakyReLU side flips)
+    for i in range(nd):
+        _put(ctx, ws, L.SG_NET_D, B, 0, i, to_nhwc(c32[f"c{i}.a"], precision))
+    _put(ctx, ws, L.SG_NET_D, B, 1, 0, prob32.reshape(-1).cuda())
     errs = {}
     grads = torch.zeros_like(fp.flat)
     act_dt = torch.bfloat16 if precision == "bf16" else torch.float32
@@ -133,6 +146,30 @@ def test_generator_layers_backward(precision, size, B):
     act_dt = torch.bfloat16 if precision == "bf16" else torch.float32
     grads = torch.zeros_like(fp.flat)
     errs = {}
+    # isolate the units: saved conv outputs, activations, image and BatchNorm statistics become the ORACLE's
+    C0 = O.g_channels(size)[0]
+
+    def bn_vectors(y, prefix, fc=False):
+        dims = [0] if y.dim() == 2 else [0, 2, 3]
+        mean, var = y.mean(dim=dims), y.var(dim=dims, unbiased=False)
+        rstd = torch.rsqrt(var + O.BN_EPS)
+        scale = g_sd[prefix + ".weight"] * rstd
+        shift = g_sd[prefix + ".bias"] - mean * scale
+        vs = [mean, rstd, scale, shift]
+        if fc:      # NCHW feature f = c*16 + hw  ->  NHWC column j = hw*C0 + c
+            vs = [v.view(C0, 16).t().reshape(-1) for v in vs]
+        return [v.float().contiguous().cuda() for v in vs]
+
+    _put(ctx, ws, L.SG_NET_G, B, 1, 0, to_nhwc(c32["fc.y"].view(B, C0, 4, 4), precision))
+    _put(ctx, ws, L.SG_NET_G, B, 2, 0, to_nhwc(c32["fc.a"].view(B, C0, 4, 4), precision))
+    for kind, v in zip((6, 7, 8, 9), bn_vectors(c32["fc.y"], "fc.1", fc=True)):
+        _put(ctx, ws, L.SG_NET_G, B, kind, 0, v)
+    for i in range(nl):
+        _put(ctx, ws, L.SG_NET_G, B, 3, i, to_nhwc(c32[f"up{i}.y"], precision))
+        _put(ctx, ws, L.SG_NET_G, B, 4, i, to_nhwc(c32[f"up{i}.a"], precision))
+        for kind, v in zip((6, 7, 8, 9), bn_vectors(c32[f"up{i}.y"], f"upsample_blocks.{i}.block.1")):
+            _put(ctx, ws, L.SG_NET_G, B, kind, i + 1, v)
+    _put(ctx, ws, L.SG_NET_G, B, 5, 0, img32.reshape(-1).cuda())
 
     def in_shape(i):      # input activation of upsample block i (= output of the stage below)
         return tuple(c32[f"up{i}.in"].shape)

@@ -363,10 +363,13 @@ def test_checkpoint_round_trip(tmp_path):
     gan2 = VanillaGAN.from_checkpoint(tmp_path / "ckpt", device="cuda")
     for (k, a), (_, b) in zip(gan.state_dict().items(), gan2.state_dict().items()):
         assert torch.equal(a, b), k
+    # the Dropout2d mask stream (process-wide, _siggan_lib.DROPOUT) is checkpointed: loading put it back where the save left it
+    off = gan2._dropout_offset
+    assert off == ck["dropout_stream"]["offset"] and off > 0
     torch.manual_seed(3)
-    gan2._dropout_offset = gan._dropout_offset       # the dropout counter is run state, not checkpoint state
     m1 = gan.train_step(real)
     torch.manual_seed(3)
+    gan2._dropout_offset = off                       # what a resumed process would start from
     m2 = gan2.train_step(real)
     assert m1 == m2, (m1, m2)       # resumed run continues bit-identically (Adam moments + step restored)
     # a plain torch.optim.Adam state dict (what the reference trainer writes) loads into the fused optimizer
