@@ -66,7 +66,7 @@ def main(work: str) -> None:
     out["resume_generator_equal"] = bool(same)
     m = trainer2._train_discriminator(torch.from_numpy(imgs[:16]).float().div(127.5).sub(1).unsqueeze(1))
     m.update(trainer2._train_generator(16))
-    out["resumed_step_metrics"] = {k: float(v) for k, v in m.items()}
+    out["resumed_step_metrics"] = {k: float(v) for k, v in m.items() if v is not None}   # grad norms: None (clipping off)
 
     # ---- utils/inference.py: load_generator + generate_signatures_batch on the checkpoint the trainer wrote
     dev = torch.device("cuda")

@@ -271,6 +271,7 @@ def test_full_batch_properties():
     outs = []
     for _ in range(2):
         gan2, _, _ = make_gan(size, 3, "bf16")
+        gan2._dropout_offset = 0        # the Dropout2d mask stream is process-wide: both runs start it at the same point
         torch.manual_seed(7)
         real = torch.rand(B, 1, size, size, device="cuda", generator=torch.Generator("cuda").manual_seed(1)) * 2 - 1
         m = [gan2.train_step(real) for _ in range(2)][-1]
