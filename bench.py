@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / cpu baseline / per-op profile")
     ap.add_argument("--cpu-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--torch-allreduce", action="store_true", help="N > 1: all-reduce the buckets through torch.distributed "
+                    "instead of the library-owned NCCL communicator (A/B)")
     ap.add_argument("--sync-bn", action="store_true", help="N > 1: global-batch BatchNorm statistics (sg_set_sync_batchnorm)")
     return ap.parse_args()
 
@@ -398,6 +400,12 @@ def input_pipeline_numbers(pool_f32, B, S, dev, pk, measure_cpu, gan=None):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def lib_nccl_version():
+    import _siggan_lib as L
+    v = int(L.load_library().sg_comm_nccl_version())
+    return "unavailable" if v < 0 else f"{v // 10000}.{v // 100 % 100}.{v % 100}"
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -416,6 +424,14 @@ def run_ours(args, rank, local_rank, world):
     gan._fused_ready()
     from data_parallel import broadcast_replica_
     broadcast_replica_([gan.generator._flat.flat, gan.generator._flat.stats, gan.discriminator._flat.flat])  # identical replicas
+    comm = "none"
+    if world > 1:
+        if args.torch_allreduce:
+            comm = "torch.distributed (NCCL process group)"
+        else:
+            from data_parallel import init_library_comm
+            init_library_comm(gan)          # libsiggan's own NCCL communicator: all-reduces issued inside sg_train_step
+            comm = f"libsiggan-owned NCCL communicator (nccl {lib_nccl_version()})"
     sync_bn = bool(args.sync_bn and world > 1)
     if sync_bn:
         from data_parallel import enable_sync_batchnorm
@@ -448,6 +464,19 @@ def run_ours(args, rank, local_rank, world):
     ms_total = float(ms)
     last_metrics = metrics.tolist()
     value = world * B * args.steps / (ms_total * 1e-3)
+    # ---- replicas must still be bit-identical after the timed steps (every rank applied the same averaged gradients
+    # to the same parameters): exact integer checksums of the raw fp32 bit patterns of the flat G / D buffers, gathered
+    replicas_identical = None
+    if world > 1:
+        def bits_checksum(t):
+            w = t.detach().contiguous().view(torch.int32).to(torch.int64)
+            idx = torch.arange(1, w.numel() + 1, device=w.device, dtype=torch.int64)
+            return torch.stack([w.sum(), (w * (idx % 65521)).sum()])
+        mine = torch.cat([bits_checksum(gan.generator._flat.flat), bits_checksum(gan.discriminator._flat.flat)])
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        replicas_identical = all(bool(torch.equal(c, allc[0])) for c in allc)
+        assert replicas_identical, "data-parallel replicas diverged: " + str([c.tolist() for c in allc])
 
     # ---- end to end: host-resident (pinned) real batches, H2D copy + D2H metric read every step ----
     host_pool = torch.empty(n_pool, B, 1, S, S, dtype=torch.float32).pin_memory()
@@ -485,11 +514,12 @@ def run_ours(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"train_step_{S}x{S}_b{B}_per_gpu", "global_batch": world * B, "image_size": S,
-                   "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1, "sync_bn": sync_bn,
+                   "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1, "sync_bn": sync_bn, "gradient_allreduce": comm,
                    "l2": "4 rotating real batches (268 MB) and multi-GB per-step activations exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": 48,
                 "steps": e2e_steps, "api": "VanillaGAN.train_step(real) from pinned host batches, double-buffered H2D"},
         "gpu_launches": int(launches),
+        "replicas_identical": replicas_identical,
         "clocks": clocks,
         "last_metrics": {k: round(v, 5) for k, v in zip(
             ["d_loss", "d_loss_real", "d_loss_fake", "d_real_acc", "d_fake_acc", "d_real_mean", "d_fake_mean", "g_loss",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2
+#define SG_ABI_VERSION 3
 
 enum { SG_PREC_BF16 = 0, SG_PREC_FP32 = 1 };
 enum { SG_NET_G = 0, SG_NET_D = 1 };
@@ -47,6 +47,8 @@ typedef struct sg_config {
     float leaky_slope; /* 0.2 (disc…:46) */
     float bn_eps;      /* 1e-5 */
     float bn_momentum; /* 0.1 */
+    float g_act_slope; /* Generator activation: 0 = ReLU (gen…:60,127); 0.2 = the ablation's ConfigurableGenerator with
+                          activation="leaky_relu" (ablation…:204-207, 265-268) */
 } sg_config;
 
 int sg_abi_version(void);
@@ -159,7 +161,11 @@ typedef struct sg_train_state {
  * caller all-reduce the flat gradient buckets between backward and update.
  * Overlapping the D all-reduce with backward: phase 11 = D forward + the classifier / last conv block part of the
  * backward (their gradients, the contiguous tail of the bucket from sg_d_grad_tail_offset() on — 76 % of it — are
- * final when it returns), phase 12 = the rest of the D backward; 11 followed by 12 equals phase 1. */
+ * final when it returns), phase 12 = the rest of the D backward; 11 followed by 12 equals phase 1. Likewise phase 31 =
+ * the G step down to upsample block 0 (bucket final from sg_g_grad_tail_offset() on), phase 32 = the fc stage; 31
+ * followed by 32 equals 3. With a communicator (sg_comm_init, world_size > 1) phase 0 runs the whole data-parallel
+ * step: every gradient group is averaged over the ranks on the communication stream while the rest of its backward pass
+ * runs, and both Adam updates use the averaged buckets. */
 int sg_train_step(sg_ctx* ctx, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
                   int batch, float* d_grads, float* g_grads, float* metrics_out, int phase, void* stream);
 
@@ -198,6 +204,27 @@ int sg_ink_stats(const float* images, int n_images, int pixels_per_image, float 
 typedef int (*sg_allreduce_fn)(void* user, float* buf, long long count, void* stream);
 int sg_set_sync_batchnorm(sg_ctx* ctx, sg_allreduce_fn fn, void* user, int world_size, float* buf,
                           long long buf_floats);
+
+/* ---- data-parallel replicas: library-owned NCCL communicator for the flat gradient buckets ---- */
+/* The reference is single-process (train…:494-502); a data-parallel launcher runs one process per GPU with identical
+ * replicas and averages the flat fp32 gradient buckets over the ranks before each Adam update (losses are batch means,
+ * vanilla…:107). NCCL is bound at run time (the libnccl.so.2 the host process already loaded, else the system one).
+ * Rank 0 calls sg_comm_unique_id (128 bytes, HOST memory) and ships the id to the other ranks by any host channel;
+ * every rank then calls sg_comm_init (collective: blocks until all `world_size` ranks arrive). */
+int sg_comm_nccl_version(void);                               /* NCCL version code, -1 when libnccl.so.2 cannot be loaded */
+int sg_comm_unique_id(void* host_id_out, size_t cap);         /* cap >= 128 */
+int sg_comm_init(sg_ctx* ctx, const void* host_id, size_t id_bytes, int rank, int world_size);
+int sg_comm_destroy(sg_ctx* ctx);
+int sg_comm_world_size(const sg_ctx* ctx);                    /* 0 without a communicator */
+/* grads[offset, offset+count) (elements of the `which` = SG_NET_G / SG_NET_D bucket; count < 0 = to its end) <- mean over
+ * the ranks, in place. async = 0: enqueued in order on `stream`. async != 0: the reduction waits for what `stream` holds
+ * so far and runs on the library's communication stream, overlapping whatever is enqueued on `stream` next (the rest of
+ * a backward pass); sg_allreduce_join makes `stream` wait for every reduction started so far. */
+int sg_allreduce_grads(sg_ctx* ctx, int which, float* grads, long long offset, long long count, int async, void* stream);
+int sg_allreduce_join(sg_ctx* ctx, void* stream);
+/* element offset of upsample block 0's weight in the flat G bucket: [offset, count) is final once the G backward has
+ * passed block 0 (only the fc stage's gradients, [0, offset), are still to come) */
+long long sg_g_grad_tail_offset(const sg_ctx* ctx);
 
 /* ---- measurement aid: per-operation device time (CUDA events on the launch stream) --------------- */
 /* on != 0 starts recording (and clears earlier records); every op of the plans is bracketed by two events. */

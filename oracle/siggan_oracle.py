@@ -89,15 +89,27 @@ def _bn_backward(dout: Tensor, xhat: Tensor, rstd: Tensor, gamma: Tensor, train:
 # --------------------------------------------------------------------------------------------
 # Generator (gen…:189-209): fc -> view -> 4-5 x (ConvT k4 s2 p1, BN2d, ReLU) -> Conv3x3 -> Tanh
 # --------------------------------------------------------------------------------------------
-def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: bool = False):
-    """Returns (image, cache, new_stats). `cache` holds every intermediate (keys documented inline)."""
+def _g_act(a: Tensor, act_slope: float) -> Tensor:
+    """ReLU (gen…:60,127) or, for the ablation's ConfigurableGenerator, LeakyReLU(act_slope) (ablation…:204-207, 265-268)."""
+    return torch.relu(a) if act_slope == 0.0 else F.leaky_relu(a, act_slope)
+
+
+def _g_act_grad(a: Tensor, act_slope: float) -> Tensor:
+    """Derivative of the activation from its OUTPUT (the reference's activations are in-place; the sign is preserved)."""
+    pos = a > 0
+    return pos.to(a.dtype) if act_slope == 0.0 else torch.where(pos, torch.ones_like(a), torch.full_like(a, act_slope))
+
+
+def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: bool = False, act_slope: float = 0.0):
+    """Returns (image, cache, new_stats). `cache` holds every intermediate (keys documented inline). act_slope > 0:
+    the ablation script's ConfigurableGenerator with activation="leaky_relu" (ablation…:216-328; same layers)."""
     ch = g_channels(image_size)
     cache: Dict[str, Tensor] = {"z": z}
     new_stats: Dict[str, Tensor] = {}
     y = F.linear(z, sd["fc.0.weight"], sd["fc.0.bias"])                       # gen…:125
     cache["fc.y"] = y
     a, xhat, rstd = _bn_forward(y, sd, "fc.1", train, new_stats)              # gen…:126
-    a = torch.relu(a)                                                         # gen…:127
+    a = _g_act(a, act_slope)                                                  # gen…:127 / ablation…:265-268
     cache["fc.xhat"], cache["fc.rstd"], cache["fc.a"] = xhat, rstd, a
     x = a.view(-1, ch[0], 4, 4)                                               # gen…:201
     for i in range(len(ch) - 1):
@@ -106,7 +118,7 @@ def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: boo
         y = F.conv_transpose2d(x, sd[p + ".0.weight"], None, stride=2, padding=1)   # gen…:46-54
         cache[f"up{i}.y"] = y
         a, xhat, rstd = _bn_forward(y, sd, p + ".1", train, new_stats)        # gen…:58
-        x = torch.relu(a)                                                     # gen…:60
+        x = _g_act(a, act_slope)                                              # gen…:60 / ablation…:204-207
         cache[f"up{i}.xhat"], cache[f"up{i}.rstd"], cache[f"up{i}.a"] = xhat, rstd, x
     pre = F.conv2d(x, sd["final_conv.0.weight"], sd["final_conv.0.bias"], stride=1, padding=1)  # gen…:154-161
     out = torch.tanh(pre)                                                     # gen…:162
@@ -115,7 +127,7 @@ def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: boo
 
 
 def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, image_size: int = 64,
-               train: bool = True, taps: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+               train: bool = True, taps: Optional[Dict[str, Tensor]] = None, act_slope: float = 0.0) -> Dict[str, Tensor]:
     """Gradients of every Generator parameter given d(loss)/d(image). `taps` (optional dict) receives the upstream
     gradient of every stage: `up{i}.dbn` / `fc.dbn` = gradient w.r.t. the stage's BatchNorm output with ReLU' applied
     (what the per-layer parity tests feed to one stage of the CUDA backward)."""
@@ -129,7 +141,7 @@ def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, im
     da = F.conv_transpose2d(dpre, sd["final_conv.0.weight"], None, stride=1, padding=1)
     for i in reversed(range(len(ch) - 1)):
         p = f"upsample_blocks.{i}.block"
-        dbn = da * (cache[f"up{i}.a"] > 0)                                    # ReLU'
+        dbn = da * _g_act_grad(cache[f"up{i}.a"], act_slope)                  # ReLU' / LeakyReLU'
         if taps is not None:
             taps[f"up{i}.dbn"] = dbn
         dy, dgam, dbet = _bn_backward(dbn, cache[f"up{i}.xhat"], cache[f"up{i}.rstd"], sd[p + ".1.weight"], train)
@@ -139,7 +151,7 @@ def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, im
         # dW[ci,co,ky,kx] = sum x[n,ci,iy,ix] * dy[n,co,2iy-1+ky,2ix-1+kx]
         g[p + ".0.weight"] = torch.nn.grad.conv2d_weight(dy, w.shape, x, stride=2, padding=1)
         da = F.conv2d(dy, w, None, stride=2, padding=1)                       # data gradient of ConvT
-    dfc = da.reshape(da.shape[0], -1) * (cache["fc.a"] > 0)
+    dfc = da.reshape(da.shape[0], -1) * _g_act_grad(cache["fc.a"], act_slope)
     if taps is not None:
         taps["fc.dbn"] = dfc
     dy, dgam, dbet = _bn_backward(dfc, cache["fc.xhat"], cache["fc.rstd"], sd["fc.1.weight"], train)

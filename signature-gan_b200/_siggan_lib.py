@@ -21,7 +21,8 @@ SG_NET_G, SG_NET_D = 0, 1
 
 class SgConfig(C.Structure):
     _fields_ = [("image_size", C.c_int), ("latent_dim", C.c_int), ("precision", C.c_int),
-                ("leaky_slope", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float)]
+                ("leaky_slope", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+                ("g_act_slope", C.c_float)]
 
 
 class SgTrainState(C.Structure):
@@ -72,6 +73,14 @@ SYMBOLS: Dict[str, Tuple[object, list]] = {
     "sg_augment_batch": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "sg_ink_stats": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "sg_set_sync_batchnorm": (_I, [_P, _P, _P, _I, _P, _LL]),
+    "sg_comm_nccl_version": (_I, []),
+    "sg_comm_unique_id": (_I, [_P, _SZ]),
+    "sg_comm_init": (_I, [_P, _P, _SZ, _I, _I]),
+    "sg_comm_destroy": (_I, [_P]),
+    "sg_comm_world_size": (_I, [_P]),
+    "sg_allreduce_grads": (_I, [_P, _I, _P, _LL, _LL, _I, _P]),
+    "sg_allreduce_join": (_I, [_P, _P]),
+    "sg_g_grad_tail_offset": (_LL, [_P]),
     "sg_train_step": (_I, [_P, C.POINTER(SgTrainState), _P, _P, _P, _I, _P, _P, _P, _I, _P]),
 }
 
@@ -161,10 +170,10 @@ class Context:
     _cache: Dict[tuple, "Context"] = {}
 
     def __init__(self, device: torch.device, image_size: int, latent_dim: int, precision: int,
-                 leaky_slope: float = 0.2, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+                 leaky_slope: float = 0.2, bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0):
         self.lib = load_library()
         self.device = device
-        cfg = SgConfig(image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum)
+        cfg = SgConfig(image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope)
         handle = _P()
         with torch.cuda.device(device):
             check(self.lib.sg_create(C.byref(cfg), C.byref(handle)), "sg_create")
@@ -173,16 +182,17 @@ class Context:
 
     @classmethod
     def get(cls, device: torch.device, image_size: int, latent_dim: int, precision: int, leaky_slope: float = 0.2,
-            bn_eps: float = 1e-5, bn_momentum: float = 0.1) -> "Context":
+            bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0) -> "Context":
         if device.type != "cuda":
             raise RuntimeError("siggan_b200 runs on CUDA (sm_100a) only; there is no CPU path "
                                f"(module is on {device}). Move the module with .to('cuda').")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (device.index, image_size, latent_dim, precision, float(leaky_slope), float(bn_eps), float(bn_momentum))
+        key = (device.index, image_size, latent_dim, precision, float(leaky_slope), float(bn_eps), float(bn_momentum),
+               float(g_act_slope))
         ctx = cls._cache.get(key)
         if ctx is None:
-            ctx = cls(device, image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum)
+            ctx = cls(device, image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope)
             cls._cache[key] = ctx
         return ctx
 
@@ -214,6 +224,38 @@ class Context:
         check(self.lib.sg_set_sync_batchnorm(self.handle, C.cast(cb, _P), None, dist.get_world_size(group), ptr(buf),
                                              buf.numel()), "sg_set_sync_batchnorm")
         self._sync = (cb, buf, errors)   # keep the callback and its buffer alive as long as the library may call them
+
+    def init_comm(self, group=None) -> int:
+        """Library-owned NCCL communicator over the ranks of `group` (default: the world group) for this context's
+        device (include/siggan.h: sg_comm_init). The 128-byte NCCL id travels from rank 0 through torch.distributed's
+        host channel (any backend); afterwards the gradient all-reduces are issued by libsiggan itself
+        (sg_allreduce_grads, and inside sg_train_step phase 0). Returns the world size (1 = nothing to do)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            return 1
+        if self.comm_world() == world:
+            return world
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            check(self.lib.sg_comm_unique_id(ident, 128), "sg_comm_unique_id")
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        with torch.cuda.device(self.device):
+            check(self.lib.sg_comm_init(self.handle, box[0], 128, rank, world), "sg_comm_init")
+        return world
+
+    def comm_world(self) -> int:
+        return int(self.lib.sg_comm_world_size(self.handle))
+
+    def allreduce_grads(self, net: int, flat_grad: torch.Tensor, offset: int = 0, count: int = -1, overlap: bool = False) -> None:
+        check(self.lib.sg_allreduce_grads(self.handle, net, ptr(flat_grad), offset, count, 1 if overlap else 0,
+                                          current_stream(self.device)), "sg_allreduce_grads")
+
+    def allreduce_join(self) -> None:
+        check(self.lib.sg_allreduce_join(self.handle, current_stream(self.device)), "sg_allreduce_join")
 
     def tensor_table(self, net: int) -> List[Tuple[str, int, Tuple[int, ...]]]:
         out = []

@@ -21,6 +21,9 @@
 
 namespace sg {
 namespace {
+// LeakyReLU with slope in [0, 1): slope 0 is ReLU and returns +0 for negative inputs (as fmaxf(x, 0) does)
+__device__ __forceinline__ float act_leaky(float x, float slope) { return fmaxf(x, 0.f) + slope * fminf(x, 0.f); }
+
 
 constexpr int kFC = 32;      // channels of the last generator level (gen…:139,149)
 constexpr int kStripW = 64;  // pixels per strip row
@@ -120,7 +123,7 @@ template <typename T, bool kAffine>
 __global__ void __launch_bounds__(kThreadsG, 1)
 gfinal_fwd_kernel(const T* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                  uint8_t* __restrict__ out_u8, int B, int S) {
+                  uint8_t* __restrict__ out_u8, int B, int S, float act_slope) {
     using Cfg = StripCfg<T>;
     extern __shared__ uint8_t smem_raw[];
     uint64_t *full, *empty;
@@ -202,7 +205,7 @@ gfinal_fwd_kernel(const T* __restrict__ in, const float* __restrict__ scale, con
                     const bool ok = d == 0 ? okl : (d == 2 ? okr : true);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float t = kAffine ? fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f) : v[j];
+                        float t = kAffine ? act_leaky(fmaf(v[j], sc[j], sh[j]), act_slope) : v[j];
                         w2[d][j] = ok ? t : 0.f;
                     }
                 }
@@ -232,7 +235,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreadsG, 1)
 gfinal_bwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ w,
-                  T* __restrict__ dbn, float* __restrict__ part_w, float* __restrict__ part_bn, int B, int S) {
+                  T* __restrict__ dbn, float* __restrict__ part_w, float* __restrict__ part_bn, int B, int S,
+                  float act_slope) {
     using Cfg = StripCfg<T>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ float red[kConsumers / 32][4][kRedFloats / 4 + 1];  // per warp, per slice: 72 dW + 8 s0 + 8 s1 (+ dbias)
@@ -293,7 +297,7 @@ gfinal_bwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, cons
                 }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                d[j] = ap[j] > 0.f ? d[j] : 0.f;
+                d[j] = ap[j] > 0.f ? d[j] : d[j] * act_slope;
                 s0[j] += d[j];
                 s1[j] = fmaf(d[j], yp[j], s1[j]);
             }
@@ -319,7 +323,7 @@ gfinal_bwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, cons
                 step(row, mine);
                 lds8(base + r * Cfg::kPitch, yp, T());
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ap[j] = fmaxf(fmaf(yp[j], sc[j], sh[j]), 0.f);
+                for (int j = 0; j < 8; ++j) ap[j] = act_leaky(fmaf(yp[j], sc[j], sh[j]), act_slope);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
@@ -414,7 +418,7 @@ static bool use_stencil_bf16() {
 
 template <typename T>
 void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift, const float* w, const float* bias,
-                             float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
+                             float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s) {
     if (C != kFC || S % kStripW != 0) return;  // sg_create only admits 64 / 128 with 32 channels at the last level
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
@@ -423,18 +427,20 @@ void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift
     if (scale) {
         static bool ok = set_smem(gfinal_fwd_kernel<T, true>, Cfg::kSmem);
         (void)ok;
-        gfinal_fwd_kernel<T, true><<<grid, kThreadsG, Cfg::kSmem, s>>>(in, scale, shift, w, bias, out, out_u8, B, S);
+        gfinal_fwd_kernel<T, true><<<grid, kThreadsG, Cfg::kSmem, s>>>(in, scale, shift, w, bias, out, out_u8, B, S,
+                                                                       act_slope);
     } else {
         static bool ok = set_smem(gfinal_fwd_kernel<T, false>, Cfg::kSmem);
         (void)ok;
-        gfinal_fwd_kernel<T, false><<<grid, kThreadsG, Cfg::kSmem, s>>>(in, scale, shift, w, bias, out, out_u8, B, S);
+        gfinal_fwd_kernel<T, false><<<grid, kThreadsG, Cfg::kSmem, s>>>(in, scale, shift, w, bias, out, out_u8, B, S,
+                                                                       act_slope);
     }
 }
 
 template <typename T>
 int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
                            const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
-                           int C, cudaStream_t s) {
+                           int C, float act_slope, cudaStream_t s) {
     if (C != kFC || S % kStripW != 0) return 0;
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
@@ -442,54 +448,60 @@ int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, cons
     static bool ok = set_smem(gfinal_bwd_kernel<T>, Cfg::kSmem);
     (void)ok;
     note_launch();
-    gfinal_bwd_kernel<T><<<grid, kThreadsG, Cfg::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, part_bn, B, S);
+    gfinal_bwd_kernel<T><<<grid, kThreadsG, Cfg::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, part_bn, B, S,
+                                                             act_slope);
     vec_finalize(part_w, grid, 9 * kFC + 1, dW, 9 * kFC, dbias, s);
     return grid;
 }
 
 template void final_conv_tanh_stencil<float>(const float*, const float*, const float*, const float*, const float*, float*,
-                                             uint8_t*, int, int, int, cudaStream_t);
+                                             uint8_t*, int, int, int, float, cudaStream_t);
 template void final_conv_tanh_stencil<bf16>(const bf16*, const float*, const float*, const float*, const float*, float*,
-                                            uint8_t*, int, int, int, cudaStream_t);
+                                            uint8_t*, int, int, int, float, cudaStream_t);
 template int final_conv_bwd_stencil<float>(const float*, const float*, const float*, const float*, const float*,
-                                           const float*, float*, float*, float*, float*, float*, int, int, int,
+                                           const float*, float*, float*, float*, float*, float*, int, int, int, float,
                                            cudaStream_t);
 template int final_conv_bwd_stencil<bf16>(const float*, const float*, const bf16*, const float*, const float*,
-                                          const float*, bf16*, float*, float*, float*, float*, int, int, int,
+                                          const float*, bf16*, float*, float*, float*, float*, int, int, int, float,
                                           cudaStream_t);
 
 template <>
 void final_conv_tanh<float>(const float* in, const float* scale, const float* shift, const float* w, const float* bias,
-                            float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
-    final_conv_tanh_stencil<float>(in, scale, shift, w, bias, out, out_u8, B, S, C, s);
+                            float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s) {
+    final_conv_tanh_stencil<float>(in, scale, shift, w, bias, out, out_u8, B, S, C, act_slope, s);
 }
 template <>
 void final_conv_tanh<bf16>(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias,
-                           float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s) {
-    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128))
-        return final_conv_tanh_stencil<bf16>(in, scale, shift, w, bias, out, out_u8, B, S, C, s);
+                           float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s) {
+    // the mma.sync kernels are specialised to ReLU; the LeakyReLU generator of the ablation runs the streaming stencil
+    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128) || (scale && act_slope != 0.f))
+        return final_conv_tanh_stencil<bf16>(in, scale, shift, w, bias, out, out_u8, B, S, C, act_slope, s);
     gfinal_fwd_mma(in, scale, shift, w, bias, out, out_u8, B, S, s);
 }
 
 template <>
 int final_conv_bwd<float>(const float* dout, const float* out, const float* y, const float* scale, const float* shift,
                           const float* w, float* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B,
-                          int S, int C, cudaStream_t s) {
-    return final_conv_bwd_stencil<float>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, s);
+                          int S, int C, float act_slope, cudaStream_t s) {
+    return final_conv_bwd_stencil<float>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, act_slope,
+                                         s);
 }
 template <>
 int final_conv_bwd<bf16>(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                          const float* w, bf16* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
-                         int C, cudaStream_t s) {
-    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128))
-        return final_conv_bwd_stencil<bf16>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C, s);
+                         int C, float act_slope, cudaStream_t s) {
+    if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128) || act_slope != 0.f)
+        return final_conv_bwd_stencil<bf16>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C,
+                                            act_slope, s);
     const int grid = gfinal_bwd_mma(dout, out, y, scale, shift, w, dbn, part_w, part_bn, B, S, dbn ? 0 : 1, nullptr,
                                     nullptr, nullptr, nullptr, nullptr, s);
     vec_finalize(part_w, grid, 9 * kFC + 1, dW, 9 * kFC, dbias, s);
     return grid;
 }
 
-bool final_conv_bwd_two_pass(int S, int C) { return !use_stencil_bf16() && C == kFC && (S == 64 || S == 128); }
+bool final_conv_bwd_two_pass(int S, int C, float act_slope) {
+    return !use_stencil_bf16() && C == kFC && (S == 64 || S == 128) && act_slope == 0.f;
+}
 void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                           const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
                           const float* k3, bf16* dy, int B, int S, cudaStream_t s) {

@@ -372,7 +372,8 @@ __device__ __forceinline__ void ldvec8(const float* __restrict__ p, float (&v)[8
 
 template <typename T>
 __global__ void bn_apply_relu_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, T* __restrict__ a, long n8, int C) {
+                                     const float* __restrict__ shift, T* __restrict__ a, long n8, int C,
+                                     float act_slope) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
         const int c0 = static_cast<int>((i * 8) & (C - 1));
@@ -381,18 +382,22 @@ __global__ void bn_apply_relu_kernel(const T* __restrict__ y, const float* __res
         ldvec8(scale + c0, sc);
         ldvec8(shift + c0, sh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        for (int j = 0; j < 8; ++j) {
+            const float q = fmaf(v[j], sc[j], sh[j]);
+            v[j] = fmaxf(q, 0.f) + act_slope * fminf(q, 0.f);  // slope 0: ReLU (+0 for negative inputs)
+        }
         store8(a + i * 8, v);
     }
 }
 template <typename T>
-void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, cudaStream_t s) {
+void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, float act_slope,
+                   cudaStream_t s) {
     const long n8 = rows * C / 8;
     note_launch();
-    bn_apply_relu_kernel<T><<<blocks_for(n8, 256), 256, 0, s>>>(y, scale, shift, a, n8, C);
+    bn_apply_relu_kernel<T><<<blocks_for(n8, 256), 256, 0, s>>>(y, scale, shift, a, n8, C, act_slope);
 }
-template void bn_apply_relu<float>(const float*, const float*, const float*, float*, long, int, cudaStream_t);
-template void bn_apply_relu<bf16>(const bf16*, const float*, const float*, bf16*, long, int, cudaStream_t);
+template void bn_apply_relu<float>(const float*, const float*, const float*, float*, long, int, float, cudaStream_t);
+template void bn_apply_relu<bf16>(const bf16*, const float*, const float*, bf16*, long, int, float, cudaStream_t);
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, long rows, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,

@@ -74,7 +74,8 @@ void bn_finalize(const float* partial, int chunks, long rows, int C, const float
                  float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
                  float* mean, float* rstd, float* scale, float* shift, cudaStream_t s);
 template <typename T>
-void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, cudaStream_t s);
+void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, float act_slope,
+                   cudaStream_t s);  // act_slope 0 = ReLU, else LeakyReLU(act_slope)
 // BatchNorm backward bookkeeping: dgamma/dbeta (parameter order) and the per-channel coefficients.
 // raw_mean != null: the second partial is sum d*y (not d*xhat) and is converted here with mean/rstd.
 void bn_bwd_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* rstd,
@@ -91,19 +92,19 @@ void col_finalize(const float* partial, int chunks, int C, int perm_c0, float* o
 // activation of the last upsample block is never written to HBM. out fp32 (B,1,S,S); out_u8 optional.
 template <typename T>
 void final_conv_tanh(const T* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
-                     uint8_t* out_u8, int B, int S, int C, cudaStream_t s);
+                     uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s);
 // Backward of the above in one pass over y: dbn = relu'(a) * convT3x3(dout*(1-out^2)), dW, dbias, plus the
 // BatchNorm-backward partial sums of the last block, part_bn[chunk][2][C] = (sum dbn, sum dbn*y) (raw form, see
 // bn_bwd_finalize). part_w must hold chunks*(C*9+1) floats. Returns the number of chunks (<= kMaxChunks).
 template <typename T>
 int final_conv_bwd(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
                    const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S, int C,
-                   cudaStream_t s);
+                   float act_slope, cudaStream_t s);
 void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na, float* out_b, cudaStream_t s);
 // bf16 two-pass form (sg_gfinal_mma.cu): final_conv_bwd with dbn == nullptr computes only the reductions (nothing is
 // written per pixel); after bn_bwd_finalize, final_conv_bwd_apply recomputes d from y and writes the
 // BatchNorm-backward result dy = k1*(d - k2 - xhat*k3) directly — 3 activation-sized HBM passes instead of 5.
-bool final_conv_bwd_two_pass(int S, int C);
+bool final_conv_bwd_two_pass(int S, int C, float act_slope);
 void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                           const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
                           const float* k3, bf16* dy, int B, int S, cudaStream_t s);

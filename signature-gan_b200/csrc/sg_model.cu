@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/siggan.h"
+#include "sg_comm.cuh"
 #include "sg_conv_umma.cuh"
 #include "sg_kernels.cuh"
 
@@ -39,6 +40,10 @@ static int fail(const char* fmt, ...) {
 #define SG_UMMA(expr)                                                  \
     do {                                                               \
         if ((expr) != 0) return fail("%s", sg::umma_last_error());     \
+    } while (0)
+#define SG_COMM(expr)                                                  \
+    do {                                                               \
+        if ((expr) != 0) return fail("%s", sg::comm_last_error());     \
     } while (0)
 #define SG_KCHECK(what)                                                   \
     do {                                                                  \
@@ -205,6 +210,8 @@ struct sg_ctx {
     std::vector<GraphEntry> graphs;
     unsigned long long graph_tick = 0;
     cudaStream_t cap_stream = nullptr;
+    // data-parallel replica: library-owned NCCL communicator (sg_comm_init) for the flat gradient buckets
+    sg::Comm comm;
 };
 
 namespace {
@@ -401,6 +408,8 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     const int F0 = c->gch[0] * 16;
     const int latent = c->cfg.latent_dim;
     const bool fused_eval = !train && !save;  // fold running-stat BN + ReLU into the producing GEMM's epilogue
+    const float gs = c->cfg.g_act_slope;      // 0: ReLU (gen…:60,127); > 0: the ablation's LeakyReLU generator (ablation…:204-207)
+    const int g_act = gs != 0.f ? sg::kActLeaky : sg::kActRelu;
     SG_TRY(pack_generator(c, params, s));
     const double es = c->es;
     if (z) {  // z == nullptr: the caller already cast the latents into the workspace (fused step, outside its graph)
@@ -425,7 +434,8 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
             if (fused_eval) {
                 e.scale = w.scale[0];
                 e.shift = w.shift[0];
-                e.act = sg::kActRelu;
+                e.act = g_act;
+                e.slope = gs;
             }
             SG_UMMA(sg::launch_conv_gemm(sg::kPlain, reinterpret_cast<const bf16*>(w.zp), c->fc_Wp, B, 1, 1, c->Kp, F0, e,
                                          s));
@@ -450,7 +460,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
             }
             PROF("g.fc.bn_apply", 0, 2.0 * es * B * (double)F0);
             sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.fc_y), w.scale[0], w.shift[0],
-                                 reinterpret_cast<T*>(w.fc_a), B, F0, s);
+                                 reinterpret_cast<T*>(w.fc_a), B, F0, gs, s);
         }
     }
     // ---- upsample blocks: ConvT 4x4 s2 p1 (no bias) + BN2d + ReLU (gen…:46-60)
@@ -459,7 +469,8 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     bool tail_done = false;
     for (int i = 0; i < c->L; ++i) {
         const int ih = g_spatial(c, i) / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
-        if (kTC && fused_eval && i == c->L - 1 && fused_tail_enabled() && sg::convt4_final_supported(ih, ih, Cin, Cout)) {
+        if (kTC && fused_eval && i == c->L - 1 && gs == 0.f && fused_tail_enabled() &&
+            sg::convt4_final_supported(ih, ih, Cin, Cout)) {
             // last block + Conv3x3 + tanh in one kernel: the full-resolution 32-channel level never reaches HBM
             const bool u8_only = out_u8 && c->u8_only;
             PROF("g.tail_fused", 2.0 * B * ih * ih * 16.0 * Cin * Cout + 2.0 * B * c->S * c->S * 9.0 * Cout,
@@ -484,7 +495,8 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
             if (fuse) {
                 e.scale = w.scale[i + 1];
                 e.shift = w.shift[i + 1];
-                e.act = sg::kActRelu;
+                e.act = g_act;
+                e.slope = gs;
             } else if (train) {
                 stat_chunks = sg::conv_gemm_stats_chunks(B, ih, ih, Cin, Cout);  // batch statistics from the epilogue
                 if (stat_chunks > 0) e.stats_partial = static_cast<float*>(c->cpart.p);
@@ -515,7 +527,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
             if (i < c->L - 1) {  // the last level is normalised on the fly inside final_conv_tanh
                 PROF((nm + ".bn_apply").c_str(), 0, 2.0 * es * (double)rows * Cout);
                 sg::bn_apply_relu<T>(reinterpret_cast<const T*>(w.y[i]), w.scale[i + 1], w.shift[i + 1],
-                                     reinterpret_cast<T*>(w.a[i]), rows, Cout, s);
+                                     reinterpret_cast<T*>(w.a[i]), rows, Cout, gs, s);
             }
         }
         in = (fuse || i < c->L - 1) ? w.a[i] : w.y[i];
@@ -526,7 +538,7 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     const bool affine = !(kTC && fused_eval);
     sg::final_conv_tanh<T>(reinterpret_cast<const T*>(in), affine ? w.scale[c->L] : nullptr,
                            affine ? w.shift[c->L] : nullptr, params + c->gt[c->g_final_w].offset,
-                           params + c->gt[c->g_final_b].offset, out, out_u8, B, c->S, c->gch[c->L], s);
+                           params + c->gt[c->g_final_b].offset, out, out_u8, B, c->S, c->gch[c->L], gs, s);
     }
     if (save && out_image) {
         cudaError_t e = cudaMemcpyAsync(out_image, w.out, static_cast<size_t>(B) * c->S * c->S * 4,
@@ -545,7 +557,7 @@ constexpr int kAllLevels = -100;
 template <typename T>
 int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float* grad_image, int B, int train,
                  float* grads, float* dz, cudaStream_t s, int only_level = kAllLevels, const void* inject = nullptr,
-                 void* d_prev_out = nullptr) {
+                 void* d_prev_out = nullptr, int stage = 0) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     GWs w = carve_g(c, const_cast<void*>(ws_ptr), B);
     float* cpart = static_cast<float*>(c->cpart.p);
@@ -561,23 +573,31 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
         const size_t px = only_level < 0 ? 1 : static_cast<size_t>(g_spatial(c, only_level)) * g_spatial(c, only_level);
         cudaMemcpyAsync(cur, inject, static_cast<size_t>(B) * px * C * sizeof(T), cudaMemcpyDeviceToDevice, s);
     }
-    const bool run_final = !single || only_level == L - 1;
-    const bool run_fc = !single || only_level < 0;
+    // stage 1: everything down to upsample block 0 (those gradients, the bucket from sg_g_grad_tail_offset() on, are
+    // final afterwards); stage 2: the fc stage, continuing from the scratch buffer stage 1 left; 0: both
+    const bool run_final = (!single || only_level == L - 1) && stage != 2;
+    const bool run_fc = (!single || only_level < 0) && stage != 1;
+    if (stage == 2 && (L & 1)) {  // stage 1 swapped the scratch buffers once per block
+        char* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
     // One pass over the last block's pre-BatchNorm output: d/d(bn output), final-conv dW/dbias, and the
     // BatchNorm-backward reductions of the last block (so that block needs no separate reduction pass below).
     float* part_bn = cpart + static_cast<size_t>(sg::kMaxChunks) * (9 * c->gch[L] + 1);
     int last_chunks = 0;
     // bf16 with batch statistics: pass 1 = reductions only, pass 2 (below) recomputes d and applies BatchNorm backward
-    const bool two_pass = kTC && train && sg::final_conv_bwd_two_pass(c->S, c->gch[L]);
+    const float gs = c->cfg.g_act_slope;
+    const bool two_pass = kTC && train && sg::final_conv_bwd_two_pass(c->S, c->gch[L], gs);
     if (run_final) {
     PROF("g.final_bwd", 4.0 * B * c->S * c->S * 9.0 * c->gch[L],
          (double)B * c->S * c->S * (8.0 + (two_pass ? 1.0 : 2.0) * es * c->gch[L]));
     last_chunks = sg::final_conv_bwd<T>(grad_image, w.out, reinterpret_cast<const T*>(w.y[L - 1]), w.scale[L], w.shift[L],
                                         params + c->gt[c->g_final_w].offset, two_pass ? nullptr : reinterpret_cast<T*>(cur),
                                         grads + c->gt[c->g_final_w].offset, grads + c->gt[c->g_final_b].offset, cpart,
-                                        part_bn, B, c->S, c->gch[L], s);
+                                        part_bn, B, c->S, c->gch[L], gs, s);
     }
-    for (int i = (only_level < 0 && single) ? -1 : lvl_hi; i >= lvl_lo; --i) {
+    for (int i = ((only_level < 0 && single) || stage == 2) ? -1 : lvl_hi; i >= lvl_lo; --i) {
         const int oh = g_spatial(c, i), ih = oh / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
         const long rows = static_cast<long>(B) * oh * oh;
         const BNInfo& bn = c->bn[i + 1];
@@ -620,8 +640,8 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
             }
             PROF((nm + ".dgrad").c_str(), cflops, es * (2.0 * B * ih * ih * Cin + (double)rows * Cout));
             sg::ConvGemmArgs e = epi_args(nxt, Cin);
-            e.gate = reinterpret_cast<const bf16*>(xin);  // ReLU' of the previous block (slope 0)
-            e.slope = 0.f;
+            e.gate = reinterpret_cast<const bf16*>(xin);  // ReLU' (slope 0) / LeakyReLU' of the previous block
+            e.slope = gs;
             SG_UMMA(sg::launch_conv_gemm(sg::kConvS2, reinterpret_cast<const bf16*>(cur), c->g_packB[i], B, oh, oh, Cout,
                                          Cin, e, s));
         } else {
@@ -629,7 +649,7 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
                                 Cout, s);
             sg::Epi e;
             e.gate = xin;
-            e.slope = 0.f;
+            e.slope = gs;
             sg::conv_s2_direct<T>(reinterpret_cast<const T*>(cur), params + c->gt[c->g_up_w[i]].offset,
                                   static_cast<long>(Cout) * 16, 16, e, reinterpret_cast<T*>(nxt), B, oh, oh, Cout, Cin,
                                   s);
@@ -941,7 +961,11 @@ static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d
         sg::adam_step_dev(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->beta1, st->beta2, st->eps,
                           c->counters->adam_d, gscale, s);
     }
-    if (phase == 3) {
+    if (phase == 32) {
+        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, static_cast<const float*>(c->dximg.p), B, 1, g_grads,
+                          nullptr, s, kAllLevels, nullptr, nullptr, 2));
+    }
+    if (phase == 3 || phase == 31) {
         // ---- G step (train…:339-376): G.train() (batch-stat BN), D.eval() (no dropout), labels = 1
         SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, nullptr, B, 1, c->g_ws.p, nullptr, nullptr,
                           true, s));
@@ -952,7 +976,8 @@ static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d
         float* dximg = static_cast<float*>(c->dximg.p);
         // weight gradients of D are not needed here (the reference's autograd computes and discards them)
         SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, fake, c->d_ws.p, nullptr, c->dlogit, B, nullptr, dximg, s));
-        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, dximg, B, 1, g_grads, nullptr, s));
+        SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, dximg, B, 1, g_grads, nullptr, s, kAllLevels, nullptr,
+                          nullptr, phase == 31 ? 1 : 0));
     }
     if (phase == 4) {
         PROF("adam.g", 0, 28.0 * c->g_count);
@@ -999,9 +1024,11 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
         if (c->mirror_d_step != st->d_step) sg::step_set(c->counters, 1, st->d_step, s);
         c->mirror_d_step = st->d_step + 1;
         if (dropout && c->mirror_drop_known) c->mirror_drop += (unsigned long long)sg_d_mask_count(c, 2 * B);
-    } else if (phase == 3) {
+    } else if (phase == 3 || phase == 31) {
         if (!noise_g || !g_grads) return fail("sg_train_step: G phase needs noise_g and g_grads");
         SG_TRY(DISPATCH_T(c, cast_latents_t, c, noise_g, c->g_ws.p, B, s));
+    } else if (phase == 32) {
+        if (!g_grads) return fail("sg_train_step: G phase needs g_grads");
     } else if (phase == 4) {
         if (!g_grads) return fail("sg_train_step: G update needs g_grads");
         if (c->mirror_g_step != st->g_step) sg::step_set(c->counters, 0, st->g_step, s);
@@ -1131,6 +1158,7 @@ int sg_create(const sg_config* cfg, sg_ctx** out) {
         return fail("sg_create: image_size must be 64 or 128, got %d", cfg->image_size);
     if (cfg->latent_dim < 1 || cfg->latent_dim > 512) return fail("sg_create: latent_dim %d unsupported", cfg->latent_dim);
     if (cfg->precision != SG_PREC_BF16 && cfg->precision != SG_PREC_FP32) return fail("sg_create: bad precision");
+    if (!(cfg->g_act_slope >= 0.f && cfg->g_act_slope < 1.f)) return fail("sg_create: g_act_slope must be in [0, 1)");
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
         cudaGetLastError();
@@ -1246,6 +1274,7 @@ void sg_destroy(sg_ctx* c) {
     for (GraphEntry& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    sg::comm_release(&c->comm);
     c->counters_buf.release();
     DevBuf* bufs[] = {&c->packs, &c->bufA, &c->bufB, &c->dpre, &c->wpart, &c->cpart, &c->small,
                       &c->g_ws,  &c->d_ws, &c->x2,   &c->masks2, &c->dximg, &c->gws_tmp};
@@ -1276,7 +1305,50 @@ size_t sg_g_workspace_bytes(const sg_ctx* c, int batch) { return carve_g(c, null
 size_t sg_d_workspace_bytes(const sg_ctx* c, int batch) { return carve_d(c, nullptr, batch).bytes; }
 long long sg_d_mask_count(const sg_ctx* c, int batch) { return mask_offset(c, batch, c->ND); }
 long long sg_d_grad_tail_offset(const sg_ctx* c) { return c->dt[c->d_conv_w[c->ND - 1]].offset; }
+long long sg_g_grad_tail_offset(const sg_ctx* c) { return c->gt[c->g_up_w[0]].offset; }
 long long sg_d_feature_count(const sg_ctx* c) { return (long long)c->dch[c->ND] * 16; }
+
+// ---- library-owned NCCL communicator ------------------------------------------------------------
+int sg_comm_nccl_version(void) { return sg::comm_version(); }
+int sg_comm_unique_id(void* host_id_out, size_t cap) {
+    if (sg::comm_unique_id(host_id_out, cap) != 0) return fail("%s", sg::comm_last_error());
+    return 0;
+}
+int sg_comm_init(sg_ctx* c, const void* host_id, size_t id_bytes, int rank, int world_size) {
+    if (!c) return fail("sg_comm_init: null ctx");
+    DeviceGuard guard(c->device);
+    if (c->comm.nccl) sg::comm_release(&c->comm);
+    if (sg::comm_create(&c->comm, host_id, id_bytes, rank, world_size) != 0) {
+        sg::comm_release(&c->comm);
+        return fail("%s", sg::comm_last_error());
+    }
+    return 0;
+}
+int sg_comm_destroy(sg_ctx* c) {
+    if (!c) return fail("sg_comm_destroy: null ctx");
+    DeviceGuard guard(c->device);
+    sg::comm_release(&c->comm);
+    return 0;
+}
+int sg_comm_world_size(const sg_ctx* c) { return (c && c->comm.nccl) ? c->comm.world : 0; }
+int sg_allreduce_grads(sg_ctx* c, int which, float* grads, long long offset, long long count, int async, void* stream) {
+    if (!c || !grads || offset < 0 || (which != SG_NET_G && which != SG_NET_D))
+        return fail("sg_allreduce_grads: bad argument");
+    const long long total = which == SG_NET_G ? c->g_count : c->d_count;
+    if (count < 0) count = total - offset;
+    if (offset + count > total) return fail("sg_allreduce_grads: [%lld, %lld) exceeds the bucket (%lld)", offset, offset + count, total);
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (async) SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, grads + offset, count, s));
+    else SG_COMM(sg::comm_all_reduce_mean(&c->comm, grads + offset, count, s));
+    return 0;
+}
+int sg_allreduce_join(sg_ctx* c, void* stream) {
+    if (!c) return fail("sg_allreduce_join: null ctx");
+    DeviceGuard guard(c->device);
+    SG_COMM(sg::comm_join(&c->comm, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
 
 long long sg_ws_offset(const sg_ctx* c, int net, int batch, int kind, int index) {
     if (!c || batch < 1) return -1;
@@ -1513,6 +1585,26 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
         SG_TRY(c->counters_buf.ensure(sizeof(sg::StepCounters)));
         c->counters = static_cast<sg::StepCounters*>(c->counters_buf.p);
         cudaMemsetAsync(c->counters, 0, sizeof(sg::StepCounters), s);
+    }
+    if (phase == 0 && c->comm.nccl && c->comm.world > 1) {
+        // data-parallel replica: each gradient group is averaged over the ranks on the communication stream as soon as
+        // it is final, while the rest of that backward pass runs (D: classifier + last conv block first, 76 % of the
+        // bucket; G: the upsample blocks and the final conv first, the fc stage last), and the update waits for both
+        const long long d_tail = sg_d_grad_tail_offset(c), g_tail = sg_g_grad_tail_offset(c);
+        if (st->grad_scale != 0.f && st->grad_scale != 1.f)
+            return fail("sg_train_step: the library's all-reduce averages; grad_scale must be 0 or 1");
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 11, s));
+        SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, d_grads + d_tail, c->d_count - d_tail, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 12, s));
+        SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, d_grads, d_tail, s));
+        SG_COMM(sg::comm_join(&c->comm, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 2, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 31, s));
+        SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, g_grads + g_tail, c->g_count - g_tail, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 32, s));
+        SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, g_grads, g_tail, s));
+        SG_COMM(sg::comm_join(&c->comm, s));
+        return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
     }
     if (phase == 0) {
         static const int seq[4] = {1, 2, 3, 4};

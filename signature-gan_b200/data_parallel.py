@@ -71,6 +71,17 @@ def broadcast_replica_(tensors: Iterable[torch.Tensor], src: int = 0) -> None:
         dist.broadcast(t, src)
 
 
+def init_library_comm(module, group: Optional["dist.ProcessGroup"] = None) -> int:
+    """Give the library context behind `module` (a siggan_b200 Generator / Discriminator / VanillaGAN on its CUDA
+    device) its own NCCL communicator over `group` (sg_comm_init). From then on VanillaGAN's data-parallel steps let
+    libsiggan issue the bucket all-reduces itself, on its communication stream, overlapped with the backward passes
+    (sg_train_step phase 0 / sg_allreduce_grads) instead of going through torch.distributed. Returns the world size."""
+    gen = getattr(module, "generator", module)
+    dev = next(gen.parameters()).device
+    gen._prepare(dev)
+    return gen._ctx.init_comm(group)
+
+
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous [begin, end) share of `n_items` for `rank`; shares differ by at most one item."""
     base, extra = divmod(n_items, world_size)

@@ -97,6 +97,7 @@ class Generator(nn.Module):
         self._flat = L.FlatParams(self, L.SG_NET_G)
         self._ctx: Optional[L.Context] = None
         self._precision = L.precision_from_env()
+        self._act_slope = 0.0      # ReLU; ablation_generator.ConfigurableGenerator sets the LeakyReLU slope
 
     def _init_weights(self, module: nn.Module) -> None:
         """DCGAN initialisation (reference gen…:168-187): N(0, 0.02) weights, zero biases, BN gamma ~ N(1, 0.02)."""
@@ -121,7 +122,7 @@ class Generator(nn.Module):
                                "(its first ConvTranspose2d is hard-wired to 256/512 input channels)")
         bns = self._bn_modules()
         self._ctx = L.Context.get(device, self.output_size, self.latent_dim, self._precision, 0.2, bns[0].eps,
-                                  bns[0].momentum)
+                                  bns[0].momentum, self._act_slope)
         self._flat.sync(self._ctx, bns)
 
     def set_precision(self, precision: str) -> "Generator":

@@ -343,13 +343,17 @@ class VanillaGAN(nn.Module):
         import data_parallel as dp
         if dp.world()[1] > 1:
             # data-parallel: the all-reduce of the bucket's tail (classifier + last conv block, 76 % of the bytes,
-            # final first) runs on NCCL's stream while the rest of the D backward executes
+            # final first) runs on the communication stream while the rest of the D backward executes
             tail = int(sctx.lib.sg_d_grad_tail_offset(sctx.handle))
+            own = sctx.comm_world() > 1      # library-owned NCCL communicator (data_parallel.init_library_comm)
             L.check(sctx.lib.sg_train_step(*args, 11, stream), "sg_train_step(D backward, last block)")
-            w_tail = dp.all_reduce_start(dgrads[tail:])
+            w_tail = sctx.allreduce_grads(L.SG_NET_D, dgrads, tail, -1, overlap=True) if own else dp.all_reduce_start(dgrads[tail:])
             L.check(sctx.lib.sg_train_step(*args, 12, stream), "sg_train_step(D backward, remaining blocks)")
-            w_head = dp.all_reduce_start(dgrads[:tail])
-            dp.all_reduce_finish([w_tail, w_head], dgrads)
+            w_head = sctx.allreduce_grads(L.SG_NET_D, dgrads, 0, tail, overlap=True) if own else dp.all_reduce_start(dgrads[:tail])
+            if own:
+                sctx.allreduce_join()
+            else:
+                dp.all_reduce_finish([w_tail, w_head], dgrads)
         else:
             L.check(sctx.lib.sg_train_step(*args, 1, stream), "sg_train_step(D backward)")
         L.check(sctx.lib.sg_train_step(*args, 2, stream), "sg_train_step(D update)")
@@ -376,8 +380,22 @@ class VanillaGAN(nn.Module):
         ggrads = self.generator._flat.grad_staging()
         stream = L.current_stream(dev)
         args = (sctx.handle, C.byref(st), None, None, L.ptr(noise), B, None, L.ptr(ggrads), L.ptr(self._metrics))
-        L.check(sctx.lib.sg_train_step(*args, 3, stream), "sg_train_step(G backward)")
-        self._allreduce(ggrads)
+        import data_parallel as dp
+        if dp.world()[1] > 1:
+            # the upsample blocks' and the final conv's gradients (the bucket from block 0's weight on) are averaged while
+            # the fc stage of the backward runs; its own gradients follow
+            tail = int(sctx.lib.sg_g_grad_tail_offset(sctx.handle))
+            own = sctx.comm_world() > 1
+            L.check(sctx.lib.sg_train_step(*args, 31, stream), "sg_train_step(G backward, upsample blocks)")
+            w_tail = sctx.allreduce_grads(L.SG_NET_G, ggrads, tail, -1, overlap=True) if own else dp.all_reduce_start(ggrads[tail:])
+            L.check(sctx.lib.sg_train_step(*args, 32, stream), "sg_train_step(G backward, fc stage)")
+            w_head = sctx.allreduce_grads(L.SG_NET_G, ggrads, 0, tail, overlap=True) if own else dp.all_reduce_start(ggrads[:tail])
+            if own:
+                sctx.allreduce_join()
+            else:
+                dp.all_reduce_finish([w_tail, w_head], ggrads)
+        else:
+            L.check(sctx.lib.sg_train_step(*args, 3, stream), "sg_train_step(G backward)")
         L.check(sctx.lib.sg_train_step(*args, 4, stream), "sg_train_step(G update)")
         self.g_optimizer.advance()
         self.generator._flat.expose(ggrads)
@@ -405,11 +423,45 @@ class VanillaGAN(nn.Module):
             dev = self.generator.fc[0].weight.device
             if self._d_loss_hist is None or self._d_loss_hist.numel() != n_critic or self._d_loss_hist.device != dev:
                 self._d_loss_hist = torch.zeros(n_critic, dtype=torch.float32, device=dev)
+        if n_critic == 1 and not self.use_spectral_norm and self.mask_override is None and self._library_dp():
+            return self._dp_step_in_library(real_images)
         for i in range(n_critic):
             m = self.discriminator_step_async(real_images)
             if n_critic > 1:
                 self._d_loss_hist[i:i + 1].copy_(m[0:1])
         return self.generator_step_async(real_images.size(0))
+
+    def _library_dp(self) -> bool:
+        g = self.generator
+        return getattr(g, "_ctx", None) is not None and g._ctx.comm_world() > 1
+
+    def _dp_step_in_library(self, real_images: torch.Tensor) -> torch.Tensor:
+        """One data-parallel D step + G step as ONE library call (sg_train_step phase 0 with a communicator): the
+        bucket all-reduces are issued by libsiggan on its communication stream between the captured phases."""
+        self.discriminator.train()
+        self.generator.train()
+        sctx = self._fused_ready()
+        dev = self.generator._flat.flat.device
+        real = real_images.to(dev, non_blocking=True).contiguous().float()
+        B = real.shape[0]
+        # two draws, as the separate D / G steps make them (the same RNG stream whichever path runs)
+        noise = [torch.randn(B, self.latent_dim, device=dev), torch.randn(B, self.latent_dim, device=dev)]
+        self.d_optimizer.zero_grad()
+        self.g_optimizer.zero_grad()
+        st = self._state()
+        dgrads, ggrads = self.discriminator._flat.grad_staging(), self.generator._flat.grad_staging()
+        L.check(sctx.lib.sg_train_step(sctx.handle, C.byref(st), L.ptr(real), L.ptr(noise[0]), L.ptr(noise[1]), B,
+                                       L.ptr(dgrads), L.ptr(ggrads), L.ptr(self._metrics), 0, L.current_stream(dev)),
+                "sg_train_step(data-parallel step)")
+        self.d_optimizer.advance()
+        self.g_optimizer.advance()
+        self.discriminator._flat.expose(dgrads)
+        self.generator._flat.expose(ggrads)
+        if st.dropout_p > 0:
+            L.DROPOUT.advance(int(sctx.lib.sg_d_mask_count(sctx.handle, 2 * B)))
+        torch._foreach_add_([bn.num_batches_tracked for bn in self.generator._bn_modules()], 1)
+        self.discriminator.eval()     # the modes the reference's G step leaves behind (vanilla…:274-275)
+        return self._metrics
 
     def train_step(self, real_images: torch.Tensor, n_critic: int = 1) -> Dict[str, float]:
         """reference vanilla…:308-336; one device->host read for all returned floats. Every critic step's own loss

@@ -24,7 +24,7 @@ def test_header_symbols_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in siggan.h but not exported"
         assert name in L.SYMBOLS, f"{name} has no ctypes signature"
-    assert lib.sg_abi_version() == 2
+    assert lib.sg_abi_version() == 3
 
 
 def test_no_cpu_path():

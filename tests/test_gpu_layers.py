@@ -135,6 +135,22 @@ def test_generator_layers_backward(precision, size, B):
     z = O.hash_normal((B, 100), 13)
     dout = O.hash_normal((B, 1, size, size), 17) * 1e-3      # d(loss)/d(image): the scale a batch-mean loss produces
     img32, c32, _ = O.g_forward(g_sd, z, size, train=True)
+    nl = len(O.g_channels(size)) - 1
+    if precision == "bf16":
+        # The top unit reads the last block's raw conv output y in its STORAGE type and recomputes BatchNorm + ReLU from it
+        # (the 64x64x32 activation is never stored). Both sides of an isolated-unit comparison must see the same input, so
+        # the oracle's backward runs on that bf16-stored y as well: with the unrounded y the oracle's OWN gradients move by
+        # 1.9e-2 (block weight) / 2.4e-2 (BatchNorm bias) at 64x64, because 0.02 % of the ReLU sides flip — an input
+        # sensitivity of the layer, not an arithmetic error of either implementation (the chained tests of
+        # test_gpu_parity.py cover the forward chain that produces y).
+        t = nl - 1
+        pre = f"upsample_blocks.{t}.block.1"
+        y = c32[f"up{t}.y"]
+        mean = y.mean(dim=[0, 2, 3], keepdim=True)
+        xhat = (y.bfloat16().float() - mean) * c32[f"up{t}.rstd"].view(1, -1, 1, 1)
+        act = torch.relu(g_sd[pre + ".weight"].view(1, -1, 1, 1) * xhat + g_sd[pre + ".bias"].view(1, -1, 1, 1))
+        c32 = dict(c32)
+        c32[f"up{t}.xhat"], c32[f"up{t}.a"], c32["final.in"] = xhat, act, act
     taps32 = {}
     g32 = O.g_backward(g_sd, c32, dout, size, train=True, taps=taps32)
     sd64 = to64(g_sd)
@@ -147,7 +163,6 @@ def test_generator_layers_backward(precision, size, B):
     st = L.current_stream(zs.device)
     stats = fp.stats.clone()
     L.check(lib.sg_g_forward(ctx.handle, L.ptr(fp.flat), L.ptr(stats), L.ptr(zs), B, 1, L.ptr(ws), None, None, st), "g fwd")
-    nl = len(O.g_channels(size)) - 1
     act_dt = torch.bfloat16 if precision == "bf16" else torch.float32
     grads = torch.zeros_like(fp.flat)
     errs = {}

@@ -416,6 +416,76 @@ def test_split_d_backward_phases_equal_the_fused_phase():
     assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1])
 
 
+@pytest.mark.parametrize("size", [64, 128])
+def test_split_g_backward_phases_equal_the_fused_phase(size):
+    """Phases 31 + 32 of sg_train_step (the G bucket's upsample-block part is all-reduced while the fc stage runs) ==
+    phase 3, bitwise; after phase 31 exactly the bucket from sg_g_grad_tail_offset() on is final."""
+    import ctypes as C
+    import _siggan_lib as L
+    B = 24
+    noise = O.hash_normal((B, 100), 5).cuda()
+    grads, stats = [], []
+    for split in (False, True):
+        gan, _, _ = make_gan(size, 6, "bf16")
+        gan.generator.train()
+        gan.discriminator.eval()
+        sctx = gan._fused_ready()
+        st = gan._state(None)
+        gg = gan.generator._flat.grad_staging()
+        gg.fill_(float("nan"))
+        stream = L.current_stream(noise.device)
+        args = (sctx.handle, C.byref(st), None, None, L.ptr(noise), B, None, L.ptr(gg), L.ptr(gan._metrics))
+        for rep in range(3):      # the third call replays the captured graphs of the phases
+            if split:
+                gg.fill_(float("nan"))
+                L.check(sctx.lib.sg_train_step(*args, 31, stream), "phase 31")
+                tail = int(sctx.lib.sg_g_grad_tail_offset(sctx.handle))
+                torch.cuda.synchronize()
+                assert torch.isfinite(gg[tail:]).all() and torch.isnan(gg[:tail]).all()
+                L.check(sctx.lib.sg_train_step(*args, 32, stream), "phase 32")
+            else:
+                L.check(sctx.lib.sg_train_step(*args, 3, stream), "phase 3")
+        torch.cuda.synchronize()
+        grads.append(gg.clone())
+        stats.append(gan.generator._flat.stats.clone())
+    assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1]) and torch.equal(stats[0], stats[1])
+
+
+def test_library_communicator_single_rank():
+    """sg_comm_* / sg_allreduce_grads with a one-rank NCCL communicator (the box the GPU suite runs on has one GPU; the
+    multi-rank path is exercised by bench.py --gpus N, which asserts bit-identical replicas): the id handshake works,
+    the mean over one rank leaves the bucket unchanged in both the in-order and the overlapped form, ranges are checked."""
+    import ctypes as C
+    import _siggan_lib as L
+    gan, _, _ = make_gan(64, 3, "bf16")
+    sctx = gan._fused_ready()
+    lib = sctx.lib
+    assert lib.sg_comm_nccl_version() >= 21800
+    assert lib.sg_comm_world_size(sctx.handle) == 0
+    ident = C.create_string_buffer(128)
+    L.check(lib.sg_comm_unique_id(ident, 128), "unique id")
+    assert lib.sg_comm_unique_id(ident, 64) != 0 and b"128" in lib.sg_last_error()
+    g = torch.randn(sctx.param_count(L.SG_NET_D), device="cuda")
+    st = L.current_stream(g.device)
+    assert lib.sg_allreduce_grads(sctx.handle, L.SG_NET_D, L.ptr(g), 0, -1, 0, st) != 0      # no communicator yet
+    assert b"communicator" in lib.sg_last_error()
+    L.check(lib.sg_comm_init(sctx.handle, ident.raw, 128, 0, 1), "comm init")
+    try:
+        assert lib.sg_comm_world_size(sctx.handle) == 1
+        ref = g.clone()
+        tail = int(lib.sg_d_grad_tail_offset(sctx.handle))
+        L.check(lib.sg_allreduce_grads(sctx.handle, L.SG_NET_D, L.ptr(g), tail, -1, 1, st), "overlapped all-reduce")
+        L.check(lib.sg_allreduce_grads(sctx.handle, L.SG_NET_D, L.ptr(g), 0, tail, 0, st), "in-order all-reduce")
+        L.check(lib.sg_allreduce_join(sctx.handle, st), "join")
+        torch.cuda.synchronize()
+        assert torch.equal(g, ref)
+        assert lib.sg_allreduce_grads(sctx.handle, L.SG_NET_D, L.ptr(g), 10, g.numel(), 0, st) != 0
+        assert b"exceeds" in lib.sg_last_error()
+    finally:
+        L.check(lib.sg_comm_destroy(sctx.handle), "comm destroy")
+    assert lib.sg_comm_world_size(sctx.handle) == 0
+
+
 def test_bulk_sampler_matches_chunked_sampling():
     """sample_uint8_to_host (double-buffered egress) == sample_uint8 chunk by chunk, including a ragged last chunk."""
     gan, _, _ = make_gan(64, 8, "bf16")

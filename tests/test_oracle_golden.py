@@ -182,3 +182,28 @@ def test_spectral_norm_training_steps_match_reference(golden_dir):
         md.update(mg)
         for k, v in gold["metrics"][s].items():
             assert abs(md[k] - v) <= 2e-4 * max(1.0, abs(v)), (s, k, md[k], v)
+
+
+@pytest.mark.parametrize("size", [64, 128])
+def test_leaky_relu_generator_matches_reference_ablation_class(golden_dir, size):
+    """g_forward / g_backward with act_slope = 0.2 == the ablation script's own ConfigurableGenerator(activation=
+    "leaky_relu") (ablation…:216-328), driven unmodified by tests/golden/make_golden_ablation.py."""
+    gold = torch.load(os.path.join(golden_dir, f"ablation_leaky_{size}.pt"), weights_only=False)
+    B, slope = gold["B"], gold["leaky_slope"]
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=gold["seed"])
+    z = O.hash_normal((B, 100), gold["z_seed"])
+    img, _, _ = O.g_forward(g_sd, z, size, train=False, act_slope=slope)
+    assert torch.allclose(img, gold["eval.image"], rtol=RTOL, atol=2e-6)
+    img, gc, stats = O.g_forward(g_sd, z, size, train=True, act_slope=slope)
+    assert torch.allclose(img, gold["train.image"], rtol=RTOL, atol=2e-6)
+    relu_img, _, _ = O.g_forward(g_sd, z, size, train=True)
+    assert not torch.allclose(relu_img, gold["train.image"], atol=1e-3)      # the slope matters
+    for k, ref in gold["train.stats"].items():
+        assert torch.allclose(stats[k].to(ref.dtype), ref, rtol=RTOL, atol=1e-6), k
+    pr, dc = O.d_forward(d_sd, img, size, None)
+    target = torch.full_like(pr, 0.9)                                        # ablation…:421,445: the smoothed label
+    assert abs(float(O.bce(pr, target)) - gold["g_loss"]) < 1e-5
+    dg = O.d_backward(d_sd, dc, O.bce_grad(pr, target), size, None, need_dx=True)
+    gg = O.g_backward(g_sd, gc, dg["__dx"], size, train=True, act_slope=slope)
+    for k in O.trainable_names(g_sd):
+        check_probe(f"g_grad.{k}", gg[k], gold["grads"][k], rtol=GTOL, atol=2e-8 if k != "fc.0.bias" else 1e-6)

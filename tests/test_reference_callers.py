@@ -93,7 +93,8 @@ def test_reference_trainer_and_inference_run_unchanged(tmp_path):
     assert "checkpoint_latest.pt" in r["checkpoints"]
     assert {"epoch", "global_step", "generator_state_dict", "discriminator_state_dict", "g_optimizer_state_dict",
             "d_optimizer_state_dict", "config", "fixed_noise", "best_g_loss"} <= set(r["checkpoint_keys"])
-    assert r["resume_epoch"] == 2 and r["resume_generator_equal"]
+    # the reference saves 'epoch': epoch + 1 (train…:607) and resumes at checkpoint['epoch'] + 1 (train…:476): 3 after 2 epochs
+    assert r["resume_epoch"] == 3 and r["resume_generator_equal"]
     assert all(v == v and abs(v) < 1e3 for v in r["resumed_step_metrics"].values())
     assert r["latent_dim"] == 100 and r["pil_count"] == 10 and r["pil_mode"] == "L" and r["pil_size"] == [64, 64]
     # the PIL images of the reference's per-image conversion loop == the fused uint8 egress on the same latents

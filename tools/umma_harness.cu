@@ -16,11 +16,11 @@
 namespace sg {
 template <typename T>
 void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift, const float* w, const float* bias,
-                             float* out, uint8_t* out_u8, int B, int S, int C, cudaStream_t s);
+                             float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s);
 template <typename T>
 int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
                            const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
-                           int C, cudaStream_t s);
+                           int C, float act_slope, cudaStream_t s);
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
                     uint8_t* out_u8, int B, int S, cudaStream_t s);
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
@@ -327,7 +327,7 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
     CK(cudaMalloc(&dW_b, 289 * 4));
     const float* scp = affine ? d_sc : nullptr;
     const float* shp = affine ? d_sh : nullptr;
-    sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, u8_a, B, S, 32, 0);
+    sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, u8_a, B, S, 32, 0.f, 0);
     sg::gfinal_fwd_mma(y.d, scp, shp, d_w, d_b, out_b, u8_b, B, S, 0);
     CK(cudaDeviceSynchronize());
     int bad = 0;
@@ -345,7 +345,7 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
     }
     if (affine) {
         const int ca = sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw,
-                                                        pbn_a, B, S, 32, 0);
+                                                        pbn_a, B, S, 32, 0.f, 0);
         const int cb = sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0, nullptr, nullptr,
                                           nullptr, nullptr, nullptr, 0);
         sg::vec_finalize(pw, cb, 289, dW_b, 288, dW_b + 288, 0);
@@ -416,11 +416,11 @@ static int test_gfinal(const char* name, int B, int S, bool affine, bool perf) {
         for (int k = 0; k < 4; ++k) {
             for (int i = 0; i < 13; ++i) {
                 if (i == 3) cudaEventRecord(e0);
-                if (k == 0) sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, nullptr, B, S, 32, 0);
+                if (k == 0) sg::final_conv_tanh_stencil<bf16>(y.d, scp, shp, d_w, d_b, out_a, nullptr, B, S, 32, 0.f, 0);
                 if (k == 1) sg::gfinal_fwd_mma(y.d, scp, shp, d_w, d_b, out_b, nullptr, B, S, 0);
                 if (k == 2 && affine)
                     sg::final_conv_bwd_stencil<bf16>(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_a, dW_a, dW_a + 288, pw, pbn_a,
-                                                     B, S, 32, 0);
+                                                     B, S, 32, 0.f, 0);
                 if (k == 3 && affine)
                     sg::gfinal_bwd_mma(d_dout, out_a, y.d, d_sc, d_sh, d_w, dbn_b, pw, pbn_b, B, S, 0, nullptr, nullptr, nullptr,
                                        nullptr, nullptr, 0);
