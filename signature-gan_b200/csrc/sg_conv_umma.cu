@@ -191,10 +191,14 @@ __device__ __forceinline__ uint32_t epi_off(int row, int k) { return row * 128 +
 // sum of squares of the stored (bf16-rounded) outputs — the BatchNorm batch statistics of gen…:58 — and the CTA writes
 // one partial row stats_partial[blockIdx.x][2][BN], so that no separate pass over the convolution output is needed.
 template <int BN, int BK, bool kPair, bool kStats>
-__global__ void __launch_bounds__(kThreads, kStats ? 1 : ConvCfg<BN, BK, kPair>::kCtasPerSm)  // statistics: +32..64 registers
+__global__ void __launch_bounds__(kThreads, (kStats && (BN > 64 || (kPair && BN == 64))) ? 1 : ConvCfg<BN, BK, kPair>::kCtasPerSm)  // statistics: +32..64 registers
 conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     using Cfg = ConvCfg<BN, BK, kPair>;
     constexpr int STAGES = Cfg::kStages;
+    // Epilogues with fused reductions (training-mode ConvT forward: BatchNorm statistics; BatchNorm-gated data gradient:
+    // BatchNorm-backward sums) have no bias / affine / activation / dropout mask (launch_conv_gemm checks), which keeps
+    // the thin variants inside the 96-register budget of two CTAs per SM
+    constexpr bool kGateStats = kStats;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;
@@ -346,9 +350,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
         const int half = (warp - 2) >> 2;             // which half of the unit's accumulator columns
         uint8_t* stage = epi_smem + (warp - 2) * kEpiStageBytes;
         const uint32_t stage_u32 = smem_u32(stage);
+        const bool ygate = args.gate && args.gate_scale;  // BatchNorm gate: sign of y * gate_scale + gate_shift
         const bool vec_ok = (((args.bias ? reinterpret_cast<uintptr_t>(args.bias) : 0) |
                               (args.scale ? reinterpret_cast<uintptr_t>(args.scale) : 0) |
                               (args.shift ? reinterpret_cast<uintptr_t>(args.shift) : 0) |
+                              (ygate ? reinterpret_cast<uintptr_t>(args.gate_scale) | reinterpret_cast<uintptr_t>(args.gate_shift) : 0) |
                               (args.mask ? reinterpret_cast<uintptr_t>(args.mask) : 0)) & 15) == 0 &&
                             (args.ldmask % 4 == 0);
         const int lgR = 31 - __clz(R), lgW = 31 - __clz(args.GW);
@@ -428,13 +434,17 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                 const int sub = kPair ? c0 / BN : 0;
                 const int n_base = tc.tile_n * BN + (kPair ? c0 - sub * BN : c0);
                 const int n8 = n_base + wr_k * 8;
-                float b8[8], sc8[8], sh8[8], m8[8];
-                if (args.bias) load_vec8(args.bias + n8, vec_ok, b8);
-                if (args.scale) {
+                float b8[8], sc8[8], sh8[8], m8[8], gs8[8], gh8[8];
+                if (ygate) {
+                    load_vec8(args.gate_scale + n8, vec_ok, gs8);
+                    load_vec8(args.gate_shift + n8, vec_ok, gh8);
+                }
+                if (!kGateStats && args.bias) load_vec8(args.bias + n8, vec_ok, b8);
+                if (!kGateStats && args.scale) {
                     load_vec8(args.scale + n8, vec_ok, sc8);
                     load_vec8(args.shift + n8, vec_ok, sh8);
                 }
-                if (args.mask && one_img) {
+                if (!kGateStats && args.mask && one_img) {
                     const int mi = row0 < args.M_total ? (mode != kPlain ? row0 >> lgR : 0) : 0;
                     load_vec8(args.mask + static_cast<size_t>(mi) * args.ldmask + n8, vec_ok, m8);
                 }
@@ -470,22 +480,23 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                     const float4 lo4 = lds128f(stage_u32 + epi_off(r, 2 * wr_k));
                     const float4 hi4 = lds128f(stage_u32 + epi_off(r, 2 * wr_k + 1));
                     float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                    if (args.bias) {
+                    if (!kGateStats && args.bias) {
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) f[jj] += b8[jj];
                     }
-                    if (args.scale) {
+                    if (!kGateStats && args.scale) {
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc8[jj], sh8[jj]);
                     }
-                    if (args.act == kActRelu) {
+                    if (kGateStats) {
+                    } else if (args.act == kActRelu) {
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
                     } else if (args.act == kActLeaky) {
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : f[jj] * args.slope;
                     }
-                    if (args.mask) {
+                    if (!kGateStats && args.mask) {
                         if (one_img) {
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) f[jj] *= m8[jj];
@@ -501,8 +512,13 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                         const uint32_t w4[4] = {gq[i].x, gq[i].y, gq[i].z, gq[i].w};
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
-                            f[tt * 2] *= bf16_lo(w4[tt]) > 0.f ? 1.f : args.slope;
-                            f[tt * 2 + 1] *= bf16_hi(w4[tt]) > 0.f ? 1.f : args.slope;
+                            float g0 = bf16_lo(w4[tt]), g1 = bf16_hi(w4[tt]);
+                            if (ygate) {
+                                g0 = fmaf(g0, gs8[tt * 2], gh8[tt * 2]);
+                                g1 = fmaf(g1, gs8[tt * 2 + 1], gh8[tt * 2 + 1]);
+                            }
+                            f[tt * 2] *= g0 > 0.f ? 1.f : args.slope;
+                            f[tt * 2 + 1] *= g1 > 0.f ? 1.f : args.slope;
                         }
                     }
                     const uint4 d = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
@@ -512,13 +528,16 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
                         if (kStats) {
                             const int cs = kStats ? ci : 0;
                             const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
+                            const uint32_t y4[4] = {gq[i].x, gq[i].y, gq[i].z, gq[i].w};
 #pragma unroll
                             for (int tt = 0; tt < 4; ++tt) {
                                 const float lo = bf16_lo(w4[tt]), hi = bf16_hi(w4[tt]);
+                                // forward statistics: sum, sum of squares; BatchNorm gate: sum d, sum d * y
+                                const float olo = ygate ? bf16_lo(y4[tt]) : lo, ohi = ygate ? bf16_hi(y4[tt]) : hi;
                                 st_sum[cs][2 * tt] += lo;
-                                st_sq[cs][2 * tt] = fmaf(lo, lo, st_sq[cs][2 * tt]);
+                                st_sq[cs][2 * tt] = fmaf(lo, olo, st_sq[cs][2 * tt]);
                                 st_sum[cs][2 * tt + 1] += hi;
-                                st_sq[cs][2 * tt + 1] = fmaf(hi, hi, st_sq[cs][2 * tt + 1]);
+                                st_sq[cs][2 * tt + 1] = fmaf(hi, ohi, st_sq[cs][2 * tt + 1]);
                             }
                         }
                     }
@@ -559,14 +578,19 @@ conv_umma_kernel(const __grid_constant__ ConvGemmArgs args) {
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // (cluster: the peer may still multicast into / arrive on this CTA)
     if (kStats && warp >= 2) {
-        // paired units: every epilogue warp covered all BN channels (of one px); fold the 8 warps in a fixed order
+        // fold the warps that covered a channel in a fixed order. Paired units (and accumulators narrower than 64
+        // columns): every active epilogue warp covered all BN channels; otherwise the warps of column half h = ch /
+        // kColsPerWarp (one per TMEM lane quarter) did.
         const int e = (warp - 2) * 32 + lane;
         if (e < 2 * BN) {
             const int which = e / BN, ch = e - which * BN;
+            constexpr bool kAllCover = kPair || Cfg::kAccCols < 64;
+            const int h = kAllCover ? 0 : ch / Cfg::kColsPerWarp;
+            const int cc = ch - h * Cfg::kColsPerWarp;
             float tot = 0.f;
 #pragma unroll
-            for (int wi = 0; wi < kEpiWarps; ++wi)
-                tot += reinterpret_cast<const float*>(epi_smem + wi * kEpiStageBytes)[which * Cfg::kColsPerWarp + ch];
+            for (int wi = 0; wi < (kAllCover ? Cfg::kActiveEpiWarps : 4); ++wi)
+                tot += reinterpret_cast<const float*>(epi_smem + (h * 4 + wi) * kEpiStageBytes)[which * Cfg::kColsPerWarp + cc];
             args.stats_partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * BN + ch] = tot;
         }
     }
@@ -594,7 +618,10 @@ static int conv_grid(int total_tiles) {
 template <int BN, int BK, bool kPair, bool kStats = false>
 static int launch_cfg(const ConvGemmArgs& a, int total_tiles, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, BK, kPair>;
-    if (kPair && !kStats && a.stats_partial) return launch_cfg<BN, BK, kPair, kPair>(a, total_tiles, stream);
+    // statistics variants exist for the paired transposed convolutions and for the BatchNorm-gated data gradients of
+    // the Generator's thin levels (sg_model.cu asks conv_gemm_gate_stats_chunks first)
+    constexpr bool kHasStats = kPair || (BN == 32 && BK == 32) || (BN == 64 && BK == 32) || (BN == 128 && BK == 64);
+    if (kHasStats && !kStats && a.stats_partial) return launch_cfg<BN, BK, kPair, kHasStats>(a, total_tiles, stream);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, kPair, kStats>,
@@ -656,8 +683,23 @@ static bool conv2_enabled() {  // SIGGAN_CONV2=0 keeps every layer on the one-CT
 // sg_convs2_thin.cu
 bool convs2_thin_supported(int inH, int inW, int Cin, int Cout);
 size_t convs2_thin_scratch_bytes();
+int convs2_thin_ctas(int nimg, int inH);
 int launch_convs2_thin(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
-                       __nv_bfloat16* out, const __nv_bfloat16* gate, float slope, void* scratch, cudaStream_t stream);
+                       __nv_bfloat16* out, const __nv_bfloat16* gate, float slope, void* scratch, cudaStream_t stream,
+                       const float* gate_scale, const float* gate_shift, float* stats_partial);
+
+// Rows of stats_partial a BatchNorm-gated kConvS2 launch writes (= its grid), 0 when the shape cannot fuse them.
+int conv_gemm_gate_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout) {
+    if (convs2_thin_supported(inH, inW, Cin, Cout)) return convs2_thin_ctas(nimg, inH);
+    const int BK = (Cin % 64 == 0) ? 64 : 32;
+    if (!((Cout == 32 && BK == 32) || (Cout == 64 && BK == 32) || (Cout == 128 && BK == 64)) || Cin % BK != 0) return 0;
+    const int GH = inH / 2, GW = inW / 2;
+    if (!is_pow2(GH) || !is_pow2(GW) || GW > kTileM) return 0;
+    const int cl = Cout >= 128 ? 2 : 1;
+    const int tiles = (((nimg * GH * GW + kTileM - 1) / kTileM) + cl - 1) / cl;   // schedule units (one per cluster)
+    const int slots = sm_count() * (Cout <= 64 ? 2 : 1) / cl;
+    return (tiles < slots ? tiles : slots) * cl;
+}
 static void* thin_scratch() {  // stacked weights of the thin stride-2 kernel, one buffer per device
     static void* buf[16] = {};
     int dev = 0;
@@ -670,16 +712,16 @@ static void* thin_scratch() {  // stacked weights of the thin stride-2 kernel, o
 int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
                      int Cin, int Cout, ConvGemmArgs a, cudaStream_t stream) {
     if (mode == kConvS2 && convs2_thin_supported(inH, inW, Cin, Cout) && !a.bias && !a.scale && !a.mask &&
-        !a.stats_partial && a.act == kActNone && a.ldo == Cout) {
+        (!a.stats_partial || (a.gate && a.gate_scale)) && a.act == kActNone && a.ldo == Cout) {
         // thin fine-grid tensors (generator's last block, data gradient): pixel-pair rows + col2im epilogue
         void* scratch = thin_scratch();
         if (!scratch) SG_FAIL("convs2_thin: cannot allocate the weight scratch");
         if (launch_convs2_thin(in, w_packed, nimg, inH, inW, static_cast<__nv_bfloat16*>(a.out), a.gate, a.slope, scratch,
-                               stream))
+                               stream, a.gate_scale, a.gate_shift, a.stats_partial))
             SG_FAIL("convs2_thin launch failed: %s (%s)", cudaGetErrorString(cudaGetLastError()), umma_last_error());
         return 0;
     }
-    if (mode != kPlain && !a.stats_partial && a.ldo == Cout && conv2_enabled() &&
+    if (mode != kPlain && !a.stats_partial && !a.gate_scale && a.ldo == Cout && conv2_enabled() &&
         conv2_supported(mode, inH, inW, Cin, Cout)) {
         // CTA-pair kernel with shared shifted-input tiles (D conv1 forward, D conv1 / conv2 data gradients)
         if (launch_conv2(mode, in, w_packed, nimg, inH, inW, Cin, Cout, a, stream))
@@ -755,7 +797,11 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
     const int cl = BN >= 128 ? 2 : 1;  // = ConvCfg::kCluster
     if (make_map_2d(&a.bmap, w_packed, (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, BK, BN / cl)) return -1;
     const bool pair = mode == kConvT && BN <= 128;
-    if (a.stats_partial && !(pair && BN == Cout)) SG_FAIL("conv_gemm: fused statistics need a paired transposed convolution");
+    if (a.stats_partial && !(BN == Cout && (pair || (mode == kConvS2 && a.gate && a.gate_scale &&
+                                                      conv_gemm_gate_stats_chunks(nimg, inH, inW, Cin, Cout) > 0))))
+        SG_FAIL("conv_gemm: fused statistics need a paired transposed convolution or a BatchNorm-gated data gradient");
+    if (a.stats_partial && (a.bias || a.scale || a.mask || a.act != kActNone || (pair && a.gate)))
+        SG_FAIL("conv_gemm: an epilogue with fused reductions has no bias / affine / activation / mask");
     const int total_tiles = (((a.M_total + kTileM - 1) / kTileM + cl - 1) / cl) * (Cout / BN) *
                             (mode == kConvT ? (pair ? 2 : 4) : 1);
 #define SG_DISPATCH(bn, bk)                                                   \

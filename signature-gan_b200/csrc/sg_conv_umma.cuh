@@ -39,7 +39,14 @@ struct ConvGemmArgs {
     const float* mask;  // [nimg][ldmask] dropout keep-scale, or null
     int ldmask;
     const __nv_bfloat16* gate;  // saved activation at the output position: v *= (g>0 ? 1 : slope)
-    float* stats_partial;       // kConvT only, optional: [conv_gemm_stats_chunks()][2][N_total] per-CTA sum / sum of squares
+    float* stats_partial;       // optional per-CTA partial rows [chunks][2][N_total]: paired kConvT — sum / sum of squares of
+                                // the stored outputs (conv_gemm_stats_chunks); BatchNorm gate — (sum d, sum d*y), see below
+    // BatchNorm gate (training backward of the Generator): `gate` is the PRE-BatchNorm output y of the layer below and the
+    // activation derivative is taken on y*gate_scale[n] + gate_shift[n] (the expression that layer's forward applied). With
+    // stats_partial the epilogue also accumulates (sum d, sum d*y) of its stored outputs d — the raw reductions of that
+    // layer's BatchNorm backward (bn_bwd_finalize), rows = conv_gemm_gate_stats_chunks() — replacing a pass over d and y.
+    const float* gate_scale;
+    const float* gate_shift;
     // Producer schedule (filled by launch_conv_gemm): entry e of a section = {A channel offset, packed (dx+1) | (dy+1)<<2 |
     // parity view<<4, B k-offset, 0} for the e-th K step; transposed convolutions keep one section per output parity.
     // It lives in the parameter (constant) bank so that the producer warp reads it with uniform loads.
@@ -79,6 +86,8 @@ int launch_convt4_final(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, 
                         uint8_t* out_u8, cudaStream_t stream);
 // Number of partial rows a kConvT launch with `stats_partial` set writes, 0 if this shape cannot fuse the statistics.
 int conv_gemm_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout);
+// Same for a kConvS2 launch with a BatchNorm gate (gate_scale / gate_shift / stats_partial): 0 = not fusable.
+int conv_gemm_gate_stats_chunks(int nimg, int inH, int inW, int Cin, int Cout);
 
 // dW[m][n][ky][kx] (fp32, PyTorch (M,N,4,4) layout) = sum_pix coarse[pix][m] * fine[2*pix-1+k][n].
 // `partial` must hold splits*16*Mc*Nf floats. `accumulate` adds into dW instead of overwriting.

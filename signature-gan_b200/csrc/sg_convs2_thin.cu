@@ -36,7 +36,8 @@ constexpr int kS2StageBytes = 4 * kS2BoxBytes;
 constexpr int kS2Stages = 2;
 constexpr int kS2WBytes = 4 * 96 * 128;  // [ky][96 rows][64] bf16
 constexpr int kS2TmemCols = 256;         // 2 accumulators of 96 columns, 128 apart
-constexpr int kS2SmemBytes = kS2WBytes + kS2Stages * kS2StageBytes + 1024 + 256;
+constexpr int kS2StatBytes = 8 * 32 * 4;  // per epilogue warp: (sum d, sum d*y) of its 16 channels
+constexpr int kS2SmemBytes = kS2WBytes + kS2Stages * kS2StageBytes + 1024 + 256 + kS2StatBytes;
 
 struct ConvS2ThinArgs {
     CUtensorMap xmap[2];  // fine tensor, row-parity planes: [64 (px,c)][32 pairs][GH rows][N]
@@ -45,6 +46,13 @@ struct ConvS2ThinArgs {
     __nv_bfloat16* out;          // [N][GH][32][32]
     const __nv_bfloat16* gate;   // saved activation of the layer below at the output position, or null
     float slope;
+    // BatchNorm-gate form (training backward): `gate` is the layer below's PRE-BatchNorm output y; the activation
+    // derivative is taken on y * gate_scale[c] + gate_shift[c] (the expression its forward applied), and the CTA also
+    // writes stats_partial[blockIdx.x][2][32] = (sum d, sum d * y) over its stored outputs d — the raw reductions of that
+    // layer's BatchNorm backward (bn_bwd_finalize), which then needs no pass of its own over d and y.
+    const float* gate_scale;
+    const float* gate_shift;
+    float* stats_partial;
 };
 
 // Wt[ky][t*32 + n][px*32 + c] from the data-gradient pack w[n][ky*4+kx][c] (n = output channel of this convolution)
@@ -86,6 +94,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) convs2_thin_kernel(const __grid
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* stat_slots = reinterpret_cast<float*>(ring + kS2Stages * kS2StageBytes + 256);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int tpi = args.GH / 4;  // tiles per image
@@ -177,6 +186,15 @@ __global__ void __launch_bounds__(kS2Threads, 1) convs2_thin_kernel(const __grid
         const int q = warp & 3;              // TMEM lane quarter = output row of the tile
         const int half = (warp - 2) >> 2;    // which 16 of the 32 output channels
         const int c0 = half * 16;
+        const bool ygate = args.gate && args.gate_scale;
+        const bool stats = ygate && args.stats_partial;
+        float gsc[16], gsh[16], s0[16], s1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            gsc[j] = ygate ? __ldg(args.gate_scale + c0 + j) : 1.f;
+            gsh[j] = ygate ? __ldg(args.gate_shift + c0 + j) : 0.f;
+            s0[j] = s1[j] = 0.f;
+        }
         uint32_t g = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++g) {
             const int acc = g & 1;
@@ -212,17 +230,56 @@ __global__ void __launch_bounds__(kS2Threads, 1) convs2_thin_kernel(const __grid
                 const uint32_t w8[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    f[2 * j] *= __uint_as_float(w8[j] << 16) > 0.f ? 1.f : args.slope;
-                    f[2 * j + 1] *= __uint_as_float(w8[j] & 0xFFFF0000u) > 0.f ? 1.f : args.slope;
+                    // plain gate: sign of the saved activation; BatchNorm gate: sign of y * scale + shift (ygate)
+                    f[2 * j] *= fmaf(__uint_as_float(w8[j] << 16), gsc[2 * j], gsh[2 * j]) > 0.f ? 1.f : args.slope;
+                    f[2 * j + 1] *=
+                        fmaf(__uint_as_float(w8[j] & 0xFFFF0000u), gsc[2 * j + 1], gsh[2 * j + 1]) > 0.f ? 1.f : args.slope;
                 }
             }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = s2_pack(f[2 * j], f[2 * j + 1]);
             uint4* op = reinterpret_cast<uint4*>(args.out + opix * 32 + c0);
-            op[0] = make_uint4(s2_pack(f[0], f[1]), s2_pack(f[2], f[3]), s2_pack(f[4], f[5]), s2_pack(f[6], f[7]));
-            op[1] = make_uint4(s2_pack(f[8], f[9]), s2_pack(f[10], f[11]), s2_pack(f[12], f[13]), s2_pack(f[14], f[15]));
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (stats) {  // of the STORED (bf16-rounded) values, as a separate reduction pass over `out` would see them
+                const uint32_t w8[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dlo = __uint_as_float(pk[j] << 16), dhi = __uint_as_float(pk[j] & 0xFFFF0000u);
+                    s0[2 * j] += dlo;
+                    s0[2 * j + 1] += dhi;
+                    s1[2 * j] = fmaf(dlo, __uint_as_float(w8[j] << 16), s1[2 * j]);
+                    s1[2 * j + 1] = fmaf(dhi, __uint_as_float(w8[j] & 0xFFFF0000u), s1[2 * j + 1]);
+                }
+            }
+        }
+        if (stats) {  // warp totals (fixed shuffle tree: deterministic) -> this warp's slot [2][16]
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = s0[j], b = s1[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) {
+                    stat_slots[(warp - 2) * 32 + j] = a;
+                    stat_slots[(warp - 2) * 32 + 16 + j] = b;
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (args.gate && args.gate_scale && args.stats_partial && threadIdx.x < 64) {
+        // fold the four row-quarter warps of each channel half in a fixed order; one partial row per CTA
+        const int which = threadIdx.x >> 5, ch = threadIdx.x & 31, hf = ch >> 4;
+        float tot = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) tot += stat_slots[(hf * 4 + qq) * 32 + which * 16 + (ch & 15)];
+        args.stats_partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * 32 + ch] = tot;
+    }
     if (warp == 1) tmem_dealloc(tmem_base, kS2TmemCols);
 }
 
@@ -250,8 +307,14 @@ size_t convs2_thin_scratch_bytes() { return static_cast<size_t>(kS2WBytes); }
 
 // w_packed: the data-gradient pack [Cout][16][Cin] (K contiguous). scratch: convs2_thin_scratch_bytes() of device
 // memory for the stacked weights (rebuilt by every call: 24 K elements).
+int convs2_thin_ctas(int nimg, int inH) {
+    const int tiles = nimg * (inH / 2 / 4);
+    return tiles < sm_count_s2() ? tiles : sm_count_s2();
+}
+
 int launch_convs2_thin(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, int nimg, int inH, int inW,
-                       __nv_bfloat16* out, const __nv_bfloat16* gate, float slope, void* scratch, cudaStream_t stream) {
+                       __nv_bfloat16* out, const __nv_bfloat16* gate, float slope, void* scratch, cudaStream_t stream,
+                       const float* gate_scale, const float* gate_shift, float* stats_partial) {
     ConvS2ThinArgs a;
     memset(&a, 0, sizeof(a));
     a.GH = inH / 2;
@@ -260,6 +323,9 @@ int launch_convs2_thin(const __nv_bfloat16* in, const __nv_bfloat16* w_packed, i
     a.out = out;
     a.gate = gate;
     a.slope = slope;
+    a.gate_scale = gate_scale;
+    a.gate_shift = gate_shift;
+    a.stats_partial = stats_partial;
     __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(scratch);
     note_launch();
     convs2_thin_pack_kernel<<<(4 * 96 * 64 + 255) / 256, 256, 0, stream>>>(w_packed, wt);

@@ -40,80 +40,87 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         bs[nb][1] = bias[nb * 8 + 2 * t4 + 1];
     }
     const int ky0 = t4 >> 1, kxo = 2 * (t4 & 1);
-    // 32-bit shift/mask index math (S and therefore tpr are powers of two): the 64-bit runtime division this replaces
-    // cost more issue slots per 16-pixel tile than its 8 MMAs
-    const int lg_tpr = ilog2(tpr);
-    const int total = B * O * tpr;
-    const int stride = static_cast<int>(gridDim.x) * 8;
-    // The kernel is latency-bound (ncu: half of all stall samples wait on the image / mask loads at their first use):
-    // the loads of the NEXT tile are issued before the current tile is computed.
-    struct TileIn {
-        float xv[8];     // im2col values: [h][rr][e]
-        float2 mk[8];    // dropout keep-scale of the tile's image, this lane's two channels per n-block
-    };
-    auto load_tile = [&](int tile, TileIn& in) {
-        const int ox0 = (tile & (tpr - 1)) * 16;
-        const int r = tile >> lg_tpr;
-        const int oy = r & (O - 1);
-        const long n = r >> lgO;
+    // A warp walks a strip of 16 output columns down ONE image (O tiles). The kernel is bound by load issue / latency
+    // (ncu: half of all stall samples wait on the image / mask loads at their first use), and in this order
+    //   * the dropout keep-scales of the image are loaded once per strip instead of once per tile,
+    //   * a tile's lower two input rows (h = 1: iy = 2 oy + 1 + ky0) are the next tile's upper two (h = 0), so only four
+    //     image values per lane and tile are loaded instead of eight — issued one tile ahead of their use.
+    constexpr int kSeg = 8;  // output rows per unit: short enough to balance the warps, long enough to amortise the set-up
+    const int segs = O / kSeg, lg_tpr = ilog2(tpr), lg_segs = ilog2(segs);
+    const int units = B * segs * tpr;  // (image, row segment, strip)
+    const int wstride = static_cast<int>(gridDim.x) * 8;
+    for (int u = static_cast<int>(blockIdx.x) * 8 + warp; u < units; u += wstride) {
+        const int strip = u & (tpr - 1);
+        const int oy_lo = ((u >> lg_tpr) & (segs - 1)) * kSeg;
+        const long n = u >> (lg_tpr + lg_segs);
+        const int ox0 = strip * 16;
         const float* xi = x + n * S * S;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int iy = 2 * oy - 1 + ky0 + 2 * h;
-            const bool yok = iy >= 0 && iy < S;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int ix = 2 * (ox0 + gid + 8 * rr) - 1 + kxo;
-                in.xv[(h * 2 + rr) * 2] = (yok && ix >= 0) ? __ldg(xi + iy * S + ix) : 0.f;
-                in.xv[(h * 2 + rr) * 2 + 1] = (yok && ix + 1 < S) ? __ldg(xi + iy * S + ix + 1) : 0.f;
-            }
-        }
+        float2 mk[8];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb)
-            in.mk[nb] = mask ? __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4))
-                             : make_float2(1.f, 1.f);
-    };
-    TileIn nxt;
-    int tile = static_cast<int>(blockIdx.x) * 8 + warp;
-    if (tile < total) load_tile(tile, nxt);
-    for (; tile < total; tile += stride) {
-        const TileIn cur = nxt;
-        if (tile + stride < total) load_tile(tile + stride, nxt);
-        const int ox0 = (tile & (tpr - 1)) * 16;
-        const int r = tile >> lg_tpr;
-        const int oy = r & (O - 1);
-        const long n = r >> lgO;
-        uint32_t af[4];
+            mk[nb] = mask ? __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4)) : make_float2(1.f, 1.f);
+        int ixs[2];
+        bool okl[2], okr[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) af[k] = pack2_bf16(cur.xv[2 * k], cur.xv[2 * k + 1]);
-        float acc[8][4];
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-            acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-            mma_bf16(acc[nb], af, bw[nb][0], bw[nb][1]);
+        for (int rr = 0; rr < 2; ++rr) {
+            ixs[rr] = 2 * (ox0 + gid + 8 * rr) - 1 + kxo;
+            okl[rr] = ixs[rr] >= 0;
+            okr[rr] = ixs[rr] + 1 < S;
         }
+        auto load_rows = [&](int iy, float (&v)[4]) {  // v[rr*2 + e] = x[iy][ixs[rr] + e] (0 outside the image)
+            const bool yok = iy >= 0 && iy < S;
+            const float* row = xi + iy * S;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-            const float m0 = cur.mk[nb].x, m1 = cur.mk[nb].y;
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float t = acc[nb][e] + bs[nb][e & 1];
-                v[e] = (t > 0.f ? t : t * slope) * ((e & 1) ? m1 : m0);
+            for (int rr = 0; rr < 2; ++rr) {
+                v[rr * 2] = (yok && okl[rr]) ? __ldg(row + ixs[rr]) : 0.f;
+                v[rr * 2 + 1] = (yok && okr[rr]) ? __ldg(row + ixs[rr] + 1) : 0.f;
             }
-            const uint32_t off = static_cast<uint32_t>((nb ^ gid) << 4) + t4 * 4;   // (gid + 8) & 7 == gid
-            *reinterpret_cast<uint32_t*>(stage + gid * 128 + off) = pack2_bf16(v[0], v[1]);
-            *reinterpret_cast<uint32_t*>(stage + (gid + 8) * 128 + off) = pack2_bf16(v[2], v[3]);
-        }
-        __syncwarp();
-        bf16* dst = a + ((n * O + oy) * O + ox0) * kC0;
+        };
+        float up[4], lo[4], lo_next[4];
+        load_rows(2 * oy_lo - 1 + ky0, up);      // first tile: rows 2 oy - 1 + ky0 and 2 oy + 1 + ky0
+        load_rows(2 * oy_lo + 1 + ky0, lo);
+        bf16* dst = a + ((n * O + oy_lo) * O + ox0) * kC0;
+        (void)lgO;
+        for (int oy = oy_lo; oy < oy_lo + kSeg; ++oy, dst += static_cast<long>(O) * kC0) {
+            if (oy + 1 < oy_lo + kSeg) load_rows(2 * oy + 3 + ky0, lo_next);
+            uint32_t af[4];
+            af[0] = pack2_bf16(up[0], up[1]);
+            af[1] = pack2_bf16(up[2], up[3]);
+            af[2] = pack2_bf16(lo[0], lo[1]);
+            af[3] = pack2_bf16(lo[2], lo[3]);
+            float acc[8][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int row = j * 4 + (lane >> 3), chunk = lane & 7;
-            const uint4 d = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
-            *reinterpret_cast<uint4*>(dst + row * kC0 + chunk * 8) = d;
+            for (int nb = 0; nb < 8; ++nb) {
+                acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+                mma_bf16(acc[nb], af, bw[nb][0], bw[nb][1]);
+            }
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const float m0 = mk[nb].x, m1 = mk[nb].y;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float t = acc[nb][e] + bs[nb][e & 1];
+                    v[e] = (t > 0.f ? t : t * slope) * ((e & 1) ? m1 : m0);
+                }
+                const uint32_t off = static_cast<uint32_t>((nb ^ gid) << 4) + t4 * 4;   // (gid + 8) & 7 == gid
+                *reinterpret_cast<uint32_t*>(stage + gid * 128 + off) = pack2_bf16(v[0], v[1]);
+                *reinterpret_cast<uint32_t*>(stage + (gid + 8) * 128 + off) = pack2_bf16(v[2], v[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = j * 4 + (lane >> 3), chunk = lane & 7;
+                const uint4 d = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+                *reinterpret_cast<uint4*>(dst + row * kC0 + chunk * 8) = d;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                up[k] = lo[k];
+                lo[k] = lo_next[k];
+            }
         }
-        __syncwarp();
     }
 }
 
@@ -222,7 +229,7 @@ dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy
 
 constexpr int kTPitch = 17;  // floats per pixel of the tap-sum tile (16 taps + 1: conflict-free col2im reads)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S) {
     extern __shared__ float T[];  // [(RB + 2)][O][kTPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, t4 = lane & 3;
@@ -244,34 +251,52 @@ dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w
         const int r0 = (u - static_cast<int>(n) * bands) * RB;
         // ---- phase 1: T rows r0-1 .. r0+RB
         const int ntile = (RB + 2) * tpr;
-        for (int tl = warp; tl < ntile; tl += 8) {
-            const int rr = tl / tpr, ox0 = (tl - rr * tpr) * 16;
-            const int oy = r0 - 1 + rr;
-            float acc[2][4];
+        // two tiles per iteration: the 8 independent 16-byte loads of both are in flight before the first MMA
+        for (int tl = warp; tl < ntile; tl += 16) {
+            uint4 A[2][4];
+            int rrs[2], oxs[2];
+            bool live[2];
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-            if (oy >= 0 && oy < O) {
-                const bf16* dp = dy + ((n * O + oy) * O + ox0 + gid) * kC0 + t4 * 8;
-                const uint4 A0 = __ldg(reinterpret_cast<const uint4*>(dp));
-                const uint4 A1 = __ldg(reinterpret_cast<const uint4*>(dp + 32));
-                const uint4 A2 = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0));
-                const uint4 A3 = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0 + 32));
-                const uint32_t lo0[4] = {A0.x, A0.y, A0.z, A0.w}, hi0[4] = {A1.x, A1.y, A1.z, A1.w};
-                const uint32_t lo8[4] = {A2.x, A2.y, A2.z, A2.w}, hi8[4] = {A3.x, A3.y, A3.z, A3.w};
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const uint32_t af[4] = {lo0[s], lo8[s], hi0[s], hi8[s]};
-                    mma_bf16(acc[0], af, bw[s][0][0], bw[s][0][1]);
-                    mma_bf16(acc[1], af, bw[s][1][0], bw[s][1][1]);
+            for (int h = 0; h < 2; ++h) {
+                const int t = tl + 8 * h;
+                rrs[h] = t / tpr;
+                oxs[h] = (t - rrs[h] * tpr) * 16;
+                const int oy = r0 - 1 + rrs[h];
+                live[h] = t < ntile && oy >= 0 && oy < O;
+                if (live[h]) {
+                    const bf16* dp = dy + ((n * O + oy) * O + oxs[h] + gid) * kC0 + t4 * 8;
+                    A[h][0] = __ldg(reinterpret_cast<const uint4*>(dp));
+                    A[h][1] = __ldg(reinterpret_cast<const uint4*>(dp + 32));
+                    A[h][2] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0));
+                    A[h][3] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0 + 32));
                 }
             }
-            float* t0 = T + (rr * O + ox0 + gid) * kTPitch + 2 * t4;
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) {
-                t0[nb * 8] = acc[nb][0];
-                t0[nb * 8 + 1] = acc[nb][1];
-                t0[8 * kTPitch + nb * 8] = acc[nb][2];
-                t0[8 * kTPitch + nb * 8 + 1] = acc[nb][3];
+            for (int h = 0; h < 2; ++h) {
+                if (tl + 8 * h >= ntile) break;
+                float acc[2][4];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+                if (live[h]) {
+                    const uint32_t lo0[4] = {A[h][0].x, A[h][0].y, A[h][0].z, A[h][0].w};
+                    const uint32_t hi0[4] = {A[h][1].x, A[h][1].y, A[h][1].z, A[h][1].w};
+                    const uint32_t lo8[4] = {A[h][2].x, A[h][2].y, A[h][2].z, A[h][2].w};
+                    const uint32_t hi8[4] = {A[h][3].x, A[h][3].y, A[h][3].z, A[h][3].w};
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const uint32_t af[4] = {lo0[s], lo8[s], hi0[s], hi8[s]};
+                        mma_bf16(acc[0], af, bw[s][0][0], bw[s][0][1]);
+                        mma_bf16(acc[1], af, bw[s][1][0], bw[s][1][1]);
+                    }
+                }
+                float* t0 = T + (rrs[h] * O + oxs[h] + gid) * kTPitch + 2 * t4;
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    t0[nb * 8] = acc[nb][0];
+                    t0[nb * 8 + 1] = acc[nb][1];
+                    t0[8 * kTPitch + nb * 8] = acc[nb][2];
+                    t0[8 * kTPitch + nb * 8 + 1] = acc[nb][3];
+                }
             }
         }
         __syncthreads();
@@ -302,9 +327,13 @@ dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w
 
 void dconv0_fwd_mma(const float* x, const float* w, const float* bias, const float* mask, float slope, bf16* a, int B,
                     int S, cudaStream_t s) {
-    const long tiles = static_cast<long>(B) * (S / 2) * (S / 32);
+    const long units = static_cast<long>(B) * (S / 2 / 8) * (S / 32);  // (image, 8-row segment, 16-column strip) per warp
+    static int per_sm = 0;
+    if (per_sm == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dconv0_fwd_mma_kernel, 256, 0) != cudaSuccess || per_sm < 1))
+        per_sm = 2;
     note_launch();
-    dconv0_fwd_mma_kernel<<<blocks_for(tiles, 8, 148 * 8), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
+    dconv0_fwd_mma_kernel<<<blocks_for(units, 8, 148 * per_sm), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
 }
 int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s) {
     const long tiles = static_cast<long>(B) * (S / 2) * (S / 32);
@@ -320,8 +349,13 @@ void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, c
     static bool ok = cudaFuncSetAttribute(dconv0_dgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) ==
                      cudaSuccess;
     (void)ok;
+    static int per_sm[2] = {0, 0};  // by image size: the band buffer of a 128 x 128 image is a little larger
+    int& ps = per_sm[S == 64 ? 0 : 1];
+    if (ps == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, dconv0_dgrad_mma_kernel, 256, smem) != cudaSuccess || ps < 1))
+        ps = 2;
     note_launch();
-    dconv0_dgrad_mma_kernel<<<units < 148 * 2 ? units : 148 * 2, 256, smem, s>>>(dy, w, dx, B, S);
+    dconv0_dgrad_mma_kernel<<<units < 148 * ps ? units : 148 * ps, 256, smem, s>>>(dy, w, dx, B, S);
 }
 
 }  // namespace sg

@@ -400,6 +400,16 @@ static bool fused_tail_enabled() {
     return on != 0;
 }
 
+// SIGGAN_FUSED_BN_REDUCE=0: BatchNorm-backward reductions as separate passes (A/B comparison)
+static bool fused_bn_reduce_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SIGGAN_FUSED_BN_REDUCE");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 template <typename T>
 int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, int B, int train, void* ws_ptr,
                 float* out_image, uint8_t* out_u8, bool save, cudaStream_t s) {
@@ -597,6 +607,10 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
                                         grads + c->gt[c->g_final_w].offset, grads + c->gt[c->g_final_b].offset, cpart,
                                         part_bn, B, c->S, c->gch[L], gs, s);
     }
+    // BatchNorm-backward reductions of the level about to be processed that the data-gradient kernel of the level above
+    // already produced in its epilogue (raw form: sum d, sum d*y per CTA); 0 = none, run the reduction pass
+    int fused_chunks = 0;
+    float* part_fused = cpart;
     for (int i = ((only_level < 0 && single) || stage == 2) ? -1 : lvl_hi; i >= lvl_lo; --i) {
         const int oh = g_spatial(c, i), ih = oh / 2, Cin = c->gch[i], Cout = c->gch[i + 1];
         const long rows = static_cast<long>(B) * oh * oh;
@@ -610,6 +624,12 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
             if (train)
                 SG_TRY(sync_bn_bwd_coefficients(c, part_bn, last_chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1],
                                                 w.mean[i + 1], 0, s));
+        } else if (fused_chunks > 0) {
+            sg::bn_bwd_finalize(part_fused, fused_chunks, rows, Cout, params + bn.gamma_off, w.rstd[i + 1], w.mean[i + 1],
+                                train, 0, grads + bn.gamma_off, grads + bn.beta_off, c->k1, c->k2, c->k3, s);
+            if (train)
+                SG_TRY(sync_bn_bwd_coefficients(c, part_fused, fused_chunks, rows, Cout, params + bn.gamma_off,
+                                                w.rstd[i + 1], w.mean[i + 1], 0, s));
         } else {
             PROF((nm + ".bn_bwd_reduce").c_str(), 0, 2.0 * es * (double)rows * Cout);
             const int chunks = sg::col_reduce<T>(1, reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]),
@@ -642,6 +662,17 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
             sg::ConvGemmArgs e = epi_args(nxt, Cin);
             e.gate = reinterpret_cast<const bf16*>(xin);  // ReLU' (slope 0) / LeakyReLU' of the previous block
             e.slope = gs;
+            // BatchNorm gate: the block below is an upsample block whose forward applied act(y * scale + shift) to its
+            // saved pre-BatchNorm output y: gate on that expression and let the epilogue produce that block's
+            // BatchNorm-backward reductions (sum d, sum d*y), so that no separate pass over d and y is needed
+            fused_chunks = (i >= 1 && fused_bn_reduce_enabled()) ? sg::conv_gemm_gate_stats_chunks(B, oh, oh, Cout, Cin) : 0;
+            if (fused_chunks > sg::kMaxChunks) fused_chunks = 0;
+            if (fused_chunks > 0) {
+                e.gate = reinterpret_cast<const bf16*>(w.y[i - 1]);
+                e.gate_scale = w.scale[i];
+                e.gate_shift = w.shift[i];
+                e.stats_partial = part_fused;
+            }
             SG_UMMA(sg::launch_conv_gemm(sg::kConvS2, reinterpret_cast<const bf16*>(cur), c->g_packB[i], B, oh, oh, Cout,
                                          Cin, e, s));
         } else {

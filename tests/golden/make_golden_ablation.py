@@ -41,7 +41,7 @@ def main():
     import ablation_vanilla_gan_signatures as A      # the reference script, unmodified
     from discriminator_vanilla_gan import Discriminator
     assert os.path.realpath(A.__file__).startswith(os.path.realpath(REF_SRC))
-    for size, B in ((64, 8), (128, 4)):
+    for size, B in ((64, 8), (128, 8)):
         g_sd, d_sd = O.make_state_dicts(size, 100, seed=11)
         G = A.ConfigurableGenerator(latent_dim=100, output_size=size, activation="leaky_relu")
         D = Discriminator(input_size=size, dropout=0.0)

@@ -67,7 +67,9 @@ def test_leaky_generator_against_reference_fixture(golden_dir, precision, size):
         dg = O.d_backward(sd_d, dc, O.bce_grad(pr, torch.full_like(pr, 0.9)), size, None, need_dx=True)
         ref[name] = O.g_backward(sd_g, gc, dg["__dx"], size, train=True, act_slope=0.2)
     got = {k: p.grad for k, p in G.named_parameters()}
-    check_grads(precision, "G", got, ref["f32"], ref["f64"])
+    # final_conv.0.bias: ONE sum of cancelling terms (at 128x128 / B = 4 its bf16 value is 50 % off and still 1e-4 of the
+    # gradient vector's norm): bounded through the whole-vector norm only
+    check_grads(precision, "G", got, ref["f32"], ref["f64"], skip=("fc.0.bias", "final_conv.0.bias"))
     for k, g in got.items():
         pr = gold["grads"][k]
         if k == "fc.0.bias" or pr["numel"] < 64:      # mathematically zero / single sums of cancelling terms

@@ -137,20 +137,23 @@ def test_generator_layers_backward(precision, size, B):
     img32, c32, _ = O.g_forward(g_sd, z, size, train=True)
     nl = len(O.g_channels(size)) - 1
     if precision == "bf16":
-        # The top unit reads the last block's raw conv output y in its STORAGE type and recomputes BatchNorm + ReLU from it
-        # (the 64x64x32 activation is never stored). Both sides of an isolated-unit comparison must see the same input, so
-        # the oracle's backward runs on that bf16-stored y as well: with the unrounded y the oracle's OWN gradients move by
-        # 1.9e-2 (block weight) / 2.4e-2 (BatchNorm bias) at 64x64, because 0.02 % of the ReLU sides flip — an input
+        # Every unit reads an upsample block's raw conv output y in its STORAGE type and derives the activation side from
+        # it: the top unit recomputes BatchNorm + ReLU of the last block from y (the 64x64x32 activation is never
+        # stored), and every data-gradient kernel gates on y * scale + shift of the block below (whose BatchNorm-backward
+        # reductions it also produces). Both sides of an isolated-unit comparison must see the same input, so the oracle's
+        # backward runs on the bf16-stored y as well: with the unrounded y the oracle's OWN gradients move by 1.9e-2
+        # (block weight) / 2.4e-2 (BatchNorm bias) at 64x64, because 0.02 % of the ReLU sides flip — an input
         # sensitivity of the layer, not an arithmetic error of either implementation (the chained tests of
         # test_gpu_parity.py cover the forward chain that produces y).
-        t = nl - 1
-        pre = f"upsample_blocks.{t}.block.1"
-        y = c32[f"up{t}.y"]
-        mean = y.mean(dim=[0, 2, 3], keepdim=True)
-        xhat = (y.bfloat16().float() - mean) * c32[f"up{t}.rstd"].view(1, -1, 1, 1)
-        act = torch.relu(g_sd[pre + ".weight"].view(1, -1, 1, 1) * xhat + g_sd[pre + ".bias"].view(1, -1, 1, 1))
         c32 = dict(c32)
-        c32[f"up{t}.xhat"], c32[f"up{t}.a"], c32["final.in"] = xhat, act, act
+        for t in range(nl):
+            pre = f"upsample_blocks.{t}.block.1"
+            y = c32[f"up{t}.y"]
+            mean = y.mean(dim=[0, 2, 3], keepdim=True)
+            xhat = (y.bfloat16().float() - mean) * c32[f"up{t}.rstd"].view(1, -1, 1, 1)
+            act = torch.relu(g_sd[pre + ".weight"].view(1, -1, 1, 1) * xhat + g_sd[pre + ".bias"].view(1, -1, 1, 1))
+            c32[f"up{t}.xhat"], c32[f"up{t}.a"] = xhat, act
+            c32[f"up{t + 1}.in" if t + 1 < nl else "final.in"] = act
     taps32 = {}
     g32 = O.g_backward(g_sd, c32, dout, size, train=True, taps=taps32)
     sd64 = to64(g_sd)
