@@ -352,6 +352,30 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
     scale[j] = sc;
     shift[j] = beta[p] - mu * sc;
 }
+// Eval mode: the coefficients of ALL BatchNorm layers of the Generator from their running statistics in one launch
+// (one thread per channel; the per-layer launches were 5-6 tiny kernels in front of every eval forward).
+__global__ void bn_eval_all_kernel(const BnEvalPlan plan, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= plan.total) return;
+    int l = 0;
+    while (l + 1 < plan.n && i >= plan.layer[l + 1].first) ++l;
+    const BnEvalLayer& L = plan.layer[l];
+    const int j = i - L.first;
+    const int p = perm_index(j, L.perm_c0);
+    const float mu = L.running_mean[p];
+    const float r = 1.0f / sqrtf(L.running_var[p] + eps);
+    L.mean[j] = mu;
+    L.rstd[j] = r;
+    const float sc = L.gamma[p] * r;
+    L.scale[j] = sc;
+    L.shift[j] = L.beta[p] - mu * sc;
+}
+void bn_eval_all(const BnEvalPlan& plan, float eps, cudaStream_t s) {
+    if (plan.total <= 0) return;
+    note_launch();
+    bn_eval_all_kernel<<<(plan.total + 255) / 256, 256, 0, s>>>(plan, eps);
+}
+
 void bn_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
                  float* mean, float* rstd, float* scale, float* shift, cudaStream_t s) {
@@ -1044,18 +1068,31 @@ void g_loss_metrics(const float* prob, int B, float* metrics, float* dlogit, cud
 // ------------------------------------------------------------------------------------------------
 // Adam over a flat buffer (torch.optim.Adam single-tensor formulas, vanilla…:110-120)
 // ------------------------------------------------------------------------------------------------
+// One Adam update (torch.optim.Adam, wd = 0, amsgrad = False; vanilla…:110-120); returns the new parameter value.
+struct AdamCoef {
+    float b1, b2, eps, grad_scale, step_size, inv_bc2_sqrt;
+};
+__device__ __forceinline__ float adam_update(float pi, float graw, float& mref, float& vref, const AdamCoef& k) {
+    // every rounding spelled out (no compiler-chosen FMA contraction): the three Adam kernels of this file must agree bit
+    // for bit, whichever of them updates a parameter
+    const float gi = __fmul_rn(graw, k.grad_scale);
+    const float mi = __fmaf_rn(__fsub_rn(gi, mref), 1.f - k.b1, mref);                       // lerp form used by torch
+    const float vi = __fmaf_rn(__fmul_rn(1.f - k.b2, gi), gi, __fmul_rn(vref, k.b2));
+    mref = mi;
+    vref = vi;
+    const float denom = __fmaf_rn(sqrtf(vi), k.inv_bc2_sqrt, k.eps);
+    return __fsub_rn(pi, __fmul_rn(k.step_size, __fdiv_rn(mi, denom)));
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long n, float b1, float b2, float eps, float step_size,
                             float inv_bc2_sqrt) {
+    const AdamCoef k{b1, b2, eps, 1.f, step_size, inv_bc2_sqrt};
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const float gi = g[i];
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp form used by torch
-        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        float mi = m[i], vi = v[i];
+        p[i] = adam_update(p[i], g[i], mi, vi, k);
         m[i] = mi;
         v[i] = vi;
-        const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-        p[i] -= step_size * (mi / denom);
     }
 }
 void adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, long step,
@@ -1100,17 +1137,166 @@ void step_set(StepCounters* c, int field, long long value, cudaStream_t s) {
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, long n, float b1, float b2, float eps,
                                 const float* __restrict__ scal, float grad_scale) {
-    const float step_size = scal[0], inv_bc2_sqrt = scal[1];
+    const AdamCoef k{b1, b2, eps, grad_scale, scal[0], scal[1]};
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const float gi = g[i] * grad_scale;
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        float mi = m[i], vi = v[i];
+        p[i] = adam_update(p[i], g[i], mi, vi, k);
         m[i] = mi;
         v[i] = vi;
-        const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-        p[i] -= step_size * (mi / denom);
     }
+}
+
+// ---- Adam + weight packs in one launch -------------------------------------------------------------
+constexpr int kMaxPlain = 16;
+struct AdamPackArgs {
+    PackPlan plan;
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    float b1, b2, eps, grad_scale;
+    const float* scal;
+    int nplain, plain_block0;          // blocks [plain_block0, gridDim.x) update the ranges no pack segment covers
+    long plain_off[kMaxPlain];
+    long plain_cum[kMaxPlain + 1];     // prefix sums of the range lengths
+};
+__global__ void __launch_bounds__(256) adam_pack_kernel(const __grid_constant__ AdamPackArgs a) {
+    constexpr int kRow = 32 * 16 + 2;
+    __shared__ bf16 tile[16 * kRow];
+    const AdamCoef k{a.b1, a.b2, a.eps, a.grad_scale, a.scal[0], a.scal[1]};
+    const int tid = threadIdx.x;
+    auto upd = [&](long i) {  // in place; returns the new value
+        float mi = a.m[i], vi = a.v[i];
+        const float pn = adam_update(a.p[i], a.g[i], mi, vi, k);
+        a.p[i] = pn;
+        a.m[i] = mi;
+        a.v[i] = vi;
+        return pn;
+    };
+    if (static_cast<int>(blockIdx.x) >= a.plain_block0) {
+        const long total = a.plain_cum[a.nplain];
+        const long i0 = (static_cast<long>(blockIdx.x) - a.plain_block0) * 4096;
+        int r = 0;
+        for (long i = i0 + tid; i < total && i < i0 + 4096; i += 256) {
+            while (i >= a.plain_cum[r + 1]) ++r;
+            upd(a.plain_off[r] + (i - a.plain_cum[r]));
+        }
+        return;
+    }
+    int sidx = 0;
+    while (sidx + 1 < a.plan.nseg && static_cast<int>(blockIdx.x) >= a.plan.seg[sidx + 1].tile0) ++sidx;
+    const PackSeg& sg_ = a.plan.seg[sidx];
+    const int t_local = blockIdx.x - sg_.tile0;
+    const long base = sg_.src - a.p;  // element offset of the segment's source tensor in the flat buffers
+    if (sg_.kind == 0) {
+        const int A = sg_.A, B = sg_.B;
+        const int bt = B / 32;
+        const int a0 = (t_local / bt) * 16, b0 = (t_local % bt) * 32;
+        for (int e = tid; e < 16 * 128; e += 256) {
+            const int ar = e >> 7, r4 = (e & 127) * 4;
+            const long o = base + (static_cast<long>(a0 + ar) * B + b0) * 16 + r4;
+            const float4 pv = *reinterpret_cast<const float4*>(a.p + o);
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(a.g + o));
+            float4 mv = *reinterpret_cast<const float4*>(a.m + o);
+            float4 vv = *reinterpret_cast<const float4*>(a.v + o);
+            float4 pn;
+            pn.x = adam_update(pv.x, gv.x, mv.x, vv.x, k);
+            pn.y = adam_update(pv.y, gv.y, mv.y, vv.y, k);
+            pn.z = adam_update(pv.z, gv.z, mv.z, vv.z, k);
+            pn.w = adam_update(pv.w, gv.w, mv.w, vv.w, k);
+            *reinterpret_cast<float4*>(a.p + o) = pn;
+            *reinterpret_cast<float4*>(a.m + o) = mv;
+            *reinterpret_cast<float4*>(a.v + o) = vv;
+            __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&tile[ar * kRow + r4]);
+            d[0] = __floats2bfloat162_rn(pn.x, pn.y);
+            d[1] = __floats2bfloat162_rn(pn.z, pn.w);
+        }
+        __syncthreads();
+        if (sg_.ab) {
+            for (int e = tid; e < 16 * 16 * 16; e += 256) {
+                const int b2 = (e & 15) * 2, t = (e >> 4) & 15, ar = e >> 8;
+                __nv_bfloat162 w;
+                w.x = tile[ar * kRow + b2 * 16 + t];
+                w.y = tile[ar * kRow + (b2 + 1) * 16 + t];
+                *reinterpret_cast<__nv_bfloat162*>(&sg_.ab[(static_cast<long>(a0 + ar) * 16 + t) * B + b0 + b2]) = w;
+            }
+        }
+        if (sg_.ba) {
+            for (int e = tid; e < 32 * 16 * 8; e += 256) {
+                const int a2 = (e & 7) * 2, t = (e >> 3) & 15, b = e >> 7;
+                __nv_bfloat162 w;
+                w.x = tile[a2 * kRow + b * 16 + t];
+                w.y = tile[(a2 + 1) * kRow + b * 16 + t];
+                *reinterpret_cast<__nv_bfloat162*>(&sg_.ba[(static_cast<long>(b0 + b) * 16 + t) * A + a0 + a2]) = w;
+            }
+        }
+    } else if (sg_.kind == 1) {  // generator fc: every (feature, latent) pair and every bias appears once in packed order
+        const int C0 = sg_.A, latent = sg_.B, Kp = sg_.Kp;
+        const long total = static_cast<long>(C0) * 16 * Kp;
+        const long bbase = sg_.src2 - a.p;
+        for (long i = static_cast<long>(t_local) * 4096 + tid; i < total && i < static_cast<long>(t_local + 1) * 4096; i += 256) {
+            const int kk = static_cast<int>(i % Kp);
+            const int j = static_cast<int>(i / Kp);
+            const int f = (j % C0) * 16 + j / C0;
+            sg_.ab[i] = __float2bfloat16(kk < latent ? upd(base + static_cast<long>(f) * latent + kk) : 0.f);
+            if (kk == 0) sg_.fdst[j] = upd(bbase + f);
+        }
+    } else {  // classifier weight: NCHW -> NHWC order, fp32
+        const int C = sg_.A, F = C * 16;
+        for (int j = t_local * 4096 + tid; j < F && j < (t_local + 1) * 4096; j += 256)
+            sg_.fdst[j] = upd(base + (j % C) * 16 + j / C);
+    }
+}
+int adam_pack_step_dev(const PackPlan& plan, float* p, const float* g, float* m, float* v, long n, float b1, float b2,
+                       float eps, const float* scal, float grad_scale, cudaStream_t s) {
+    AdamPackArgs a;
+    a.plan = plan;
+    a.p = p; a.g = g; a.m = m; a.v = v;
+    a.b1 = b1; a.b2 = b2; a.eps = eps; a.grad_scale = grad_scale; a.scal = scal;
+    // covered intervals of the flat buffer, sorted; the complement becomes the plain ranges
+    long lo[2 * 8], hi[2 * 8];
+    int nc = 0;
+    for (int i = 0; i < plan.nseg; ++i) {
+        const PackSeg& sg_ = plan.seg[i];
+        const long off = sg_.src - p;
+        long len = 0;
+        if (sg_.kind == 0) len = static_cast<long>(sg_.A) * sg_.B * 16;
+        else if (sg_.kind == 1) len = static_cast<long>(sg_.A) * 16 * sg_.B;
+        else len = static_cast<long>(sg_.A) * 16;
+        if (off < 0 || off + len > n || (off & 3)) return -1;
+        lo[nc] = off; hi[nc] = off + len; ++nc;
+        if (sg_.kind == 1) {
+            const long boff = sg_.src2 - p;
+            if (boff < 0 || boff + sg_.A * 16 > n) return -1;
+            lo[nc] = boff; hi[nc] = boff + sg_.A * 16; ++nc;
+        }
+    }
+    for (int i = 1; i < nc; ++i)
+        for (int j = i; j > 0 && lo[j] < lo[j - 1]; --j) {
+            const long tl = lo[j], th = hi[j];
+            lo[j] = lo[j - 1]; hi[j] = hi[j - 1];
+            lo[j - 1] = tl; hi[j - 1] = th;
+        }
+    a.nplain = 0;
+    a.plain_cum[0] = 0;
+    long cur = 0;
+    for (int i = 0; i <= nc; ++i) {
+        const long end = i < nc ? lo[i] : n;
+        if (end < cur) return -1;  // overlapping segments
+        if (end > cur) {
+            if (a.nplain >= kMaxPlain) return -1;
+            a.plain_off[a.nplain] = cur;
+            a.plain_cum[a.nplain + 1] = a.plain_cum[a.nplain] + (end - cur);
+            ++a.nplain;
+        }
+        if (i < nc) cur = hi[i];
+    }
+    a.plain_block0 = plan.total_tiles;
+    const int plain_blocks = static_cast<int>((a.plain_cum[a.nplain] + 4095) / 4096);
+    note_launch();
+    adam_pack_kernel<<<plan.total_tiles + plain_blocks, 256, 0, s>>>(a);
+    return 0;
 }
 void adam_step_dev(float* p, const float* g, float* m, float* v, long n, float b1, float b2, float eps, const float* scal,
                    float grad_scale, cudaStream_t s) {

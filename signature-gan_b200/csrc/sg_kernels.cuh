@@ -73,6 +73,17 @@ int col_reduce(int mode, const T* a, const T* y, const float* mean, const float*
 void bn_finalize(const float* partial, int chunks, long rows, int C, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int perm_c0,
                  float* mean, float* rstd, float* scale, float* shift, cudaStream_t s);
+// Eval-mode coefficients (mean, rstd, scale, shift from the running statistics) of up to 8 BatchNorm layers in one launch.
+struct BnEvalLayer {
+    const float *gamma, *beta, *running_mean, *running_var;
+    float *mean, *rstd, *scale, *shift;
+    int first, perm_c0;  // first global channel index of the layer; perm_c0 as in bn_finalize
+};
+struct BnEvalPlan {
+    BnEvalLayer layer[8];
+    int n = 0, total = 0;
+};
+void bn_eval_all(const BnEvalPlan& plan, float eps, cudaStream_t s);
 template <typename T>
 void bn_apply_relu(const T* y, const float* scale, const float* shift, T* a, long rows, int C, float act_slope,
                    cudaStream_t s);  // act_slope 0 = ReLU, else LeakyReLU(act_slope)
@@ -159,6 +170,13 @@ void step_prep(StepCounters* c, int which /* 0 = G, 1 = D */, float lr, float b1
 void step_set(StepCounters* c, int field /* 0 g_step, 1 d_step, 2 dropout_offset */, long long value, cudaStream_t s);
 void adam_step_dev(float* p, const float* g, float* m, float* v, long n, float b1, float b2, float eps, const float* scal,
                    float grad_scale, cudaStream_t s);
+// Adam over the whole flat buffer AND the network's bf16 / permuted weight packs in ONE launch (the
+// optimizer emits the packed copies): `plan` lists the pack segments whose sources lie inside [p, p + n); the blocks of
+// a segment update their parameters and write the packs from the updated values, the rest of the buffer is updated by
+// plain element-wise blocks. Same arithmetic, element by element, as adam_step_dev followed by pack_plan_launch.
+// Returns 0, or -1 when the plan does not tile the buffer (caller falls back to the two launches).
+int adam_pack_step_dev(const PackPlan& plan, float* p, const float* g, float* m, float* v, long n, float b1, float b2,
+                       float eps, const float* scal, float grad_scale, cudaStream_t s);
 void dropout_masks_dev(uint64_t seed, const unsigned long long* offset_ptr, long n, float p, float* out, cudaStream_t s);
 
 // ---- direct convolutions (validation mode / fallback). Weights are the fp32 master tensors in PyTorch

@@ -190,6 +190,10 @@ struct sg_ctx {
     DevBuf bufA, bufB, dpre, wpart, cpart, small, g_ws, d_ws, x2, masks2, dximg, gws_tmp;
     const float* d_pack_src = nullptr;  // parameter buffer the Discriminator packs were last built from
     const float* g_pack_src = nullptr;  // same for the Generator (several modules may share one context)
+    // Inside ONE sg_train_step(phase 0) call nobody but the library writes the parameters, so the G-step phase can reuse
+    // the Generator packs of the D-step phase (G is only updated at the very end) and the Discriminator packs its fused
+    // Adam + pack kernel just wrote: set by the phase-0 sequence around phase 3 / 31, false everywhere else
+    bool skip_g_pack = false, skip_d_pack = false;
     int device = 0;                     // CUDA device ordinal this context was created on
     // SyncBN (sg_set_sync_batchnorm): per-channel BatchNorm sums are all-reduced over the ranks through the caller's callback
     sg_allreduce_fn sync_fn = nullptr;
@@ -349,6 +353,7 @@ int sync_bn_bwd_coefficients(sg_ctx* c, const float* partial, int chunks, long r
 // weight packs
 // ------------------------------------------------------------------------------------------------
 int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
+    if (c->skip_g_pack && c->g_pack_src == params) return 0;
     c->g_pack_src = params;
     if (c->cfg.precision != SG_PREC_BF16) return 0;
     PROF("g.pack", 0, 10.0 * c->g_count);
@@ -363,17 +368,21 @@ int pack_generator(sg_ctx* c, const float* params, cudaStream_t s) {
     SG_KCHECK("pack_generator");
     return 0;
 }
-int pack_discriminator(sg_ctx* c, const float* params, cudaStream_t s) {
-    PROF("d.pack", 0, 10.0 * c->d_count);
-    c->d_pack_src = params;
-    sg::PackPlan plan;
+int discriminator_pack_plan(sg_ctx* c, const float* params, sg::PackPlan& plan) {
     int rc = sg::pack_plan_add_classifier(plan, params + c->dt[c->d_cls_w].offset, c->cls_wp, c->dch[c->ND]);
     if (c->cfg.precision == SG_PREC_BF16) {
         for (int i = 1; i < c->ND; ++i)  // W (Cout, Cin, 4, 4): forward pack [Cout][16][Cin] = AB, dgrad pack = BA
             rc |= sg::pack_plan_add_w16(plan, params + c->dt[c->d_conv_w[i]].offset, c->d_packF[i], c->d_packB[i],
                                         c->dch[i + 1], c->dch[i]);
     }
-    if (rc) return fail("pack_discriminator: pack plan overflow");
+    return rc;
+}
+int pack_discriminator(sg_ctx* c, const float* params, cudaStream_t s) {
+    if (c->skip_d_pack && c->d_pack_src == params) return 0;
+    PROF("d.pack", 0, 10.0 * c->d_count);
+    c->d_pack_src = params;
+    sg::PackPlan plan;
+    if (discriminator_pack_plan(c, params, plan)) return fail("pack_discriminator: pack plan overflow");
     sg::pack_plan_launch(plan, s);
     SG_KCHECK("pack_discriminator");
     return 0;
@@ -428,10 +437,22 @@ int g_forward_t(sg_ctx* c, const float* params, float* stats, const float* z, in
     }
     if (!train) {
         PROF("g.bn_eval", 0, 0);
-        for (int i = 0; i <= c->L; ++i)
-            sg::bn_finalize(nullptr, 0, 1, c->bn[i].C, params + c->bn[i].gamma_off, params + c->bn[i].beta_off,
-                            stats + c->bn[i].mean_off, stats + c->bn[i].var_off, c->cfg.bn_momentum, c->cfg.bn_eps, 0,
-                            i == 0 ? c->gch[0] : 0, w.mean[i], w.rstd[i], w.scale[i], w.shift[i], s);
+        sg::BnEvalPlan plan;
+        for (int i = 0; i <= c->L; ++i) {
+            sg::BnEvalLayer& l = plan.layer[plan.n++];
+            l.gamma = params + c->bn[i].gamma_off;
+            l.beta = params + c->bn[i].beta_off;
+            l.running_mean = stats + c->bn[i].mean_off;
+            l.running_var = stats + c->bn[i].var_off;
+            l.mean = w.mean[i];
+            l.rstd = w.rstd[i];
+            l.scale = w.scale[i];
+            l.shift = w.shift[i];
+            l.first = plan.total;
+            l.perm_c0 = i == 0 ? c->gch[0] : 0;
+            plan.total += c->bn[i].C;
+        }
+        sg::bn_eval_all(plan, c->cfg.bn_eps, s);
     }
     // ---- fc + BN1d + ReLU (gen…:124-128), output already NHWC (B,4,4,C0)
     {
@@ -985,12 +1006,23 @@ static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d
         SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s,
                           phase == 11 ? 1 : 0));
     }
-    if (phase == 2) {
+    if (phase == 2 || phase == 22) {
         PROF("adam.d", 0, 28.0 * c->d_count);
         sg::step_prep(c->counters, 1, st->d_lr, st->beta1, st->beta2,
                       dropout ? (unsigned long long)sg_d_mask_count(c, 2 * B) : 0ull, s);
-        sg::adam_step_dev(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->beta1, st->beta2, st->eps,
-                          c->counters->adam_d, gscale, s);
+        bool done = false;
+        if (phase == 22) {  // the optimizer emits the packed copies the G step's D forward / backward will read (K10)
+            sg::PackPlan plan;
+            done = discriminator_pack_plan(c, st->d_params, plan) == 0 &&
+                   sg::adam_pack_step_dev(plan, st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->beta1,
+                                          st->beta2, st->eps, c->counters->adam_d, gscale, s) == 0;
+            if (done) c->d_pack_src = st->d_params;
+        }
+        if (!done) {
+            if (phase == 22) return fail("sg_train_step: the Discriminator's pack plan does not tile its parameter buffer");
+            sg::adam_step_dev(st->d_params, d_grads, st->d_exp_avg, st->d_exp_avg_sq, c->d_count, st->beta1, st->beta2,
+                              st->eps, c->counters->adam_d, gscale, s);
+        }
     }
     if (phase == 32) {
         SG_TRY(DISPATCH_T(c, g_backward_t, c, st->g_params, c->g_ws.p, static_cast<const float*>(c->dximg.p), B, 1, g_grads,
@@ -1050,7 +1082,7 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
         }
     } else if (phase == 12) {
         if (!d_grads) return fail("sg_train_step: D phase needs d_grads");
-    } else if (phase == 2) {
+    } else if (phase == 2 || phase == 22) {
         if (!d_grads) return fail("sg_train_step: D update needs d_grads");
         if (c->mirror_d_step != st->d_step) sg::step_set(c->counters, 1, st->d_step, s);
         c->mirror_d_step = st->d_step + 1;
@@ -1075,7 +1107,7 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
     memset(&key, 0, sizeof(key));
     key.phase = phase;
     key.B = B;
-    key.flags = (masks_injected ? 1 : 0) | (dropout ? 2 : 0);
+    key.flags = (masks_injected ? 1 : 0) | (dropout ? 2 : 0) | (c->skip_g_pack ? 4 : 0) | (c->skip_d_pack ? 8 : 0);
     const void* ptrs[10] = {st->g_params, st->g_running_stats, st->g_exp_avg, st->g_exp_avg_sq, st->d_params,
                             st->d_exp_avg, st->d_exp_avg_sq, d_grads, g_grads, metrics};
     memcpy(key.ptr, ptrs, sizeof(ptrs));
@@ -1145,6 +1177,13 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
     sg::g_launches += static_cast<unsigned long long>(ent->n_launches);
     return 0;
 }
+
+// Scope of the G-step phase inside one phase-0 call: the packs written earlier in the same call are current.
+struct StepPackReuse {
+    sg_ctx* c;
+    explicit StepPackReuse(sg_ctx* ctx) : c(ctx) { c->skip_g_pack = c->skip_d_pack = true; }
+    ~StepPackReuse() { c->skip_g_pack = c->skip_d_pack = false; }
+};
 
 // ================================================================================================
 // extern "C"
@@ -1629,8 +1668,11 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
         SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 12, s));
         SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, d_grads, d_tail, s));
         SG_COMM(sg::comm_join(&c->comm, s));
-        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 2, s));
-        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 31, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 22, s));
+        {
+            StepPackReuse reuse(c);
+            SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 31, s));
+        }
         SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, g_grads + g_tail, c->g_count - g_tail, s));
         SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 32, s));
         SG_COMM(sg::comm_all_reduce_mean_start(&c->comm, g_grads, g_tail, s));
@@ -1638,9 +1680,13 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
         return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
     }
     if (phase == 0) {
-        static const int seq[4] = {1, 2, 3, 4};
-        for (int ph : seq) SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, ph, s));
-        return 0;
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 1, s));
+        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 22, s));
+        {
+            StepPackReuse reuse(c);
+            SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 3, s));
+        }
+        return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
     }
     return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, phase, s);
 }

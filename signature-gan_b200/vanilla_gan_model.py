@@ -423,21 +423,27 @@ class VanillaGAN(nn.Module):
             dev = self.generator.fc[0].weight.device
             if self._d_loss_hist is None or self._d_loss_hist.numel() != n_critic or self._d_loss_hist.device != dev:
                 self._d_loss_hist = torch.zeros(n_critic, dtype=torch.float32, device=dev)
-        if n_critic == 1 and not self.use_spectral_norm and self.mask_override is None and self._library_dp():
-            return self._dp_step_in_library(real_images)
+        if n_critic == 1 and not self.use_spectral_norm and self.mask_override is None and self._whole_step_in_library():
+            return self._step_in_library(real_images)
         for i in range(n_critic):
             m = self.discriminator_step_async(real_images)
             if n_critic > 1:
                 self._d_loss_hist[i:i + 1].copy_(m[0:1])
         return self.generator_step_async(real_images.size(0))
 
-    def _library_dp(self) -> bool:
+    def _whole_step_in_library(self) -> bool:
+        """A single process, or data-parallel ranks whose context owns its NCCL communicator (init_library_comm); ranks
+        that all-reduce through torch.distributed drive the phases themselves."""
+        import data_parallel as dp
+        if dp.world()[1] == 1:
+            return True
         g = self.generator
         return getattr(g, "_ctx", None) is not None and g._ctx.comm_world() > 1
 
-    def _dp_step_in_library(self, real_images: torch.Tensor) -> torch.Tensor:
-        """One data-parallel D step + G step as ONE library call (sg_train_step phase 0 with a communicator): the
-        bucket all-reduces are issued by libsiggan on its communication stream between the captured phases."""
+    def _step_in_library(self, real_images: torch.Tensor) -> torch.Tensor:
+        """One D step + G step as ONE library call (sg_train_step phase 0). Inside the call nobody else writes the
+        parameters, so the D update emits the Discriminator's weight packs itself and the G step re-packs nothing; with a
+        communicator the bucket all-reduces are issued by libsiggan on its communication stream between the phases."""
         self.discriminator.train()
         self.generator.train()
         sctx = self._fused_ready()

@@ -451,6 +451,32 @@ def test_split_g_backward_phases_equal_the_fused_phase(size):
     assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1]) and torch.equal(stats[0], stats[1])
 
 
+def test_whole_step_call_equals_the_four_phases():
+    """sg_train_step(phase 0) — the D update emits the Discriminator's packs itself (fused Adam + pack kernel) and the G step
+    re-packs nothing — leaves the same parameters, moments and BatchNorm statistics, bit for bit, as the four phases called
+    one by one (each of which packs from the fp32 masters); 5 steps, so the captured graphs of both forms replay."""
+    import _siggan_lib as L
+    B, size = 32, 64
+    reals = [O.synthetic_signatures(B, size, seed=70 + i).cuda() for i in range(5)]
+    outs = []
+    for whole in (True, False):
+        gan, _, _ = make_gan(size, 9, "bf16")
+        torch.manual_seed(123)
+        L.DROPOUT.offset = 0
+        for x in reals:
+            if whole:
+                m = gan.train_step_async(x)                         # one call
+            else:
+                gan.discriminator_step_async(x)                     # phases 1, 2
+                m = gan.generator_step_async(x.size(0))             # phases 3, 4
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (gan.generator._flat.flat, gan.discriminator._flat.flat, gan.generator._flat.stats,
+                                         gan.g_optimizer._m, gan.g_optimizer._v, gan.d_optimizer._m, gan.d_optimizer._v, m)])
+        assert gan.g_optimizer._steps == 5 and gan.d_optimizer._steps == 5
+    for a, b in zip(*outs):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
 def test_library_communicator_single_rank():
     """sg_comm_* / sg_allreduce_grads with a one-rank NCCL communicator (the box the GPU suite runs on has one GPU; the
     multi-rank path is exercised by bench.py --gpus N, which asserts bit-identical replicas): the id handshake works,
