@@ -971,6 +971,15 @@ static bool graphs_enabled() {
     return on != 0;
 }
 
+static bool whole_step_graph_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SIGGAN_STEP_GRAPH");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 template <typename T>
 static int cast_latents_t(sg_ctx* c, const float* z, void* ws, int B, cudaStream_t s) {
     GWs w = carve_g(c, ws, B);
@@ -1052,12 +1061,12 @@ static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d
     return 0;
 }
 
-static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
-                       int B, float* d_grads, float* g_grads, float* metrics, int phase, cudaStream_t s) {
+// Per-step inputs and counters of one phase: plain launches on the caller's stream, outside any graph.
+static int stage_phase_inputs(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
+                              int B, float* d_grads, float* g_grads, int phase, cudaStream_t s) {
     const size_t img = (size_t)B * c->S * c->S;
     const bool dropout = st->dropout_p > 0.f;
     const bool masks_injected = dropout && st->masks_real && st->masks_fake;
-    // ---- per-step inputs and counters: plain launches on the caller's stream, outside any graph -------------------
     if (phase == 1 || phase == 11) {
         if (!real || !noise_d || !d_grads) return fail("sg_train_step: D phase needs real, noise_d and d_grads");
         float* x2 = static_cast<float*>(c->x2.p);
@@ -1100,8 +1109,36 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
         return fail("sg_train_step: unknown phase %d", phase);
     }
     SG_KCHECK("sg_train_step(inputs)");
+    return 0;
+}
+
+// kWholeStep: phases 1, 22, 3, 4 of one single-process step as ONE body (one graph): the staged inputs of all four are
+// in place before it starts (the G step's latents go to their own workspace), and the G-step part reuses the packs.
+constexpr int kWholeStep = 100;
+static int phase_bodies(sg_ctx* c, const sg_train_state* st, int B, float* d_grads, float* g_grads, float* metrics,
+                        int phase, bool masks_injected, cudaStream_t s) {
+    if (phase != kWholeStep) return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+    SG_TRY(train_phase_body(c, st, B, d_grads, g_grads, metrics, 1, masks_injected, s));
+    SG_TRY(train_phase_body(c, st, B, d_grads, g_grads, metrics, 22, masks_injected, s));
+    c->skip_g_pack = c->skip_d_pack = true;
+    const int rc = train_phase_body(c, st, B, d_grads, g_grads, metrics, 3, masks_injected, s);
+    c->skip_g_pack = c->skip_d_pack = false;
+    if (rc != 0) return rc;
+    return train_phase_body(c, st, B, d_grads, g_grads, metrics, 4, masks_injected, s);
+}
+
+static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const float* noise_d, const float* noise_g,
+                       int B, float* d_grads, float* g_grads, float* metrics, int phase, cudaStream_t s) {
+    const bool dropout = st->dropout_p > 0.f;
+    const bool masks_injected = dropout && st->masks_real && st->masks_fake;
+    if (phase == kWholeStep) {
+        static const int seq[4] = {1, 22, 3, 4};
+        for (int ph : seq) SG_TRY(stage_phase_inputs(c, st, real, noise_d, noise_g, B, d_grads, g_grads, ph, s));
+    } else {
+        SG_TRY(stage_phase_inputs(c, st, real, noise_d, noise_g, B, d_grads, g_grads, phase, s));
+    }
     const bool use_graph = graphs_enabled() && !c->prof.on && !sync_bn_on(c);
-    if (!use_graph) return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+    if (!use_graph) return phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
 
     GraphKey key;
     memset(&key, 0, sizeof(key));
@@ -1138,7 +1175,7 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
     if (ent->bad || ent->seen == 0) {
         // first sight of this configuration: run it eagerly (loads modules, sets kernel attributes, sizes buffers)
         ent->seen = 1;
-        return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+        return phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
     }
     if (!ent->exec) {
         if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -1147,10 +1184,10 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
         if (e != cudaSuccess) {
             cudaGetLastError();
             ent->bad = true;
-            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+            return phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
         }
         const unsigned long long launches0 = sg::g_launches;
-        const int rc = train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, c->cap_stream);
+        const int rc = phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, c->cap_stream);
         ent->n_launches = static_cast<int>(sg::g_launches - launches0);
         sg::g_launches = launches0;  // counted per graph launch below
         cudaGraph_t graph = nullptr;
@@ -1160,7 +1197,7 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
             cudaGetLastError();
             ent->bad = true;
             if (rc != 0) return rc;
-            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+            return phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
         }
         e = cudaGraphInstantiate(&ent->exec, graph, 0);
         cudaGraphDestroy(graph);
@@ -1168,7 +1205,7 @@ static int train_phase(sg_ctx* c, sg_train_state* st, const float* real, const f
             cudaGetLastError();
             ent->exec = nullptr;
             ent->bad = true;
-            return train_phase_body(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
+            return phase_bodies(c, st, B, d_grads, g_grads, metrics, phase, masks_injected, s);
         }
         ent->epoch = g_alloc_epoch;
     }
@@ -1680,13 +1717,16 @@ int sg_train_step(sg_ctx* c, sg_train_state* st, const float* real, const float*
         return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
     }
     if (phase == 0) {
-        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 1, s));
-        SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 22, s));
-        {
-            StepPackReuse reuse(c);
-            SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 3, s));
+        if (!whole_step_graph_enabled()) {  // SIGGAN_STEP_GRAPH=0: one graph per phase (A/B comparison)
+            SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 1, s));
+            SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 22, s));
+            {
+                StepPackReuse reuse(c);
+                SG_TRY(train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 3, s));
+            }
+            return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
         }
-        return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, 4, s);
+        return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, kWholeStep, s);
     }
     return train_phase(c, st, real, noise_d, noise_g, B, d_grads, g_grads, metrics, phase, s);
 }
