@@ -444,8 +444,12 @@ class VanillaGAN(nn.Module):
         """One D step + G step as ONE library call (sg_train_step phase 0). Inside the call nobody else writes the
         parameters, so the D update emits the Discriminator's weight packs itself and the G step re-packs nothing; with a
         communicator the bucket all-reduces are issued by libsiggan on its communication stream between the phases."""
-        self.discriminator.train()
-        self.generator.train()
+        # module modes: the library's phases do not read them; leave the ones the reference's G step leaves behind
+        # (vanilla…:274-275: G.train(), D.eval()) without walking the module trees when they are already set
+        if not self.generator.training:
+            self.generator.train()
+        if self.discriminator.training:
+            self.discriminator.eval()
         sctx = self._fused_ready()
         dev = self.generator._flat.flat.device
         real = real_images.to(dev, non_blocking=True).contiguous().float()
@@ -466,7 +470,6 @@ class VanillaGAN(nn.Module):
         if st.dropout_p > 0:
             L.DROPOUT.advance(int(sctx.lib.sg_d_mask_count(sctx.handle, 2 * B)))
         torch._foreach_add_([bn.num_batches_tracked for bn in self.generator._bn_modules()], 1)
-        self.discriminator.eval()     # the modes the reference's G step leaves behind (vanilla…:274-275)
         return self._metrics
 
     def train_step(self, real_images: torch.Tensor, n_critic: int = 1) -> Dict[str, float]:
