@@ -31,21 +31,23 @@ LEAKY_SLOPE = 0.2   # disc…:46,71
 DROPOUT_P = 0.25    # disc…:45,75
 
 
-def g_channels(image_size: int) -> List[int]:
-    """Channel ladder of the upsample blocks (gen…:131-149)."""
+def g_channels(image_size: int, width: int = 1) -> List[int]:
+    """Channel ladder of the upsample blocks (gen…:131-149). width = 2: the "2x hidden width" variant of BASELINE
+    configs[4] — not a configuration of the reference (its base_features is inert): the same blocks
+    (gen…:33-42) assembled with doubled channel counts."""
     if image_size == 64:
-        return [256, 128, 64, 32, 32]
+        return [c * width for c in (256, 128, 64, 32, 32)]
     if image_size == 128:
-        return [512, 256, 128, 64, 32, 32]
+        return [c * width for c in (512, 256, 128, 64, 32, 32)]
     raise ValueError(f"output_size must be 64 or 128, got {image_size}")
 
 
-def d_channels(image_size: int, in_ch: int = 1) -> List[int]:
-    """Channel ladder of the downsample blocks (disc…:131-194)."""
+def d_channels(image_size: int, in_ch: int = 1, width: int = 1) -> List[int]:
+    """Channel ladder of the downsample blocks (disc…:131-194); width as in g_channels (disc…:36-47 blocks)."""
     if image_size == 64:
-        return [in_ch, 64, 128, 256, 512]
+        return [in_ch] + [c * width for c in (64, 128, 256, 512)]
     if image_size == 128:
-        return [in_ch, 64, 128, 256, 512, 512]
+        return [in_ch] + [c * width for c in (64, 128, 256, 512, 512)]
     raise ValueError(f"input_size must be 64 or 128, got {image_size}")
 
 
@@ -103,7 +105,7 @@ def _g_act_grad(a: Tensor, act_slope: float) -> Tensor:
 def g_forward(sd: Dict[str, Tensor], z: Tensor, image_size: int = 64, train: bool = False, act_slope: float = 0.0):
     """Returns (image, cache, new_stats). `cache` holds every intermediate (keys documented inline). act_slope > 0:
     the ablation script's ConfigurableGenerator with activation="leaky_relu" (ablation…:216-328; same layers)."""
-    ch = g_channels(image_size)
+    ch = g_channels(image_size, sd["fc.0.weight"].shape[0] // (16 * g_channels(image_size)[0]))
     cache: Dict[str, Tensor] = {"z": z}
     new_stats: Dict[str, Tensor] = {}
     y = F.linear(z, sd["fc.0.weight"], sd["fc.0.bias"])                       # gen…:125
@@ -131,7 +133,7 @@ def g_backward(sd: Dict[str, Tensor], cache: Dict[str, Tensor], dout: Tensor, im
     """Gradients of every Generator parameter given d(loss)/d(image). `taps` (optional dict) receives the upstream
     gradient of every stage: `up{i}.dbn` / `fc.dbn` = gradient w.r.t. the stage's BatchNorm output with ReLU' applied
     (what the per-layer parity tests feed to one stage of the CUDA backward)."""
-    ch = g_channels(image_size)
+    ch = g_channels(image_size, sd["fc.0.weight"].shape[0] // (16 * g_channels(image_size)[0]))
     g: Dict[str, Tensor] = {}
     dpre = dout * (1.0 - cache["out"] ** 2)                                   # tanh'
     xin = cache["final.in"]
@@ -481,10 +483,10 @@ def hash_uniform(shape, seed: int) -> Tensor:
     return _hash_uniform(n, seed).to(torch.float32).reshape(*shape)
 
 
-def make_state_dicts(image_size: int = 64, latent_dim: int = 100, seed: int = 0, in_ch: int = 1):
+def make_state_dicts(image_size: int = 64, latent_dim: int = 100, seed: int = 0, in_ch: int = 1, width: int = 1):
     """DCGAN-style init (gen…:168-187, disc…:212-239) from the counter-based generator: N(0,.02) weights,
     zero bias, BN gamma ~ N(1,.02). Running stats are perturbed away from (0,1) so eval-mode BN is exercised."""
-    gch, dch = g_channels(image_size), d_channels(image_size, in_ch)
+    gch, dch = g_channels(image_size, width), d_channels(image_size, in_ch, width)
     s = seed * 1000
     g: Dict[str, Tensor] = {}
     f0 = gch[0] * 16
@@ -513,8 +515,8 @@ def make_state_dicts(image_size: int = 64, latent_dim: int = 100, seed: int = 0,
     return g, d
 
 
-def make_dropout_masks(batch: int, image_size: int, seed: int, p: float = DROPOUT_P) -> List[Tensor]:
-    dch = d_channels(image_size)
+def make_dropout_masks(batch: int, image_size: int, seed: int, p: float = DROPOUT_P, width: int = 1) -> List[Tensor]:
+    dch = d_channels(image_size, 1, width)
     return [(hash_uniform((batch, c), seed * 100 + i) >= p).float() / (1.0 - p) for i, c in enumerate(dch[1:])]
 
 

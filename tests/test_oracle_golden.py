@@ -207,3 +207,41 @@ def test_leaky_relu_generator_matches_reference_ablation_class(golden_dir, size)
     gg = O.g_backward(g_sd, gc, dg["__dx"], size, train=True, act_slope=slope)
     for k in O.trainable_names(g_sd):
         check_probe(f"g_grad.{k}", gg[k], gold["grads"][k], rtol=GTOL, atol=2e-8 if k != "fc.0.bias" else 1e-6)
+
+
+def test_double_width_matches_assembled_reference_blocks(golden_dir):
+    """The oracle at width = 2 (BASELINE configs[4]'s "2x hidden width") == a model assembled from the
+    reference's own channel-parameterised UpsampleBlock / DownsampleBlock with doubled channel counts
+    (tests/golden/make_golden_wide.py): forward in both modes, running statistics, G-loss and D-loss gradients."""
+    gold = torch.load(os.path.join(golden_dir, "wide2_64.pt"), weights_only=False)
+    size, width, B = gold["size"], gold["width"], gold["B"]
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=gold["seed"], width=width)
+    assert g_sd["upsample_blocks.3.block.0.weight"].shape == (64, 64, 4, 4) and d_sd["classifier.0.weight"].shape == (1, 16384)
+    z = O.hash_normal((B, 100), gold["z_seed"])
+    real = O.synthetic_signatures(B, size, seed=gold["real_seed"])
+    img, _, _ = O.g_forward(g_sd, z, size, train=False)
+    assert torch.allclose(img, gold["eval.image"], rtol=RTOL, atol=2e-6)
+    assert torch.allclose(O.d_forward(d_sd, img, size, None)[0], gold["eval.prob_fake"], rtol=RTOL, atol=1e-6)
+    assert torch.allclose(O.d_forward(d_sd, real, size, None)[0], gold["eval.prob_real"], rtol=RTOL, atol=1e-6)
+    img, gc, stats = O.g_forward(g_sd, z, size, train=True)
+    assert torch.allclose(img, gold["train.image"], rtol=RTOL, atol=2e-6)
+    for k, ref in gold["train.stats"].items():
+        assert torch.allclose(stats[k].to(ref.dtype), ref, rtol=RTOL, atol=1e-6), k
+    pr, dc = O.d_forward(d_sd, img, size, None)
+    ones = torch.ones_like(pr)
+    assert abs(float(O.bce(pr, ones)) - gold["g_loss"]) < 1e-5
+    dg = O.d_backward(d_sd, dc, O.bce_grad(pr, ones), size, None, need_dx=True)
+    gg = O.g_backward(g_sd, gc, dg["__dx"], size, train=True)
+    for k in O.trainable_names(g_sd):
+        check_probe(f"g_grad.{k}", gg[k], gold["g_grads"][k], rtol=GTOL, atol=2e-8 if k != "fc.0.bias" else 1e-6)
+    # D loss: real vs 0.9 + fake vs 0 with the reference's captured masks
+    p_r, c_r = O.d_forward(d_sd, real, size, gold["masks_real"])
+    p_f, c_f = O.d_forward(d_sd, img.detach(), size, gold["masks_fake"])
+    assert torch.allclose(p_r, gold["train.prob_real"], rtol=RTOL, atol=1e-6)
+    assert torch.allclose(p_f, gold["train.prob_fake"], rtol=RTOL, atol=1e-6)
+    loss = float(O.bce(p_r, torch.full_like(p_r, 0.9)) + O.bce(p_f, torch.zeros_like(p_f)))
+    assert abs(loss - gold["d_loss"]) < 1e-5
+    g_r = O.d_backward(d_sd, c_r, O.bce_grad(p_r, torch.full_like(p_r, 0.9)), size, gold["masks_real"])
+    g_f = O.d_backward(d_sd, c_f, O.bce_grad(p_f, torch.zeros_like(p_f)), size, gold["masks_fake"])
+    for k in O.trainable_names(d_sd):
+        check_probe(f"d_grad.{k}", g_r[k] + g_f[k], gold["d_grads"][k], rtol=GTOL, atol=2e-8)
