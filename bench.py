@@ -25,6 +25,18 @@ sys.path.insert(0, os.path.join(ROOT, "signature-gan_b200"))
 
 FLOP_PER_IMG_TRAIN = {64: 1.9707e9, 128: 9.2199e9}     # algorithmically necessary conv/linear FLOPs
 FLOP_PER_IMG_SAMPLE = {64: 87.06e6, 128: 413.73e6}
+
+
+def flops_per_image(size, width=1):
+    """(training step, sampling) conv / linear FLOPs per image (2 x MAC) of the ladders gen…:131-149 / disc…:131-194 with
+    every hidden width multiplied by `width`; width 1 reproduces the SURVEY.md §8d figures above."""
+    g = [c * width for c in ((256, 128, 64, 32, 32) if size == 64 else (512, 256, 128, 64, 32, 32))]
+    d = [1] + [c * width for c in ((64, 128, 256, 512) if size == 64 else (64, 128, 256, 512, 512))]
+    fc = 2.0 * 100 * g[0] * 16
+    f_g = fc + sum(2.0 * (4 << i) ** 2 * 16 * g[i] * g[i + 1] for i in range(len(g) - 1)) + 2.0 * size * size * 9 * g[-1]
+    c0 = 2.0 * (size // 2) ** 2 * 16 * d[1]
+    f_d = sum(2.0 * (size >> (i + 1)) ** 2 * 16 * d[i] * d[i + 1] for i in range(len(d) - 1)) + 2.0 * d[-1] * 16
+    return 8 * f_d + 4 * f_g - 2 * c0 - fc, f_g
 # sampling, algorithmic HBM bytes per image with the eval tail fused: z (400) + every bf16 level up to the input of the
 # last block written and read once (8K + 16K + 32K + 64K, x2) + the fp32 image (16K)
 SAMPLE_BYTES_PER_IMG = {64: 400 + 2 * (8192 + 16384 + 32768 + 65536) + 16384}
@@ -38,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--width", type=int, default=1, choices=[1, 2],
+                    help="hidden-width multiplier (2 = the '2x hidden width' variant of BASELINE configs[4]; bf16 only)")
     ap.add_argument("--sampling-batch", type=int, default=16384)
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / cpu baseline / per-op profile")
@@ -420,8 +434,10 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B, S = args.batch, args.size
     torch.manual_seed(1234 + rank)
-    gan = VanillaGAN(latent_dim=100, image_size=S, device=str(dev))
+    gan = VanillaGAN(latent_dim=100, image_size=S, device=str(dev), **({"width_mult": args.width} if args.width != 1 else {}))
     gan._fused_ready()
+    flop_train, flop_sample = flops_per_image(S, args.width)
+    assert args.width != 1 or abs(flop_train / FLOP_PER_IMG_TRAIN[S] - 1) < 1e-3, (flop_train, FLOP_PER_IMG_TRAIN[S])
     from data_parallel import broadcast_replica_
     broadcast_replica_([gan.generator._flat.flat, gan.generator._flat.stats, gan.discriminator._flat.flat])  # identical replicas
     comm = "none"
@@ -513,7 +529,8 @@ def run_ours(args, rank, local_rank, world):
         "metric": "training images/sec (G+D step)", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"train_step_{S}x{S}_b{B}_per_gpu", "global_batch": world * B, "image_size": S,
+        "config": {"workload": f"train_step_{S}x{S}_b{B}_per_gpu" + (f"_width{args.width}x" if args.width != 1 else ""),
+                   "global_batch": world * B, "image_size": S, "width_mult": args.width,
                    "latent_dim": 100, "parallelism": f"dp{world}", "n_critic": 1, "sync_bn": sync_bn, "gradient_allreduce": comm,
                    "l2": "4 rotating real batches (268 MB) and multi-GB per-step activations exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": 48,
@@ -526,10 +543,10 @@ def run_ours(args, rank, local_rank, world):
              "g_fake_mean"], last_metrics)},
     }
     pk = peaks()
-    step_tflops = FLOP_PER_IMG_TRAIN[S] * value / world / 1e12
+    step_tflops = flop_train * value / world / 1e12
     line["step_tensor"] = {"achieved": step_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": step_tflops / pk["bf16_tflops_sustained"], "peak_source": pk["source"],
-                           "flop_per_image": FLOP_PER_IMG_TRAIN[S]}
+                           "flop_per_image": flop_train}
 
     if not args.no_extras:
         sctx = gan.generator._ctx
@@ -615,15 +632,15 @@ def run_ours(args, rank, local_rank, world):
                 t0 = time.perf_counter()
                 G.sample_uint8_to_host(8 * SB, batch=SB, latents=zh, out=out_h)
                 samp_e2e = 8 * SB / (time.perf_counter() - t0)
-            sf = FLOP_PER_IMG_SAMPLE[S] * SB / (samp_ms * 1e-3) / 1e12
+            sf = flop_sample * SB / (samp_ms * 1e-3) / 1e12
             line["sampling"] = {"batch": SB, "images_per_s_fp32_out": SB / (samp_ms * 1e-3),
                                 "images_per_s_uint8_out": SB / (samp8_ms * 1e-3), "ms_fp32_out": samp_ms,
                                 "achieved_tflops": sf, "tensor_frac": sf / pk["bf16_tflops"],
                                 # layered bf16 activations with the tail fused: z + fc + 3 ConvT levels
                                 # read and written once + the fp32 image
-                                "bytes_per_image": SAMPLE_BYTES_PER_IMG.get(S),
+                                "bytes_per_image": SAMPLE_BYTES_PER_IMG.get(S) if args.width == 1 else None,
                                 "hbm_frac": (SAMPLE_BYTES_PER_IMG[S] * SB / (samp_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
-                                if S in SAMPLE_BYTES_PER_IMG else None,
+                                if S in SAMPLE_BYTES_PER_IMG and args.width == 1 else None,
                                 "e2e_images_per_s_uint8_host": samp_e2e,
                                 "e2e_bytes": {"h2d": SB * 400, "d2h": SB * S * S},
                                 "e2e_api": "Generator.sample_uint8_to_host (8 chunks, double-buffered D2H)"}
@@ -635,7 +652,10 @@ def run_ours(args, rank, local_rank, world):
             line["input_pipeline"] = input_pipeline_numbers(pool, B, S, dev, pk, measure_cpu=(world == 1),
                                                              gan=gan if world == 1 else None)
         # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference on the host cores, bounded sample ----
-        if rank == 0 and world == 1:
+        if rank == 0 and world == 1 and args.width != 1:
+            line["cpu_baseline"] = {"unavailable": "the 2x-width variant is not a configuration of the reference "
+                                                   "(its base_features argument is inert)"}
+        elif rank == 0 and world == 1:
             try:
                 r = cpu_baseline_subprocess(S, args.cpu_batch, 12, 2, sampling=True)
                 line["cpu_baseline"] = {"value": r["train_images_per_s"], "unit": "images/s", "cores": r["cores"],

@@ -49,6 +49,9 @@ typedef struct sg_config {
     float bn_momentum; /* 0.1 */
     float g_act_slope; /* Generator activation: 0 = ReLU (gen…:60,127); 0.2 = the ablation's ConfigurableGenerator with
                           activation="leaky_relu" (ablation…:204-207, 265-268) */
+    int width_mult;    /* 0 / 1: the reference's channel ladders (gen…:131-149, disc…:131-194); 2: every hidden width doubled —
+                          the "2x hidden width" of the width / resolution sweep. Not a configuration of the reference (its
+                          base_features argument is inert): the same blocks with doubled channel counts; bf16 mode, ReLU */
 } sg_config;
 
 int sg_abi_version(void);

@@ -22,7 +22,7 @@ SG_NET_G, SG_NET_D = 0, 1
 class SgConfig(C.Structure):
     _fields_ = [("image_size", C.c_int), ("latent_dim", C.c_int), ("precision", C.c_int),
                 ("leaky_slope", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
-                ("g_act_slope", C.c_float)]
+                ("g_act_slope", C.c_float), ("width_mult", C.c_int)]
 
 
 class SgTrainState(C.Structure):
@@ -170,10 +170,11 @@ class Context:
     _cache: Dict[tuple, "Context"] = {}
 
     def __init__(self, device: torch.device, image_size: int, latent_dim: int, precision: int,
-                 leaky_slope: float = 0.2, bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0):
+                 leaky_slope: float = 0.2, bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0,
+                 width_mult: int = 1):
         self.lib = load_library()
         self.device = device
-        cfg = SgConfig(image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope)
+        cfg = SgConfig(image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope, width_mult)
         handle = _P()
         with torch.cuda.device(device):
             check(self.lib.sg_create(C.byref(cfg), C.byref(handle)), "sg_create")
@@ -182,17 +183,17 @@ class Context:
 
     @classmethod
     def get(cls, device: torch.device, image_size: int, latent_dim: int, precision: int, leaky_slope: float = 0.2,
-            bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0) -> "Context":
+            bn_eps: float = 1e-5, bn_momentum: float = 0.1, g_act_slope: float = 0.0, width_mult: int = 1) -> "Context":
         if device.type != "cuda":
             raise RuntimeError("siggan_b200 runs on CUDA (sm_100a) only; there is no CPU path "
                                f"(module is on {device}). Move the module with .to('cuda').")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         key = (device.index, image_size, latent_dim, precision, float(leaky_slope), float(bn_eps), float(bn_momentum),
-               float(g_act_slope))
+               float(g_act_slope), int(width_mult))
         ctx = cls._cache.get(key)
         if ctx is None:
-            ctx = cls(device, image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope)
+            ctx = cls(device, image_size, latent_dim, precision, leaky_slope, bn_eps, bn_momentum, g_act_slope, width_mult)
             cls._cache[key] = ctx
         return ctx
 

@@ -772,7 +772,7 @@ int launch_conv_gemm(ConvMode mode, const __nv_bfloat16* in, const __nv_bfloat16
     if (mode != kPlain) {  // producer schedule (see ConvGemmArgs::tab)
         const int cc_n = Cin / BK, num_k = taps * cc_n / (mode == kConvT ? 4 : 1);
         const int n_ent = (mode == kConvT ? 4 : 1) * num_k;
-        if (n_ent > 128) SG_FAIL("conv_gemm: schedule of %d entries does not fit", n_ent);
+        if (n_ent > 256) SG_FAIL("conv_gemm: schedule of %d entries does not fit", n_ent);
         for (int e = 0; e < n_ent; ++e) {
             const int ph4 = e / num_k, it = e - ph4 * num_k;
             const int tap = it / cc_n, cc = it - tap * cc_n;

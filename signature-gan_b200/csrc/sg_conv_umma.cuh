@@ -50,7 +50,8 @@ struct ConvGemmArgs {
     // Producer schedule (filled by launch_conv_gemm): entry e of a section = {A channel offset, packed (dx+1) | (dy+1)<<2 |
     // parity view<<4, B k-offset, 0} for the e-th K step; transposed convolutions keep one section per output parity.
     // It lives in the parameter (constant) bank so that the producer warp reads it with uniform loads.
-    int4 tab[128];
+    int4 tab[256];  // 256 entries: 16 taps x 16 K blocks (the widest layer of the 2x-width variant: 1024 channels); > 4 KB of
+                    // kernel parameters needs CUDA 12.1+ (large kernel parameters)
 };
 
 struct WgradArgs {

@@ -20,8 +20,11 @@
 namespace sg {
 namespace {
 
-constexpr int kC0 = 64;  // output channels of the first block (disc…:134)
+constexpr int kC0 = 64;  // output channels one launch handles (the first block's width, disc…:134)
+// LD = channels of the NHWC activation tensor the 64 channels live in: 64 for the reference's widths; the 2x-width variant
+// (BASELINE configs[4]) runs two launches over the halves of a 128-channel tensor (pointers pre-offset by the caller).
 
+template <int LD>
 __global__ void __launch_bounds__(256)
 dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ mask, float slope, bf16* __restrict__ a, int B, int S) {
@@ -58,7 +61,7 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         float2 mk[8];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb)
-            mk[nb] = mask ? __ldg(reinterpret_cast<const float2*>(mask + n * kC0 + nb * 8 + 2 * t4)) : make_float2(1.f, 1.f);
+            mk[nb] = mask ? __ldg(reinterpret_cast<const float2*>(mask + n * LD + nb * 8 + 2 * t4)) : make_float2(1.f, 1.f);
         int ixs[2];
         bool okl[2], okr[2];
 #pragma unroll
@@ -79,9 +82,9 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         float up[4], lo[4], lo_next[4];
         load_rows(2 * oy_lo - 1 + ky0, up);      // first tile: rows 2 oy - 1 + ky0 and 2 oy + 1 + ky0
         load_rows(2 * oy_lo + 1 + ky0, lo);
-        bf16* dst = a + ((n * O + oy_lo) * O + ox0) * kC0;
+        bf16* dst = a + ((n * O + oy_lo) * O + ox0) * LD;
         (void)lgO;
-        for (int oy = oy_lo; oy < oy_lo + kSeg; ++oy, dst += static_cast<long>(O) * kC0) {
+        for (int oy = oy_lo; oy < oy_lo + kSeg; ++oy, dst += static_cast<long>(O) * LD) {
             if (oy + 1 < oy_lo + kSeg) load_rows(2 * oy + 3 + ky0, lo_next);
             uint32_t af[4];
             af[0] = pack2_bf16(up[0], up[1]);
@@ -112,7 +115,7 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
             for (int j = 0; j < 4; ++j) {
                 const int row = j * 4 + (lane >> 3), chunk = lane & 7;
                 const uint4 d = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
-                *reinterpret_cast<uint4*>(dst + row * kC0 + chunk * 8) = d;
+                *reinterpret_cast<uint4*>(dst + row * LD + chunk * 8) = d;
             }
             __syncwarp();
 #pragma unroll
@@ -125,6 +128,7 @@ dconv0_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 // partial[block][64*16 + 64]: dW in (c, tap) order followed by dbias.
+template <int LD>
 __global__ void __launch_bounds__(256)
 dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int B,
                         int S) {
@@ -155,11 +159,11 @@ dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy
         const int r = tile >> lg_tpr;
         const int oy = r & (O - 1);
         const long n = r >> lgO;
-        const bf16* dp = dy + ((n * O + oy) * O + ox0) * kC0 + gid * 8;
-        in.L[0] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4) * kC0));
-        in.L[1] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 1) * kC0));
-        in.L[2] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 8) * kC0));
-        in.L[3] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 9) * kC0));
+        const bf16* dp = dy + ((n * O + oy) * O + ox0) * LD + gid * 8;
+        in.L[0] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4) * LD));
+        in.L[1] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 1) * LD));
+        in.L[2] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 8) * LD));
+        in.L[3] = __ldg(reinterpret_cast<const uint4*>(dp + (2 * t4 + 9) * LD));
         const float* xi = x + n * S * S;
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
@@ -229,8 +233,10 @@ dconv0_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy
 
 constexpr int kTPitch = 17;  // floats per pixel of the tap-sum tile (16 taps + 1: conflict-free col2im reads)
 
+template <int LD>
 __global__ void __launch_bounds__(256, 3)
-dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S) {
+dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int S,
+                        int accumulate) {
     extern __shared__ float T[];  // [(RB + 2)][O][kTPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, t4 = lane & 3;
     const int O = S / 2, tpr = O / 16, lgS = ilog2(S);
@@ -264,11 +270,11 @@ dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w
                 const int oy = r0 - 1 + rrs[h];
                 live[h] = t < ntile && oy >= 0 && oy < O;
                 if (live[h]) {
-                    const bf16* dp = dy + ((n * O + oy) * O + oxs[h] + gid) * kC0 + t4 * 8;
+                    const bf16* dp = dy + ((n * O + oy) * O + oxs[h] + gid) * LD + t4 * 8;
                     A[h][0] = __ldg(reinterpret_cast<const uint4*>(dp));
                     A[h][1] = __ldg(reinterpret_cast<const uint4*>(dp + 32));
-                    A[h][2] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0));
-                    A[h][3] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * kC0 + 32));
+                    A[h][2] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * LD));
+                    A[h][3] = __ldg(reinterpret_cast<const uint4*>(dp + 8 * LD + 32));
                 }
             }
 #pragma unroll
@@ -317,7 +323,8 @@ dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w
                     if (ox >= 0 && ox < O) s += T[(trow * O + ox) * kTPitch + ky * 4 + kx];
                 }
             }
-            dx[(n * S + iy) * S + ix] = s;
+            float* o = dx + (n * S + iy) * S + ix;
+            *o = accumulate ? *o + s : s;   // second channel half of a wide first block adds to the first
         }
         __syncthreads();
     }
@@ -326,36 +333,48 @@ dconv0_dgrad_mma_kernel(const bf16* __restrict__ dy, const float* __restrict__ w
 }  // namespace
 
 void dconv0_fwd_mma(const float* x, const float* w, const float* bias, const float* mask, float slope, bf16* a, int B,
-                    int S, cudaStream_t s) {
+                    int S, cudaStream_t s, int ld) {
     const long units = static_cast<long>(B) * (S / 2 / 8) * (S / 32);  // (image, 8-row segment, 16-column strip) per warp
     static int per_sm = 0;
     if (per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dconv0_fwd_mma_kernel, 256, 0) != cudaSuccess || per_sm < 1))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dconv0_fwd_mma_kernel<64>, 256, 0) != cudaSuccess || per_sm < 1))
         per_sm = 2;
     note_launch();
-    dconv0_fwd_mma_kernel<<<blocks_for(units, 8, 148 * per_sm), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
+    if (ld == 64)
+        dconv0_fwd_mma_kernel<64><<<blocks_for(units, 8, 148 * per_sm), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
+    else
+        dconv0_fwd_mma_kernel<128><<<blocks_for(units, 8, 148 * per_sm), 256, 0, s>>>(x, w, bias, mask, slope, a, B, S);
 }
-int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s) {
+int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s, int ld) {
     const long tiles = static_cast<long>(B) * (S / 2) * (S / 32);
     const int blocks = blocks_for(tiles, 8, 148 * 4);
     note_launch();
-    dconv0_wgrad_mma_kernel<<<blocks, 256, 0, s>>>(x, dy, partial, B, S);
+    if (ld == 64)
+        dconv0_wgrad_mma_kernel<64><<<blocks, 256, 0, s>>>(x, dy, partial, B, S);
+    else
+        dconv0_wgrad_mma_kernel<128><<<blocks, 256, 0, s>>>(x, dy, partial, B, S);
     return blocks;
 }
-void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s) {
+void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s, int ld, int accumulate) {
     const int O = S / 2, RB = 1024 / O;
     const int units = B * (O / RB);
     const int smem = (RB + 2) * O * kTPitch * 4;
-    static bool ok = cudaFuncSetAttribute(dconv0_dgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) ==
-                     cudaSuccess;
+    static bool ok = cudaFuncSetAttribute(dconv0_dgrad_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) ==
+                         cudaSuccess &&
+                     cudaFuncSetAttribute(dconv0_dgrad_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) ==
+                         cudaSuccess;
     (void)ok;
     static int per_sm[2] = {0, 0};  // by image size: the band buffer of a 128 x 128 image is a little larger
     int& ps = per_sm[S == 64 ? 0 : 1];
     if (ps == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, dconv0_dgrad_mma_kernel, 256, smem) != cudaSuccess || ps < 1))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, dconv0_dgrad_mma_kernel<64>, 256, smem) != cudaSuccess || ps < 1))
         ps = 2;
     note_launch();
-    dconv0_dgrad_mma_kernel<<<units < 148 * ps ? units : 148 * ps, 256, smem, s>>>(dy, w, dx, B, S);
+    const int grid = units < 148 * ps ? units : 148 * ps;
+    if (ld == 64)
+        dconv0_dgrad_mma_kernel<64><<<grid, 256, smem, s>>>(dy, w, dx, B, S, accumulate);
+    else
+        dconv0_dgrad_mma_kernel<128><<<grid, 256, smem, s>>>(dy, w, dx, B, S, accumulate);
 }
 
 }  // namespace sg

@@ -402,10 +402,10 @@ bool set_smem(K kernel, int bytes) {
 
 // sg_gfinal_mma.cu
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
-                    uint8_t* out_u8, int B, int S, cudaStream_t s);
+                    uint8_t* out_u8, int B, int S, cudaStream_t s, int C = 32);
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                    const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
-                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s);
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s, int ld = 32);
 
 // SIGGAN_GFINAL=stencil keeps the bf16 path on the streaming-stencil kernels (A/B comparison in the harness).
 static bool use_stencil_bf16() {
@@ -419,7 +419,10 @@ static bool use_stencil_bf16() {
 template <typename T>
 void final_conv_tanh_stencil(const T* in, const float* scale, const float* shift, const float* w, const float* bias,
                              float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s) {
-    if (C != kFC || S % kStripW != 0) return;  // sg_create only admits 64 / 128 with 32 channels at the last level
+    if (C != kFC || S % kStripW != 0) {  // the streaming stencil is specialised to the reference's 32-channel last level
+        note_unsupported("final_conv_tanh (stencil)", C);
+        return;
+    }
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
     const int grid = units < sm_count_g() ? units : sm_count_g();
@@ -441,7 +444,10 @@ template <typename T>
 int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, const float* scale, const float* shift,
                            const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
                            int C, float act_slope, cudaStream_t s) {
-    if (C != kFC || S % kStripW != 0) return 0;
+    if (C != kFC || S % kStripW != 0) {
+        note_unsupported("final_conv_bwd (stencil)", C);
+        return 0;
+    }
     using Cfg = StripCfg<T>;
     const int units = B * (S / kStripW);
     const int grid = units < sm_count_g() ? units : sm_count_g();
@@ -474,6 +480,8 @@ template <>
 void final_conv_tanh<bf16>(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias,
                            float* out, uint8_t* out_u8, int B, int S, int C, float act_slope, cudaStream_t s) {
     // the mma.sync kernels are specialised to ReLU; the LeakyReLU generator of the ablation runs the streaming stencil
+    if (C == 2 * kFC && (S == 64 || S == 128) && !(scale && act_slope != 0.f))   // 2x-width variant: mma.sync kernel only
+        return gfinal_fwd_mma(in, scale, shift, w, bias, out, out_u8, B, S, s, C);
     if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128) || (scale && act_slope != 0.f))
         return final_conv_tanh_stencil<bf16>(in, scale, shift, w, bias, out, out_u8, B, S, C, act_slope, s);
     gfinal_fwd_mma(in, scale, shift, w, bias, out, out_u8, B, S, s);
@@ -490,6 +498,17 @@ template <>
 int final_conv_bwd<bf16>(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                          const float* w, bf16* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
                          int C, float act_slope, cudaStream_t s) {
+    if (C == 2 * kFC && (S == 64 || S == 128) && act_slope == 0.f) {
+        // 2x-width variant: one launch per 32-channel half of the 64-channel level; the halves share d(pre-tanh) and are
+        // independent otherwise (the bias gradient is taken from the first)
+        int grid = 0;
+        for (int c0 = 0; c0 < C; c0 += kFC) {
+            grid = gfinal_bwd_mma(dout, out, y + c0, scale + c0, shift + c0, w + c0 * 9, dbn ? dbn + c0 : nullptr, part_w,
+                                  part_bn + c0, B, S, dbn ? 0 : 1, nullptr, nullptr, nullptr, nullptr, nullptr, s, C);
+            vec_finalize(part_w, grid, 9 * kFC + 1, dW + c0 * 9, 9 * kFC, c0 == 0 ? dbias : nullptr, s);
+        }
+        return grid;
+    }
     if (use_stencil_bf16() || C != kFC || (S != 64 && S != 128) || act_slope != 0.f)
         return final_conv_bwd_stencil<bf16>(dout, out, y, scale, shift, w, dbn, dW, dbias, part_w, part_bn, B, S, C,
                                             act_slope, s);
@@ -500,12 +519,14 @@ int final_conv_bwd<bf16>(const float* dout, const float* out, const bf16* y, con
 }
 
 bool final_conv_bwd_two_pass(int S, int C, float act_slope) {
-    return !use_stencil_bf16() && C == kFC && (S == 64 || S == 128) && act_slope == 0.f;
+    return (S == 64 || S == 128) && act_slope == 0.f && ((C == kFC && !use_stencil_bf16()) || C == 2 * kFC);
 }
 void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                           const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
-                          const float* k3, bf16* dy, int B, int S, cudaStream_t s) {
-    gfinal_bwd_mma(dout, out, y, scale, shift, w, dy, nullptr, nullptr, B, S, 2, mean, rstd, k1, k2, k3, s);
+                          const float* k3, bf16* dy, int B, int S, int C, cudaStream_t s) {
+    for (int c0 = 0; c0 < C; c0 += kFC)
+        gfinal_bwd_mma(dout, out, y + c0, scale + c0, shift + c0, w + c0 * 9, dy + c0, nullptr, nullptr, B, S, 2, mean + c0,
+                       rstd + c0, k1 + c0, k2 + c0, k3 + c0, s, C);
 }
 
 }  // namespace sg

@@ -29,7 +29,10 @@ constexpr int kThr = 256;       // 8 warps
 constexpr int kChunkPx = 512;   // pixels per chunk: 32 groups of 16 = 4 per warp
 constexpr int kDepth = 4;       // cp.async ring depth (groups per thread)
 constexpr int kGroupsPerWarp = kChunkPx / 16 / (kThr / 32);
-constexpr int kStageBytes = kThr * kDepth * 32;
+constexpr int kStageBytes = kThr * kDepth * 32;   // per 32-channel group: two 16-byte pieces per thread and ring slot
+// 2x-width variant (BASELINE configs[4]): the last level has 64 channels. The forward kernel loops over CG = 2 groups of
+// 32 channels per pixel group (the tap sums of both halves go into the same accumulators); the backward kernels handle one
+// 32-channel half per launch inside the LD = 64 channel tensor (the halves are independent but for the bias gradient).
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -59,47 +62,52 @@ __device__ __forceinline__ void bn_relu8(const uint4& u, const float (&sc)[8], c
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int CG = 1>
 struct FwdCfg {
     static constexpr int kPitch = S + 4;               // == 4 (mod 16): conflict-free accumulator stores; >= S + 2
     static constexpr int kCR = kChunkPx / S;           // image rows per chunk
     static constexpr int kRing = 2 * kCR + 2;          // rows being written (next chunk) + rows being read
     static constexpr int kChunks = S / kCR;
     static constexpr int kPBytes = kRing * 9 * kPitch * 4;
-    static constexpr int kSmem = kPBytes + kStageBytes;
+    static constexpr int kSmem = kPBytes + CG * kStageBytes;
 };
 
-template <int S, bool kAffine>
+template <int S, bool kAffine, int CG = 1>
 __global__ void __launch_bounds__(kThr, 2)
 gfinal_fwd_mma_kernel(const bf16* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                       uint8_t* __restrict__ out_u8, int B) {
-    using Cfg = FwdCfg<S>;
+    using Cfg = FwdCfg<S, CG>;
+    constexpr int LD = kC * CG;  // channels per pixel of the input tensor
     constexpr int pitch = Cfg::kPitch, CR = Cfg::kCR, RING = Cfg::kRing, CHUNKS = Cfg::kChunks;
     constexpr int lgS = S == 64 ? 6 : 7;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* P = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, t = lane & 3;
-    const uint32_t my_stage = smem_addr(smem_raw + Cfg::kPBytes) + tid * 16;  // piece p of ring slot d: + (d*2+p)*kThr*16
+    // piece p of channel group cg in ring slot d: + ((d * CG + cg) * 2 + p) * kThr * 16
+    const uint32_t my_stage = smem_addr(smem_raw + Cfg::kPBytes) + tid * 16;
 
     // B fragments: n-block nb holds taps nb*8 + gid; k-step ks covers channels 8t+4ks .. 8t+4ks+3 of every lane quad
-    uint32_t bw[2][2][2];
+    uint32_t bw[CG][2][2][2];
+    float sc[CG][8], sh[CG][8];
 #pragma unroll
-    for (int nb = 0; nb < 2; ++nb) {
-        const int tap = nb * 8 + gid;
+    for (int cg = 0; cg < CG; ++cg) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+        for (int nb = 0; nb < 2; ++nb) {
+            const int tap = nb * 8 + gid;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int ch = 8 * t + 4 * ks + 2 * r;
-                bw[nb][ks][r] = tap < 9 ? pack2_bf16(w[ch * 9 + tap], w[(ch + 1) * 9 + tap]) : 0u;
-            }
-    }
-    float sc[8], sh[8];
+            for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = kAffine ? scale[8 * t + j] : 1.f;
-        sh[j] = kAffine ? shift[8 * t + j] : 0.f;
+                for (int r = 0; r < 2; ++r) {
+                    const int ch = cg * kC + 8 * t + 4 * ks + 2 * r;
+                    bw[cg][nb][ks][r] = tap < 9 ? pack2_bf16(w[ch * 9 + tap], w[(ch + 1) * 9 + tap]) : 0u;
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[cg][j] = kAffine ? scale[cg * kC + 8 * t + j] : 1.f;
+            sh[cg][j] = kAffine ? shift[cg * kC + 8 * t + j] : 0.f;
+        }
     }
     const float b0 = bias[0];
     for (int i = tid; i < RING * 9 * pitch; i += kThr) P[i] = 0.f;  // border columns 0 and S+1 stay zero forever
@@ -114,14 +122,17 @@ gfinal_fwd_mma_kernel(const bf16* __restrict__ in, const float* __restrict__ sca
         const int c = r / kGroupsPerWarp, g = r - c * kGroupsPerWarp;
         const int n = blockIdx.x + li * gridDim.x;
         const int pix = c * kChunkPx + (warp * kGroupsPerWarp + g) * 16 + gid;
-        return in + (static_cast<size_t>(n) * S * S + pix) * kC + t * 8;
+        return in + (static_cast<size_t>(n) * S * S + pix) * LD + t * 8;
     };
     auto issue = [&](long it) {
         if (it < total_items) {
             const bf16* src = item_src(it);
-            const uint32_t dst = my_stage + static_cast<uint32_t>(it % kDepth) * 2 * kThr * 16;
-            cp_async16(dst, src);
-            cp_async16(dst + kThr * 16, src + 8 * kC);
+#pragma unroll
+            for (int cg = 0; cg < CG; ++cg) {
+                const uint32_t dst = my_stage + (static_cast<uint32_t>(it % kDepth) * CG + cg) * 2 * kThr * 16;
+                cp_async16(dst, src + cg * kC);
+                cp_async16(dst + kThr * 16, src + 8 * LD + cg * kC);
+            }
         }
         cp_async_commit();
     };
@@ -153,25 +164,28 @@ gfinal_fwd_mma_kernel(const bf16* __restrict__ in, const float* __restrict__ sca
             for (int g = 0; g < kGroupsPerWarp; ++g, ++it) {
                 issue(it + kDepth - 1);
                 cp_async_wait<kDepth - 1>();
-                const uint8_t* st = smem_raw + Cfg::kPBytes + tid * 16 + (it % kDepth) * 2 * kThr * 16;
-                const uint4 u0 = *reinterpret_cast<const uint4*>(st);
-                const uint4 u1 = *reinterpret_cast<const uint4*>(st + kThr * 16);
-                float a0[8], a1[8];
-                bn_relu8<kAffine>(u0, sc, sh, a0);
-                bn_relu8<kAffine>(u1, sc, sh, a1);
-                uint32_t p0[4], p1[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    p0[j] = kAffine ? pack2_bf16(a0[2 * j], a0[2 * j + 1]) : (&u0.x)[j];
-                    p1[j] = kAffine ? pack2_bf16(a1[2 * j], a1[2 * j + 1]) : (&u1.x)[j];
-                }
                 float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t A0[4] = {p0[0], p1[0], p0[1], p1[1]};
-                const uint32_t A1[4] = {p0[2], p1[2], p0[3], p1[3]};
-                mma_bf16(d0, A0, bw[0][0][0], bw[0][0][1]);
-                mma_bf16(d1, A0, bw[1][0][0], bw[1][0][1]);
-                mma_bf16(d0, A1, bw[0][1][0], bw[0][1][1]);
-                mma_bf16(d1, A1, bw[1][1][0], bw[1][1][1]);
+#pragma unroll
+                for (int cg = 0; cg < CG; ++cg) {
+                    const uint8_t* st = smem_raw + Cfg::kPBytes + tid * 16 + ((it % kDepth) * CG + cg) * 2 * kThr * 16;
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(st);
+                    const uint4 u1 = *reinterpret_cast<const uint4*>(st + kThr * 16);
+                    float a0[8], a1[8];
+                    bn_relu8<kAffine>(u0, sc[cg], sh[cg], a0);
+                    bn_relu8<kAffine>(u1, sc[cg], sh[cg], a1);
+                    uint32_t p0[4], p1[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        p0[j] = kAffine ? pack2_bf16(a0[2 * j], a0[2 * j + 1]) : (&u0.x)[j];
+                        p1[j] = kAffine ? pack2_bf16(a1[2 * j], a1[2 * j + 1]) : (&u1.x)[j];
+                    }
+                    const uint32_t A0[4] = {p0[0], p1[0], p0[1], p1[1]};
+                    const uint32_t A1[4] = {p0[2], p1[2], p0[3], p1[3]};
+                    mma_bf16(d0, A0, bw[cg][0][0][0], bw[cg][0][0][1]);
+                    mma_bf16(d1, A0, bw[cg][1][0][0], bw[cg][1][0][1]);
+                    mma_bf16(d0, A1, bw[cg][0][1][0], bw[cg][0][1][1]);
+                    mma_bf16(d1, A1, bw[cg][1][1][0], bw[cg][1][1][1]);
+                }
                 const int pix = c * kChunkPx + (warp * kGroupsPerWarp + g) * 16;
                 const int yy = pix >> lgS, x = (pix & (S - 1)) + gid;
                 float* pr = P + (yy % RING) * 9 * pitch + 1 + x;
@@ -219,7 +233,7 @@ struct BwdCfg {
 struct BnBwdCoef {
     const float *mean, *rstd, *k1, *k2, *k3;
 };
-template <int S, int MODE>
+template <int S, int MODE, int LD = kC>
 __global__ void __launch_bounds__(kThr, 2)
 gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ dout, const float* __restrict__ outimg, const float* __restrict__ w,
@@ -286,10 +300,10 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
             const int c = r / kGroupsPerWarp, g = r - c * kGroupsPerWarp;
             const int n = blockIdx.x + li * gridDim.x;
             const int pix = c * kChunkPx + (warp * kGroupsPerWarp + g) * 16 + gid;
-            const bf16* src = y + (static_cast<size_t>(n) * S * S + pix) * kC + t * 8;
+            const bf16* src = y + (static_cast<size_t>(n) * S * S + pix) * LD + t * 8;
             const uint32_t dst = my_stage + static_cast<uint32_t>(it % kDepth) * 2 * kThr * 16;
             cp_async16(dst, src);
-            cp_async16(dst + kThr * 16, src + 8 * kC);
+            cp_async16(dst + kThr * 16, src + 8 * LD);
         }
         cp_async_commit();
     };
@@ -360,9 +374,9 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
                 o1[j] = pack2_bf16(f0, f1);
             }
             if (kWrite) {
-                bf16* dst = dbn + (static_cast<size_t>(n) * S * S + pix0 + gid) * kC + t * 8;
+                bf16* dst = dbn + (static_cast<size_t>(n) * S * S + pix0 + gid) * LD + t * 8;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-                *reinterpret_cast<uint4*>(dst + 8 * kC) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<uint4*>(dst + 8 * LD) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
             }
             if (!kSums) continue;
             // ---- weight gradient: [taps][16 pixels] x [16 pixels][32 channels]
@@ -416,8 +430,10 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
         for (int wv = 0; wv < kThr / 32; ++wv) s += red[wv * Cfg::kRedFloats + i];
         if (i < 9 * kC)
             part_w[static_cast<size_t>(blockIdx.x) * (9 * kC + 1) + i] = s;
-        else if (i < 9 * kC + 2 * kC)
-            part_bn[static_cast<size_t>(blockIdx.x) * 2 * kC + (i - 9 * kC)] = s;
+        else if (i < 9 * kC + 2 * kC) {  // row layout [2][LD]: this launch's 32 channels inside the level's LD
+            const int e = i - 9 * kC;
+            part_bn[static_cast<size_t>(blockIdx.x) * 2 * LD + (e / kC) * LD + (e % kC)] = s;
+        }
         else
             part_w[static_cast<size_t>(blockIdx.x) * (9 * kC + 1) + 9 * kC] = s;
     }
@@ -445,51 +461,66 @@ int grid_for(K kernel, int smem, int B) {
 }  // namespace
 
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
-                    uint8_t* out_u8, int B, int S, cudaStream_t s) {
+                    uint8_t* out_u8, int B, int S, cudaStream_t s, int C) {
     note_launch();
-#define SG_GF_LAUNCH(SZ, AFF)                                                                                     \
-    do {                                                                                                          \
-        static int grid_cache = 0, grid_b = -1;                                                                   \
-        if (grid_b != B) {                                                                                        \
-            grid_cache = grid_for(gfinal_fwd_mma_kernel<SZ, AFF>, FwdCfg<SZ>::kSmem, B);                          \
-            grid_b = B;                                                                                           \
-        }                                                                                                         \
-        gfinal_fwd_mma_kernel<SZ, AFF><<<grid_cache, kThr, FwdCfg<SZ>::kSmem, s>>>(in, scale, shift, w, bias, out, \
-                                                                                   out_u8, B);                    \
+#define SG_GF_LAUNCH(SZ, AFF, CGN)                                                                                      \
+    do {                                                                                                                \
+        static int grid_cache = 0, grid_b = -1;                                                                         \
+        if (grid_b != B) {                                                                                              \
+            cudaFuncSetAttribute(gfinal_fwd_mma_kernel<SZ, AFF, CGN>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 FwdCfg<SZ, CGN>::kSmem);                                                               \
+            grid_cache = grid_for(gfinal_fwd_mma_kernel<SZ, AFF, CGN>, FwdCfg<SZ, CGN>::kSmem, B);                      \
+            grid_b = B;                                                                                                 \
+        }                                                                                                               \
+        gfinal_fwd_mma_kernel<SZ, AFF, CGN><<<grid_cache, kThr, FwdCfg<SZ, CGN>::kSmem, s>>>(in, scale, shift, w, bias,  \
+                                                                                           out, out_u8, B);             \
     } while (0)
-    if (S == 64) {
-        if (scale) SG_GF_LAUNCH(64, true); else SG_GF_LAUNCH(64, false);
+    if (C == 2 * kC) {
+        if (S == 64) {
+            if (scale) SG_GF_LAUNCH(64, true, 2); else SG_GF_LAUNCH(64, false, 2);
+        } else {
+            if (scale) SG_GF_LAUNCH(128, true, 2); else SG_GF_LAUNCH(128, false, 2);
+        }
+    } else if (S == 64) {
+        if (scale) SG_GF_LAUNCH(64, true, 1); else SG_GF_LAUNCH(64, false, 1);
     } else {
-        if (scale) SG_GF_LAUNCH(128, true); else SG_GF_LAUNCH(128, false);
+        if (scale) SG_GF_LAUNCH(128, true, 1); else SG_GF_LAUNCH(128, false, 1);
     }
 #undef SG_GF_LAUNCH
 }
 
 // mode 0 / 1 / 2: see gfinal_bwd_mma_kernel. Returns the number of partial rows written to part_w ([chunks][9*32+1])
-// and part_bn ([chunks][2][32]) (modes 0 and 1).
+// and part_bn ([chunks][2][ld]) (modes 0 and 1). One launch handles 32 channels of a level with `ld` channels per pixel
+// (32, or 64 for the 2x-width variant: the caller pre-offsets every per-channel pointer by the half it wants).
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                    const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
-                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s) {
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s, int ld) {
     note_launch();
     const BnBwdCoef coef{mean, rstd, k1, k2, k3};
     int grid = 0;
-#define SG_GB_LAUNCH(SZ, MD)                                                                                          \
-    do {                                                                                                              \
-        static int per_b = -1, g_cache = 0;                                                                           \
-        if (per_b != B) {                                                                                             \
-            g_cache = grid_for(gfinal_bwd_mma_kernel<SZ, MD>, BwdCfg<SZ>::kSmem, B);                                  \
-            if (g_cache > kMaxChunks) g_cache = kMaxChunks;                                                           \
-            per_b = B;                                                                                                \
-        }                                                                                                             \
-        grid = g_cache;                                                                                               \
-        gfinal_bwd_mma_kernel<SZ, MD><<<grid, kThr, BwdCfg<SZ>::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, \
-                                                                           part_bn, B, coef);                         \
+#define SG_GB_LAUNCH(SZ, MD, LDN)                                                                                          \
+    do {                                                                                                                   \
+        static int per_b = -1, g_cache = 0;                                                                                \
+        if (per_b != B) {                                                                                                  \
+            g_cache = grid_for(gfinal_bwd_mma_kernel<SZ, MD, LDN>, BwdCfg<SZ>::kSmem, B);                                  \
+            if (g_cache > kMaxChunks) g_cache = kMaxChunks;                                                                \
+            per_b = B;                                                                                                     \
+        }                                                                                                                  \
+        grid = g_cache;                                                                                                    \
+        gfinal_bwd_mma_kernel<SZ, MD, LDN><<<grid, kThr, BwdCfg<SZ>::kSmem, s>>>(y, scale, shift, dout, out, w, dbn, part_w, \
+                                                                                part_bn, B, coef);                         \
     } while (0)
-    if (S == 64) {
-        if (mode == 0) SG_GB_LAUNCH(64, 0); else if (mode == 1) SG_GB_LAUNCH(64, 1); else SG_GB_LAUNCH(64, 2);
+#define SG_GB_MODES(SZ, LDN)                                                                   \
+    do {                                                                                       \
+        if (mode == 0) SG_GB_LAUNCH(SZ, 0, LDN); else if (mode == 1) SG_GB_LAUNCH(SZ, 1, LDN); \
+        else SG_GB_LAUNCH(SZ, 2, LDN);                                                         \
+    } while (0)
+    if (ld == 2 * kC) {
+        if (S == 64) SG_GB_MODES(64, 64); else SG_GB_MODES(128, 64);
     } else {
-        if (mode == 0) SG_GB_LAUNCH(128, 0); else if (mode == 1) SG_GB_LAUNCH(128, 1); else SG_GB_LAUNCH(128, 2);
+        if (S == 64) SG_GB_MODES(64, 32); else SG_GB_MODES(128, 32);
     }
+#undef SG_GB_MODES
 #undef SG_GB_LAUNCH
     return grid;
 }

@@ -11,10 +11,20 @@ namespace sg {
 unsigned long long g_launches = 0;
 static thread_local char k_err[256] = "";
 const char* kernels_last_error() { return k_err; }
+static thread_local bool k_unsupported = false;  // a launcher refused its arguments since the last kernels_check
+void note_unsupported(const char* what, int C) {
+    snprintf(k_err, sizeof(k_err), "%s: %d channels unsupported in this precision mode (no kernel launched)", what, C);
+    k_unsupported = true;
+}
 int kernels_check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(k_err, sizeof(k_err), "%s: %s", what, cudaGetErrorString(e));
+        k_unsupported = false;
+        return -1;
+    }
+    if (k_unsupported) {  // k_err holds the launcher's message
+        k_unsupported = false;
         return -1;
     }
     return 0;
@@ -597,8 +607,9 @@ template <typename T>
 void d_conv0(const float* x, const float* w, const float* bias, const float* mask, float slope, T* a, int B, int S,
              int C, cudaStream_t s) {
     if constexpr (std::is_same<T, bf16>::value) {
-        if (C == 64) {
-            dconv0_fwd_mma(x, w, bias, mask, slope, a, B, S, s);
+        if (C == 64 || C == 128) {  // 64 channels per launch inside the C-channel NHWC tensor
+            for (int c0 = 0; c0 < C; c0 += 64)
+                dconv0_fwd_mma(x, w + c0 * 16, bias + c0, mask ? mask + c0 : nullptr, slope, a + c0, B, S, s, C);
             return;
         }
     }
@@ -699,8 +710,17 @@ d_conv0_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, floa
 }
 template <typename T>
 void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s) {
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (C == 128) {  // 2x-width variant: one launch per 64-channel half; dW (C*16) is followed by dbias (C)
+            for (int c0 = 0; c0 < C; c0 += 64) {
+                const int chunks = dconv0_wgrad_mma(x, dy + c0, partial, B, S, s, C);
+                vec_finalize(partial, chunks, 64 * 17, dW + c0 * 16, 64 * 16, dW + C * 16 + c0, s);
+            }
+            return;
+        }
+    }
     if (C != 64) {
-        snprintf(k_err, sizeof(k_err), "d_conv0_wgrad: C=%d unsupported (reference uses 64)", C);
+        note_unsupported("d_conv0_wgrad", C);
         return;
     }
     const long total = static_cast<long>(B) * (S / 2) * (S / 2);
@@ -786,12 +806,14 @@ d_conv0_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, floa
 }
 template <typename T>
 void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s) {
-    if (C != 64) {
-        snprintf(k_err, sizeof(k_err), "d_conv0_dgrad: C=%d unsupported (reference uses 64)", C);
-        return;
-    }
     if constexpr (std::is_same<T, bf16>::value) {
-        dconv0_dgrad_mma(dy, w, dx, B, S, s);
+        if (C == 64 || C == 128) {
+            for (int c0 = 0; c0 < C; c0 += 64) dconv0_dgrad_mma(dy + c0, w + c0 * 16, dx, B, S, s, C, c0 > 0 ? 1 : 0);
+            return;
+        }
+    }
+    if (C != 64) {
+        note_unsupported("d_conv0_dgrad", C);
         return;
     }
     const long threads = static_cast<long>(B) * (S / 2) * (S / 2) * 4;

@@ -118,7 +118,9 @@ void vec_finalize(const float* partial, int chunks, int n, float* out_a, int na,
 bool final_conv_bwd_two_pass(int S, int C, float act_slope);
 void final_conv_bwd_apply(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                           const float* w, const float* mean, const float* rstd, const float* k1, const float* k2,
-                          const float* k3, bf16* dy, int B, int S, cudaStream_t s);
+                          const float* k3, bf16* dy, int B, int S, int C, cudaStream_t s);
+// records "<what>: C=<C> unsupported" for kernels_check (the next SG_KCHECK fails with it)
+void note_unsupported(const char* what, int C);
 
 // ---- discriminator side ----------------------------------------------------------------------
 // Conv 4x4 s2 p1, 1 -> C channels (disc…:134-139) with bias + LeakyReLU + dropout mask.
@@ -129,11 +131,13 @@ template <typename T>
 void d_conv0_wgrad(const float* x, const T* dy, float* dW, float* partial, int B, int S, int C, cudaStream_t s);
 template <typename T>
 void d_conv0_dgrad(const T* dy, const float* w, float* dx, int B, int S, int C, cudaStream_t s);
-// bf16 mode implementations of the three calls above (sg_dconv0.cu, warp-level mma.sync); C = 64 only.
+// bf16 mode implementations of the three calls above (sg_dconv0.cu, warp-level mma.sync): 64 channels per launch inside an
+// NHWC tensor of `ld` channels (64, or 128 for the 2x-width variant: two launches, pointers pre-offset per half).
 void dconv0_fwd_mma(const float* x, const float* w, const float* bias, const float* mask, float slope, bf16* a, int B,
-                    int S, cudaStream_t s);
-int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s);  // returns chunks
-void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s);
+                    int S, cudaStream_t s, int ld = 64);
+int dconv0_wgrad_mma(const float* x, const bf16* dy, float* partial, int B, int S, cudaStream_t s, int ld = 64);  // returns chunks
+void dconv0_dgrad_mma(const bf16* dy, const float* w, float* dx, int B, int S, cudaStream_t s, int ld = 64,
+                      int accumulate = 0);
 // logit = <a, wp> + b ; prob = sigmoid(logit). a is [B][F] NHWC-flattened.
 template <typename T>
 void classifier_sigmoid(const T* a, const float* wp, const float* bias, float* prob, int B, int F, cudaStream_t s);

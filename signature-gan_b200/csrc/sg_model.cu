@@ -289,7 +289,7 @@ long long mask_offset(const sg_ctx* c, int batch, int layer) {
 
 int ensure_scratch(sg_ctx* c, int B) {
     if (B <= c->scratch_batch) return 0;
-    const size_t lvl = static_cast<size_t>(B) * c->S * c->S * 32 * c->es;  // largest activation level
+    const size_t lvl = static_cast<size_t>(B) * c->S * c->S * c->gch[c->L] * c->es;  // largest activation level
     SG_TRY(c->bufA.ensure(lvl));
     SG_TRY(c->bufB.ensure(lvl));
     SG_TRY(c->dpre.ensure(static_cast<size_t>(B) * c->S * c->S * 4));
@@ -311,11 +311,12 @@ int ensure_scratch(sg_ctx* c, int B) {
     SG_TRY(c->wpart.ensure(wp * 4));
     SG_TRY(c->cpart.ensure(static_cast<size_t>(sg::kMaxChunks) * 2 * 2048 * 4));
     const size_t b_pad = (static_cast<size_t>(B) + 63) / 64 * 64;  // keeps k1..k3 16-byte aligned (float4 loads)
-    SG_TRY(c->small.ensure((b_pad + 3 * 8192) * 4));
+    const size_t kmax = static_cast<size_t>(c->gch[0]) * 16;  // the widest BatchNorm: the fc stage's BatchNorm1d
+    SG_TRY(c->small.ensure((b_pad + 3 * kmax) * 4));
     c->dlogit = static_cast<float*>(c->small.p);
     c->k1 = c->dlogit + b_pad;
-    c->k2 = c->k1 + 8192;
-    c->k3 = c->k2 + 8192;
+    c->k2 = c->k1 + kmax;
+    c->k3 = c->k2 + kmax;
     c->scratch_batch = B;
     return 0;
 }
@@ -665,7 +666,7 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
             PROF((nm + ".bn_bwd_apply").c_str(), 4.0 * B * c->S * c->S * 9.0 * Cout, 2.0 * es * (double)rows * Cout);
             sg::final_conv_bwd_apply(grad_image, w.out, reinterpret_cast<const bf16*>(w.y[i]), w.scale[L], w.shift[L],
                                      params + c->gt[c->g_final_w].offset, w.mean[L], w.rstd[L], c->k1, c->k2, c->k3,
-                                     reinterpret_cast<bf16*>(cur), B, c->S, s);
+                                     reinterpret_cast<bf16*>(cur), B, c->S, Cout, s);
         } else {
         PROF((nm + ".bn_bwd_apply").c_str(), 0, 3.0 * es * (double)rows * Cout);
         sg::bn_bwd_apply<T>(reinterpret_cast<const T*>(cur), reinterpret_cast<const T*>(w.y[i]), w.mean[i + 1],
@@ -1266,6 +1267,12 @@ int sg_create(const sg_config* cfg, sg_ctx** out) {
     if (cfg->latent_dim < 1 || cfg->latent_dim > 512) return fail("sg_create: latent_dim %d unsupported", cfg->latent_dim);
     if (cfg->precision != SG_PREC_BF16 && cfg->precision != SG_PREC_FP32) return fail("sg_create: bad precision");
     if (!(cfg->g_act_slope >= 0.f && cfg->g_act_slope < 1.f)) return fail("sg_create: g_act_slope must be in [0, 1)");
+    const int wm = cfg->width_mult == 0 ? 1 : cfg->width_mult;
+    if (wm != 1 && wm != 2) return fail("sg_create: width_mult must be 1 or 2, got %d", cfg->width_mult);
+    if (wm == 2 && cfg->precision != SG_PREC_BF16)
+        return fail("sg_create: the 2x-width variant runs in the bf16 tensor-core mode only (its first conv / final conv "
+                    "kernels in the fp32 validation mode are specialised to the reference's widths)");
+    if (wm == 2 && cfg->g_act_slope != 0.f) return fail("sg_create: the 2x-width variant supports the ReLU generator only");
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
         cudaGetLastError();
@@ -1290,6 +1297,9 @@ int sg_create(const sg_config* cfg, sg_ctx** out) {
         memcpy(c->gch, g, sizeof(g));
         memcpy(c->dch, d, sizeof(d));
     }
+    // 2x hidden width (BASELINE configs[4]; not a configuration of the reference — the same blocks, doubled ladders)
+    for (int i = 0; i <= c->L; ++i) c->gch[i] *= wm;
+    for (int i = 1; i <= c->ND; ++i) c->dch[i] *= wm;
     // ---- parameter tables in reference named_parameters() order (gen…:124-163, disc…:131-207)
     long long off = 0, soff = 0;
     const int F0 = c->gch[0] * 16;

@@ -109,16 +109,25 @@ class Discriminator(nn.Module):
     """
 
     def __init__(self, input_size: int = 64, input_channels: int = 1, use_spectral_norm: bool = False,
-                 dropout: float = 0.25, leaky_slope: float = 0.2) -> None:
+                 dropout: float = 0.25, leaky_slope: float = 0.2, base_features: int = 64) -> None:
         super().__init__()
         if input_size not in [64, 128]:
             raise ValueError(f"input_size must be 64 or 128, got {input_size}")
+        # base_features (an extension, last in the signature; the reference's ladder starts at 64, disc…:131-194): 128
+        # selects the "2x hidden width" variant of the width / resolution sweep (bf16 mode, no spectral norm)
+        if base_features not in (64, 128):
+            raise ValueError(f"base_features must be 64 or 128, got {base_features}")
+        if base_features == 128 and use_spectral_norm:
+            raise NotImplementedError("the 2x-width Discriminator is built without spectral norm")
+        self.base_features = base_features
+        self._width_mult = base_features // 64
         self.input_size = input_size
         self.input_channels = input_channels
         self.use_spectral_norm = use_spectral_norm
         self.dropout = dropout
         self.leaky_slope = leaky_slope
-        ladder = [input_channels, 64, 128, 256, 512] if input_size == 64 else [input_channels, 64, 128, 256, 512, 512]
+        ladder = [input_channels] + [c * self._width_mult
+                                     for c in ([64, 128, 256, 512] if input_size == 64 else [64, 128, 256, 512, 512])]
         self.conv_blocks = nn.Sequential(*[
             DownsampleBlock(a, b, use_spectral_norm=use_spectral_norm, dropout=dropout, leaky_slope=leaky_slope)
             for a, b in zip(ladder[:-1], ladder[1:])])
@@ -149,7 +158,7 @@ class Discriminator(nn.Module):
         if self.input_channels != 1:
             raise NotImplementedError("siggan_b200 implements the grayscale (input_channels=1) configuration")
         self._ctx = L.Context.get(device, self.input_size, getattr(self, "_latent_hint", 100), self._precision,
-                                  self.leaky_slope)
+                                  self.leaky_slope, width_mult=self._width_mult)
         self._flat.sync(self._ctx)
 
     def _sn_modules(self) -> List[nn.Module]:

@@ -89,7 +89,12 @@ class Generator(nn.Module):
         self.init_channels = base_features if output_size == 64 else base_features * 2
         feat = self.init_channels * self.init_size * self.init_size
         self.fc = nn.Sequential(nn.Linear(latent_dim, feat), nn.BatchNorm1d(feat), nn.ReLU(inplace=True))
-        ladder = [256, 128, 64, 32, 32] if output_size == 64 else [512, 256, 128, 64, 32, 32]
+        # base_features is inert in the reference (any value but 256 fails in its first ConvTranspose2d, whose widths are
+        # literals, gen…:131-149). Here 512 selects the "2x hidden width" variant of the width / resolution sweep: the same
+        # blocks with every channel count doubled (bf16 mode only); other values keep the reference's ladder and fail as
+        # the reference does, at the first use.
+        self._width_mult = 2 if base_features == 512 else 1
+        ladder = [c * self._width_mult for c in ([256, 128, 64, 32, 32] if output_size == 64 else [512, 256, 128, 64, 32, 32])]
         self.upsample_blocks = nn.Sequential(*[UpsampleBlock(a, b) for a, b in zip(ladder[:-1], ladder[1:])])
         self.final_conv = nn.Sequential(nn.Conv2d(ladder[-1], output_channels, kernel_size=3, stride=1, padding=1,
                                                   bias=True), nn.Tanh())
@@ -117,12 +122,12 @@ class Generator(nn.Module):
         if self.output_channels != 1:
             raise NotImplementedError("siggan_b200 implements the grayscale (output_channels=1) configuration the "
                                       "reference trains and serves")
-        if self.init_channels != (256 if self.output_size == 64 else 512):
+        if self.init_channels != (256 if self.output_size == 64 else 512) * self._width_mult:
             raise RuntimeError("base_features other than 256 is not a working configuration of the reference either "
                                "(its first ConvTranspose2d is hard-wired to 256/512 input channels)")
         bns = self._bn_modules()
         self._ctx = L.Context.get(device, self.output_size, self.latent_dim, self._precision, 0.2, bns[0].eps,
-                                  bns[0].momentum, self._act_slope)
+                                  bns[0].momentum, self._act_slope, self._width_mult)
         self._flat.sync(self._ctx, bns)
 
     def set_precision(self, precision: str) -> "Generator":

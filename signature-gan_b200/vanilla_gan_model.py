@@ -165,8 +165,11 @@ class VanillaGAN(nn.Module):
 
     def __init__(self, latent_dim: int = 100, image_size: int = 64, image_channels: int = 1, g_lr: float = 2e-4,
                  d_lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, label_smoothing: float = 0.9,
-                 use_spectral_norm: bool = False, device: Optional[str] = None) -> None:
+                 use_spectral_norm: bool = False, device: Optional[str] = None, width_mult: int = 1) -> None:
         super().__init__()
+        if width_mult not in (1, 2):      # extension (last in the signature): 2 = the "2x hidden width" sweep variant
+            raise ValueError(f"width_mult must be 1 or 2, got {width_mult}")
+        self.width_mult = width_mult
         self.latent_dim, self.image_size, self.image_channels = latent_dim, image_size, image_channels
         self.g_lr, self.d_lr, self.beta1, self.beta2 = g_lr, d_lr, beta1, beta2
         self.label_smoothing = label_smoothing
@@ -175,9 +178,10 @@ class VanillaGAN(nn.Module):
             self._device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         else:
             self._device = torch.device(device)
-        self.generator = Generator(latent_dim=latent_dim, output_size=image_size, output_channels=image_channels)
+        self.generator = Generator(latent_dim=latent_dim, output_size=image_size, output_channels=image_channels,
+                                   base_features=256 * width_mult)
         self.discriminator = Discriminator(input_size=image_size, input_channels=image_channels,
-                                           use_spectral_norm=use_spectral_norm)
+                                           use_spectral_norm=use_spectral_norm, base_features=64 * width_mult)
         self.discriminator._latent_hint = latent_dim
         self.criterion = BCELoss()
         self.g_optimizer = FusedAdam(self.generator, lr=g_lr, betas=(beta1, beta2))
@@ -518,7 +522,7 @@ class VanillaGAN(nn.Module):
                 "g_lr": self.g_lr, "d_lr": self.d_lr, "beta1": self.beta1, "beta2": self.beta2,
                 "label_smoothing": self.label_smoothing, "use_spectral_norm": self.use_spectral_norm,
                 "current_epoch": self.current_epoch, "global_step": self.global_step, "g_params": gp, "d_params": dp,
-                "total_params": gp + dp}
+                "total_params": gp + dp, **({"width_mult": self.width_mult} if self.width_mult != 1 else {})}
 
     def save(self, path: Union[str, Path], save_optimizer: bool = True, save_history: bool = True) -> None:
         """Checkpoint in the reference's format (vanilla…:433-474): `<path>.pt` + `<path>_config.json`."""
@@ -572,7 +576,8 @@ class VanillaGAN(nn.Module):
         cfg = torch.load(path, map_location="cpu", weights_only=False)["config"]
         model = cls(latent_dim=cfg["latent_dim"], image_size=cfg["image_size"], image_channels=cfg["image_channels"],
                     g_lr=cfg["g_lr"], d_lr=cfg["d_lr"], beta1=cfg["beta1"], beta2=cfg["beta2"],
-                    label_smoothing=cfg["label_smoothing"], use_spectral_norm=cfg["use_spectral_norm"], device=device)
+                    label_smoothing=cfg["label_smoothing"], use_spectral_norm=cfg["use_spectral_norm"], device=device,
+                    width_mult=cfg.get("width_mult", 1))
         model.load(path, load_optimizer=True, load_history=True)
         return model
 

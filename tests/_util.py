@@ -62,10 +62,10 @@ def check_grads(precision, net, got: dict, ref32: dict, ref64: dict, skip=("fc.0
     return errs
 
 
-def make_gan(size: int, seed: int, precision: str, device="cuda"):
+def make_gan(size: int, seed: int, precision: str, device="cuda", width: int = 1):
     from vanilla_gan_model import VanillaGAN
-    g_sd, d_sd = O.make_state_dicts(size, 100, seed=seed)
-    gan = VanillaGAN(latent_dim=100, image_size=size, device=device)
+    g_sd, d_sd = O.make_state_dicts(size, 100, seed=seed, width=width)
+    gan = VanillaGAN(latent_dim=100, image_size=size, device=device, **({"width_mult": width} if width != 1 else {}))
     gan.generator.set_precision(precision)
     gan.discriminator.set_precision(precision)
     gan.generator.load_state_dict(g_sd)

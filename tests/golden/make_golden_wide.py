@@ -5,7 +5,7 @@ ConvTranspose2d), so the fixture comes from a model ASSEMBLED FR
 channel-parameterised `UpsampleBlock` (src/generator_vanilla_gan.py:17-66) and `DownsampleBlock`
 (src/discriminator_vanilla_gan.py:18-81), imported unmodified from /root/reference/src, stacked exactly as
 `Generator.__init__` / `Discriminator.__init__` stack them (gen…:124-163, disc…:131-207) with every channel count doubled.
-Records, at 64x64 and B = 8: eval / training-mode generator images, running statistics, the discriminator's probabilities
+Records, at 64x64 and B = 16: eval / training-mode generator images, running statistics, the discriminator's probabilities
 (eval and with captured Dropout2d masks), and probes of every parameter gradient of the G loss (labels 1) and the D loss
 (real vs 0.9, fake vs 0).
 
@@ -66,7 +66,7 @@ def build(size, width):
 
 
 def main():
-    size, width, B, seed = 64, 2, 8, 21
+    size, width, B, seed = 64, 2, 16, 21
     g_sd, d_sd = O.make_state_dicts(size, 100, seed=seed, width=width)
     G, D = build(size, width)
     G.load_state_dict(g_sd)

@@ -22,10 +22,10 @@ int final_conv_bwd_stencil(const float* dout, const float* out, const T* y, cons
                            const float* w, T* dbn, float* dW, float* dbias, float* part_w, float* part_bn, int B, int S,
                            int C, float act_slope, cudaStream_t s);
 void gfinal_fwd_mma(const bf16* in, const float* scale, const float* shift, const float* w, const float* bias, float* out,
-                    uint8_t* out_u8, int B, int S, cudaStream_t s);
+                    uint8_t* out_u8, int B, int S, cudaStream_t s, int C = 32);
 int gfinal_bwd_mma(const float* dout, const float* out, const bf16* y, const float* scale, const float* shift,
                    const float* w, bf16* dbn, float* part_w, float* part_bn, int B, int S, int mode, const float* mean,
-                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s);
+                   const float* rstd, const float* k1, const float* k2, const float* k3, cudaStream_t s, int ld = 32);
 }  // namespace sg
 
 using bf16 = __nv_bfloat16;
