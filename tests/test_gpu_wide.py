@@ -99,14 +99,15 @@ def test_wide_fused_steps_against_oracle():
             assert rel_err(gsd[k], g_sd[k]) <= tol("bf16", "param"), k
 
 
-def test_wide_whole_step_runs_and_fp32_mode_refuses():
-    gan, _, _ = make_gan(64, 4, "bf16", width=2)
-    real = O.synthetic_signatures(32, 64, seed=2).cuda()
+@pytest.mark.parametrize("size", [64, 128])
+def test_wide_whole_step_runs_and_fp32_mode_refuses(size):
+    gan, _, _ = make_gan(size, 4, "bf16", width=2)
+    real = O.synthetic_signatures(32 if size == 64 else 16, size, seed=2).cuda()
     for _ in range(4):       # eager, capture, replay
         m = gan.train_step(real)
     assert all(v == v and abs(v) < 50 for v in m.values())
     assert all(bool(torch.isfinite(p).all()) for p in list(gan.generator.parameters()) + list(gan.discriminator.parameters()))
     from generator_vanilla_gan import Generator
-    G = Generator(base_features=512).to("cuda").set_precision("fp32")
+    G = Generator(output_size=size, base_features=512).to("cuda").set_precision("fp32")
     with pytest.raises(RuntimeError, match="bf16"):
         G(torch.randn(4, 100, device="cuda"))
