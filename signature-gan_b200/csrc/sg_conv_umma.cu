@@ -1248,13 +1248,50 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
+// Split-K reductions on a side stream (wgrad_side_begin .. wgrad_side_end, set by the backward plans of sg_model.cu): the
+// reduction of layer i's partials only feeds the gradient bucket, so it runs on `side` while the launch stream goes on
+// with layer i's data gradient — a small grid that shares the SMs with the persistent tensor kernel instead of a ~25 us
+// serial step (plus two kernel boundaries) per layer. The partial buffer is shared by all layers: the next weight-gradient
+// kernel waits for the pending reduction (launch_wgrad), and wgrad_side_end joins the side stream back.
+static thread_local struct {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool pending = false;
+} t_wside;
+void wgrad_side_begin(cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
+    t_wside.side = side;
+    t_wside.fork = fork_ev;
+    t_wside.join = join_ev;
+    t_wside.pending = false;
+}
+static void wgrad_side_wait(cudaStream_t stream) {  // `stream` may not touch the partial buffer / bucket before this
+    if (t_wside.side && t_wside.pending) {
+        cudaStreamWaitEvent(stream, t_wside.join, 0);
+        t_wside.pending = false;
+    }
+}
+void wgrad_side_end(cudaStream_t stream) {
+    wgrad_side_wait(stream);
+    t_wside.side = nullptr;
+}
+
 void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accumulate, cudaStream_t stream,
                   const float* bias_partial, float* dbias, int SB) {
     const long total = static_cast<long>(M) * N * 16;
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     note_launch();
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dW, S, M, N, accumulate, bias_partial, dbias, SB);
+    cudaStream_t on = stream;
+    if (t_wside.side) {
+        cudaEventRecord(t_wside.fork, stream);
+        cudaStreamWaitEvent(t_wside.side, t_wside.fork, 0);
+        on = t_wside.side;
+    }
+    wgrad_reduce_kernel<<<blocks, 256, 0, on>>>(partial, dW, S, M, N, accumulate, bias_partial, dbias, SB);
+    if (t_wside.side) {
+        cudaEventRecord(t_wside.join, t_wside.side);
+        t_wside.pending = true;
+    }
 }
 
 // sg_wgrad_thin.cu
@@ -1335,6 +1372,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
                  float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream, float* dbias) {
     if (!is_pow2(cH) || !is_pow2(cW) || cW > kWgK) SG_FAIL("wgrad: coarse grid %dx%d unsupported", cH, cW);
     if (Mc % 8 != 0 || Nf % 8 != 0) SG_FAIL("wgrad: channels must be multiples of 8 (Mc=%d Nf=%d)", Mc, Nf);
+    wgrad_side_wait(stream);  // the previous layer's reduction still reads the shared partial buffer
     if (wgrad_pair_supported(cH, cW, Mc, Nf)) {  // generator's last block: pixel-pair formulation on tcgen05
         if (dbias) SG_FAIL("wgrad: the pair kernel has no fused bias gradient");
         if (static_cast<size_t>(wgrad_pair_ctas(nimg, cH)) * 16 * Mc * Nf > partial_floats)
@@ -1438,6 +1476,7 @@ size_t fc_wgrad_partial_floats(int B, int F, int Kp) {
 int launch_fc_wgrad(const __nv_bfloat16* dy, const __nv_bfloat16* zp, int B, int C0, int Kp, int latent, float* partial,
                     size_t partial_floats, float* dW, cudaStream_t stream) {
     const int F = C0 * 16;
+    wgrad_side_wait(stream);  // a pending split-K reduction of the layer above still reads the shared partial buffer
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.plain = 1;

@@ -98,6 +98,11 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
                  float* partial, size_t partial_floats, float* dW, int accumulate, cudaStream_t stream,
                  float* dbias = nullptr);
 size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf);
+// Between begin and end (same host thread) every launch_wgrad puts its split-K reduction on `side` (ordered after the
+// weight-gradient kernel by `fork_ev`), so that it overlaps whatever the launch stream does next; the next launch_wgrad
+// and wgrad_side_end make the launch stream wait for it (`join_ev`). Works inside stream capture (fork / join branches).
+void wgrad_side_begin(cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev);
+void wgrad_side_end(cudaStream_t stream);
 
 // Generator fc weight gradient (plain MN-major GEMM over the batch), un-permuting rows into dW (F, latent).
 size_t fc_wgrad_partial_floats(int B, int F, int Kp);

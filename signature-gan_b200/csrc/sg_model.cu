@@ -214,6 +214,9 @@ struct sg_ctx {
     std::vector<GraphEntry> graphs;
     unsigned long long graph_tick = 0;
     cudaStream_t cap_stream = nullptr;
+    // side stream + events for the split-K reductions of the weight gradients (wgrad_side_begin)
+    cudaStream_t red_stream = nullptr;
+    cudaEvent_t red_fork = nullptr, red_join = nullptr;
     // data-parallel replica: library-owned NCCL communicator (sg_comm_init) for the flat gradient buckets
     sg::Comm comm;
 };
@@ -410,6 +413,35 @@ static bool fused_tail_enabled() {
     return on != 0;
 }
 
+// Scope of a backward plan: split-K reductions of the weight gradients on the context's side stream (SIGGAN_SIDE_REDUCE=0:
+// in line on the launch stream). The destructor joins the side stream back into the launch stream.
+struct SideReduce {
+    cudaStream_t s;
+    bool on = false;
+    SideReduce(sg_ctx* c, cudaStream_t stream) : s(stream) {
+        static int enabled = -1;
+        if (enabled < 0) {
+            const char* e = getenv("SIGGAN_SIDE_REDUCE");
+            enabled = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (!enabled || c->cfg.precision != SG_PREC_BF16) return;
+        if (!c->red_stream) {
+            if (cudaStreamCreateWithFlags(&c->red_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->red_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->red_join, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                c->red_stream = nullptr;
+                return;
+            }
+        }
+        sg::wgrad_side_begin(c->red_stream, c->red_fork, c->red_join);
+        on = true;
+    }
+    ~SideReduce() {
+        if (on) sg::wgrad_side_end(s);
+    }
+};
+
 // SIGGAN_FUSED_BN_REDUCE=0: BatchNorm-backward reductions as separate passes (A/B comparison)
 static bool fused_bn_reduce_enabled() {
     static int on = -1;
@@ -592,6 +624,7 @@ int g_backward_t(sg_ctx* c, const float* params, const void* ws_ptr, const float
                  void* d_prev_out = nullptr, int stage = 0) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     GWs w = carve_g(c, const_cast<void*>(ws_ptr), B);
+    SideReduce side_reduce(c, s);
     float* cpart = static_cast<float*>(c->cpart.p);
     float* wpart = static_cast<float*>(c->wpart.p);
     char* cur = static_cast<char*>(c->bufA.p);
@@ -819,6 +852,7 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
                  const void* inject = nullptr, void* dz_prev_out = nullptr) {
     constexpr bool kTC = std::is_same<T, bf16>::value;
     DWs w = carve_d(c, const_cast<void*>(ws_ptr), B);
+    SideReduce side_reduce(c, s);
     const float slope = c->cfg.leaky_slope;
     float* cpart = static_cast<float*>(c->cpart.p);
     float* wpart = static_cast<float*>(c->wpart.p);
@@ -1391,6 +1425,9 @@ void sg_destroy(sg_ctx* c) {
     for (GraphEntry& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    if (c->red_stream) cudaStreamDestroy(c->red_stream);
+    if (c->red_fork) cudaEventDestroy(c->red_fork);
+    if (c->red_join) cudaEventDestroy(c->red_join);
     sg::comm_release(&c->comm);
     c->counters_buf.release();
     DevBuf* bufs[] = {&c->packs, &c->bufA, &c->bufB, &c->dpre, &c->wpart, &c->cpart, &c->small,
