@@ -1257,6 +1257,7 @@ static thread_local struct {
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool pending = false;
+    bool forked = false;  // wgrad_side_fork really opened the branch (wgrad_side_mark is a no-op otherwise)
 } t_wside;
 void wgrad_side_begin(cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
     t_wside.side = side;
@@ -1269,6 +1270,27 @@ static void wgrad_side_wait(cudaStream_t stream) {  // `stream` may not touch th
         cudaStreamWaitEvent(stream, t_wside.join, 0);
         t_wside.pending = false;
     }
+}
+// Other small kernels that only feed the gradient bucket may share the branch: fork returns the stream to launch them on
+// (the side stream, ordered after everything `stream` holds so far; `stream` itself when no branch is open) and mark
+// records them as pending.
+cudaStream_t wgrad_side_fork(cudaStream_t stream) {
+    static const bool extras = [] {  // SIGGAN_SIDE_EXTRA=0: only the split-K reductions use the branch (A/B comparison)
+        const char* e = getenv("SIGGAN_SIDE_EXTRA");
+        return !(e && e[0] == '0');
+    }();
+    t_wside.forked = false;
+    if (!t_wside.side || !extras) return stream;
+    cudaEventRecord(t_wside.fork, stream);
+    cudaStreamWaitEvent(t_wside.side, t_wside.fork, 0);
+    t_wside.forked = true;
+    return t_wside.side;
+}
+void wgrad_side_mark() {
+    if (!t_wside.side || !t_wside.forked) return;
+    cudaEventRecord(t_wside.join, t_wside.side);
+    t_wside.pending = true;
+    t_wside.forked = false;
 }
 void wgrad_side_end(cudaStream_t stream) {
     wgrad_side_wait(stream);

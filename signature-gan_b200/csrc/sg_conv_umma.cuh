@@ -103,6 +103,8 @@ size_t wgrad_partial_floats(int nimg, int cH, int cW, int Mc, int Nf);
 // and wgrad_side_end make the launch stream wait for it (`join_ev`). Works inside stream capture (fork / join branches).
 void wgrad_side_begin(cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev);
 void wgrad_side_end(cudaStream_t stream);
+cudaStream_t wgrad_side_fork(cudaStream_t stream);  // stream for other bucket-only kernels (ordered after `stream` so far)
+void wgrad_side_mark();                             // ... which are pending until the next join
 
 // Generator fc weight gradient (plain MN-major GEMM over the batch), un-permuting rows into dW (F, latent).
 size_t fc_wgrad_partial_floats(int B, int F, int Kp);

@@ -413,8 +413,9 @@ static bool fused_tail_enabled() {
     return on != 0;
 }
 
-// Scope of a backward plan: split-K reductions of the weight gradients on the context's side stream (SIGGAN_SIDE_REDUCE=0:
-// in line on the launch stream). The destructor joins the side stream back into the launch stream.
+// Scope of a backward plan: with SIGGAN_SIDE_REDUCE=1 the split-K reductions of the weight gradients (and the other
+// bucket-only kernels that use wgrad_side_fork) run on the context's side stream; by default they stay in line on the
+// launch stream. The destructor joins the side stream back into the launch stream.
 struct SideReduce {
     cudaStream_t s;
     bool on = false;
@@ -422,7 +423,7 @@ struct SideReduce {
         static int enabled = -1;
         if (enabled < 0) {
             const char* e = getenv("SIGGAN_SIDE_REDUCE");
-            enabled = (e && e[0] == '0') ? 0 : 1;
+            enabled = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral within the +-0.05 ms box-to-box noise
         }
         if (!enabled || c->cfg.precision != SG_PREC_BF16) return;
         if (!c->red_stream) {
@@ -874,10 +875,13 @@ int d_backward_t(sg_ctx* c, const float* params, const float* x, const void* ws_
     if (single ? only_layer == c->ND : stage != 2) {
     PROF("d.cls_bwd", 4.0 * B * Cl * 16, 3.0 * es * B * Cl * 16.0);
     if (grads) {
+        // the classifier's weight / bias gradients only feed the bucket: on the reduction branch, next to the data path
+        cudaStream_t sb = sg::wgrad_side_fork(s);
         const int chunks = sg::col_reduce<T>(2, reinterpret_cast<const T*>(w.a[last]), nullptr, nullptr, nullptr, dlogit,
-                                             B, Cl * 16, cpart, s);
-        sg::col_finalize(cpart, chunks, Cl * 16, Cl, grads + c->dt[c->d_cls_w].offset, nullptr, s);
-        sg::sum_vector(dlogit, B, grads + c->dt[c->d_cls_b].offset, s);
+                                             B, Cl * 16, cpart, sb);
+        sg::col_finalize(cpart, chunks, Cl * 16, Cl, grads + c->dt[c->d_cls_w].offset, nullptr, sb);
+        sg::sum_vector(dlogit, B, grads + c->dt[c->d_cls_b].offset, sb);
+        sg::wgrad_side_mark();
     }
     sg::classifier_bwd_dy<T>(dlogit, c->cls_wp, masks ? masks + mask_offset(c, B, last) : nullptr,
                              reinterpret_cast<const T*>(w.a[last]), slope, reinterpret_cast<T*>(cur), B, Cl, s);
@@ -1035,16 +1039,33 @@ static int train_phase_body(sg_ctx* c, const sg_train_state* st, int B, float* d
     }
     if (phase == 1 || phase == 11) {
         // ---- D step (train…:281-337): D.train(), G.eval(); one 2B batch [real | G(noise)] since D has no batch coupling
-        SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, nullptr, B, 0, c->gws_tmp.p, x2 + img,
-                          nullptr, false, s));
+        // The Discriminator's weight packs and dropout masks do not depend on the generated half of the batch: they run
+        // on the side branch while the Generator produces it
         const float* masks = nullptr;
-        if (dropout) {
-            float* m2 = static_cast<float*>(c->masks2.p);
-            if (!masks_injected)
-                sg::dropout_masks_dev(st->seed, &c->counters->dropout_offset, sg_d_mask_count(c, 2 * B), st->dropout_p, m2, s);
-            masks = m2;
+        bool packed_aside = false;
+        {
+            SideReduce branch(c, s);  // (joins the branch back at the end of this scope)
+            cudaStream_t sb = sg::wgrad_side_fork(s);
+            if (dropout) {
+                float* m2 = static_cast<float*>(c->masks2.p);
+                if (!masks_injected)
+                    sg::dropout_masks_dev(st->seed, &c->counters->dropout_offset, sg_d_mask_count(c, 2 * B), st->dropout_p, m2,
+                                          sb);
+                masks = m2;
+            }
+            if (sb != s && !(c->skip_d_pack && c->d_pack_src == st->d_params)) {
+                SG_TRY(pack_discriminator(c, st->d_params, sb));
+                packed_aside = true;
+            }
+            sg::wgrad_side_mark();
+            SG_TRY(DISPATCH_T(c, g_forward_t, c, st->g_params, st->g_running_stats, nullptr, B, 0, c->gws_tmp.p, x2 + img,
+                              nullptr, false, s));
         }
-        SG_TRY(DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s));
+        const bool keep = c->skip_d_pack;
+        if (packed_aside) c->skip_d_pack = true;  // d_forward_t finds the packs it needs
+        const int rc_fwd = DISPATCH_T(c, d_forward_t, c, st->d_params, x2, 2 * B, masks, c->d_ws.p, nullptr, nullptr, s);
+        c->skip_d_pack = keep;
+        SG_TRY(rc_fwd);
         DWs w = carve_d(c, c->d_ws.p, 2 * B);
         sg::d_loss_metrics(w.prob, B, st->label_smoothing, metrics, c->dlogit, s);
         SG_TRY(DISPATCH_T(c, d_backward_t, c, st->d_params, x2, c->d_ws.p, masks, c->dlogit, 2 * B, d_grads, nullptr, s,
