@@ -573,7 +573,7 @@ def run_ours(args, rank, local_rank, world):
             # images of an average launch of the op: the D step runs it on 2B images, the G step on B)
             traffic, traffic_src = None, None
             try:
-                with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")) as f:
                     t = json.load(f).get(k)
                 if t and S == 64:
                     per_img = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["images"]
