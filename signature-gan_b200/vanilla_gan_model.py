@@ -466,7 +466,7 @@ class VanillaGAN(nn.Module):
         dgrads, ggrads = self.discriminator._flat.grad_staging(), self.generator._flat.grad_staging()
         L.check(sctx.lib.sg_train_step(sctx.handle, C.byref(st), L.ptr(real), L.ptr(noise[0]), L.ptr(noise[1]), B,
                                        L.ptr(dgrads), L.ptr(ggrads), L.ptr(self._metrics), 0, L.current_stream(dev)),
-                "sg_train_step(data-parallel step)")
+                "sg_train_step(whole step)")
         self.d_optimizer.advance()
         self.g_optimizer.advance()
         self.discriminator._flat.expose(dgrads)
