@@ -49,14 +49,23 @@ __device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// relu(y * scale + shift) of 8 channels held as one 16-byte piece; returns fp32 values
+// y * scale + shift of 8 channels held as one 16-byte piece, BEFORE the ReLU: the ReLU is folded into the bf16 conversion
+// of the value that feeds the tensor cores (pack2_relu: cvt.rn.relu.bf16x2, the same result as max(x, 0) then rounding),
+// and its derivative is taken on the sign of this pre-activation (max(t, 0) > 0 <=> t > 0) — 16 FMNMX fewer per 16-pixel
+// group in kernels that ncu shows issue-bound (60-67 % of the issue slots busy)
 template <bool kAffine>
-__device__ __forceinline__ void bn_relu8(const uint4& u, const float (&sc)[8], const float (&sh)[8], float (&a)[8]) {
+__device__ __forceinline__ void bn_pre8(const uint4& u, const float (&sc)[8], const float (&sh)[8], float (&a)[8]) {
     unpack8(u, a);
     if (kAffine) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f);
+        for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sh[j]);
     }
+}
+// {relu(lo), relu(hi)} as packed bf16
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,13 +180,13 @@ gfinal_fwd_mma_kernel(const bf16* __restrict__ in, const float* __restrict__ sca
                     const uint4 u0 = *reinterpret_cast<const uint4*>(st);
                     const uint4 u1 = *reinterpret_cast<const uint4*>(st + kThr * 16);
                     float a0[8], a1[8];
-                    bn_relu8<kAffine>(u0, sc[cg], sh[cg], a0);
-                    bn_relu8<kAffine>(u1, sc[cg], sh[cg], a1);
+                    bn_pre8<kAffine>(u0, sc[cg], sh[cg], a0);
+                    bn_pre8<kAffine>(u1, sc[cg], sh[cg], a1);
                     uint32_t p0[4], p1[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        p0[j] = kAffine ? pack2_bf16(a0[2 * j], a0[2 * j + 1]) : (&u0.x)[j];
-                        p1[j] = kAffine ? pack2_bf16(a1[2 * j], a1[2 * j + 1]) : (&u1.x)[j];
+                        p0[j] = kAffine ? pack2_relu(a0[2 * j], a0[2 * j + 1]) : (&u0.x)[j];
+                        p1[j] = kAffine ? pack2_relu(a1[2 * j], a1[2 * j + 1]) : (&u1.x)[j];
                     }
                     const uint32_t A0[4] = {p0[0], p1[0], p0[1], p1[1]};
                     const uint32_t A1[4] = {p0[2], p1[2], p0[3], p1[3]};
@@ -340,8 +349,8 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
             const int pix0 = c * kChunkPx + (warp * kGroupsPerWarp + g) * 16;
             const float* dpp = dp + (pix0 >> lgS) * pitch + (pix0 & (S - 1));
             float a0[8], a1[8];
-            bn_relu8<true>(u0, sc, sh, a0);
-            bn_relu8<true>(u1, sc, sh, a1);
+            bn_pre8<true>(u0, sc, sh, a0);   // pre-activations: > 0 <=> the ReLU passed the element
+            bn_pre8<true>(u1, sc, sh, a1);
             // ---- data gradient: [16 pixels][taps] x [taps][32 channels]
             uint32_t A[4];
             A[0] = pack2_bf16(dpp[gid + offT0], dpp[gid + offT1]);
@@ -387,8 +396,8 @@ gfinal_bwd_mma_kernel(const bf16* __restrict__ y, const float* __restrict__ scal
             AW[3] = gid == 0 ? pack2_bf16(dpp[2 * t + 8 + off8], dpp[2 * t + 9 + off8]) : 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t b0 = movmatrix_t(pack2_bf16(a0[2 * j], a0[2 * j + 1]));
-                const uint32_t b1 = movmatrix_t(pack2_bf16(a1[2 * j], a1[2 * j + 1]));
+                const uint32_t b0 = movmatrix_t(pack2_relu(a0[2 * j], a0[2 * j + 1]));
+                const uint32_t b1 = movmatrix_t(pack2_relu(a1[2 * j], a1[2 * j + 1]));
                 mma_bf16(accw[j], AW, b0, b1);
             }
         }
