@@ -74,7 +74,6 @@ struct Conv2Args {
     int ldmask;
     const __nv_bfloat16* gate;
     long long* dbg;  // optional [gridDim.x][16] cycle counters (SIGGAN_CONV2_DEBUG): where each role waits
-    int stream_hints;  // SIGGAN_CONV2_STREAM=1: evict-first gate loads / streaming stores in the lean epilogue (experiment)
 };
 
 #define C2_TIMED_WAIT(slot, bar, parity)              \
@@ -310,7 +309,6 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
         __nv_bfloat16* const outp = static_cast<__nv_bfloat16*>(args.out);
         const uint32_t tempty_leader[2] = {mapa_rank(smem_u32(&tempty[0]), 0), mapa_rank(smem_u32(&tempty[1]), 0)};
         const float slope = args.slope;
-        const bool stream_hints = args.stream_hints != 0;  // experiment: evict-first loads of the gate / streaming stores
         // element offsets of this lane's four rows (gid + 8k) of a unit at its 16-byte block (columns 8 * t4 ..) of a
         // 32-channel chunk of the parity's 64 channels
         auto unit_offsets = [&](int u, size_t (&off)[4], bool (&ok)[4]) {
@@ -329,8 +327,7 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
         auto gate_fetch = [&](const size_t (&off)[4], const bool (&ok)[4], int ch, uint4 (&g)[4]) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                g[k] = (args.gate && ok[k]) ? (stream_hints ? __ldcs(reinterpret_cast<const uint4*>(args.gate + off[k] + ch * 32))
-                                                            : __ldg(reinterpret_cast<const uint4*>(args.gate + off[k] + ch * 32)))
+                g[k] = (args.gate && ok[k]) ? __ldg(reinterpret_cast<const uint4*>(args.gate + off[k] + ch * 32))
                                             : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // open
         };
         // gate words: chunk 0 before the accumulator is waited for, chunk 1 while chunk 0 is processed. (Fetching the
@@ -388,11 +385,8 @@ conv2_umma_kernel(const __grid_constant__ Conv2Args args) {
                             r4[n] = c2_pack(f0, f1);
                         }
                         quad_transpose(r4, t4);            // r4 = columns 8 t4 .. 8 t4 + 7 of the row
-                        if (ok[k]) {
-                            uint4* op = reinterpret_cast<uint4*>(outp + off[k] + ch * 32);
-                            if (stream_hints) __stcs(op, make_uint4(r4[0], r4[1], r4[2], r4[3]));
-                            else *op = make_uint4(r4[0], r4[1], r4[2], r4[3]);
-                        }
+                        if (ok[k])
+                            *reinterpret_cast<uint4*>(outp + off[k] + ch * 32) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
                     }
             }
         }
@@ -613,11 +607,6 @@ int launch_c2(const Conv2Args& a_in, cudaStream_t stream) {
     static const bool debug = getenv("SIGGAN_CONV2_DEBUG") != nullptr;
     static long long* dbg = nullptr;
     Conv2Args a = a_in;
-    static const bool stream_hints = [] {
-        const char* e = getenv("SIGGAN_CONV2_STREAM");
-        return e && e[0] == '1';
-    }();
-    a.stream_hints = stream_hints ? 1 : 0;
     if (debug) {
         if (!dbg) cudaMalloc(&dbg, 148 * 16 * 8);
         cudaMemsetAsync(dbg, 0, 148 * 16 * 8, stream);
