@@ -1324,7 +1324,7 @@ int launch_wgrad_thin(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, in
 
 // sg_wgrad_pair.cu
 bool wgrad_pair_supported(int cH, int cW, int Mc, int Nf);
-int wgrad_pair_ctas(int nimg, int cH);
+int wgrad_pair_ctas(int nimg, int cH, int cW);
 int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, float* partial,
                       float* dW, int accumulate, cudaStream_t stream);
 
@@ -1397,7 +1397,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
     wgrad_side_wait(stream);  // the previous layer's reduction still reads the shared partial buffer
     if (wgrad_pair_supported(cH, cW, Mc, Nf)) {  // generator's last block: pixel-pair formulation on tcgen05
         if (dbias) SG_FAIL("wgrad: the pair kernel has no fused bias gradient");
-        if (static_cast<size_t>(wgrad_pair_ctas(nimg, cH)) * 16 * Mc * Nf > partial_floats)
+        if (static_cast<size_t>(wgrad_pair_ctas(nimg, cH, cW)) * 16 * Mc * Nf > partial_floats)
             SG_FAIL("wgrad: partial workspace too small");
         if (launch_wgrad_pair(coarse, fine, nimg, cH, cW, partial, dW, accumulate, stream))
             SG_FAIL("wgrad_pair launch failed: %s (%s)", cudaGetErrorString(cudaGetLastError()), umma_last_error());

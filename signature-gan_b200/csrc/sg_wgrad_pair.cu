@@ -45,6 +45,7 @@ struct WgradPairArgs {
     CUtensorMap fmap[2];  // fine tensor, row-parity planes: [64 (px,n)][32 pairs][cH rows][N]
     CUtensorMap cmap;     // coarse tensor NHWC [32][32][cH][N], box {32, 32, 4, 1}
     int cH, nimg, total_tiles;
+    int halves;      // 32-pixel column blocks per coarse row: 1 (coarse grid 32 wide) or 2 (64 wide: the 128 x 128 model)
     float* partial;  // [gridDim.x][16][32][32]
 };
 
@@ -83,7 +84,11 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
         int s = 0;
         uint32_t ph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int n0 = t / tpi, y0 = (t - n0 * tpi) * 4;
+            // tile = (image, 4 coarse rows, 32-column block): pair j of the block meets coarse pixel x0 + j + s, so the
+            // shifted coarse boxes of an inner block edge read the neighbouring block's real pixels, and only the image
+            // border is zero-filled
+            const int tb = t / args.halves, x0 = (t - tb * args.halves) * 32;
+            const int n0 = tb / tpi, y0 = (tb - n0 * tpi) * 4;
             mbar_wait(&empty_bar[s], ph ^ 1);
             if (issuer) {
                 mbar_arrive_expect_tx(&full_bar[s], kWpStageBytes);
@@ -91,13 +96,13 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
                 uint8_t* sc = sf + 4 * kWpFineBox;
                 // atoms [ky 1 | ky 2] and [ky 0 | ky 3]; fine row 2 iy - 1 + ky: ky 0 -> odd plane row iy - 1, 1 -> even
                 // plane row iy, 2 -> odd plane row iy, 3 -> even plane row iy + 1
-                tma_load_4d(sf + 0 * kWpFineBox, &args.fmap[0], &full_bar[s], 0, 0, y0, n0);      // ky 1
-                tma_load_4d(sf + 1 * kWpFineBox, &args.fmap[1], &full_bar[s], 0, 0, y0, n0);      // ky 2
-                tma_load_4d(sf + 2 * kWpFineBox, &args.fmap[1], &full_bar[s], 0, 0, y0 - 1, n0);  // ky 0
-                tma_load_4d(sf + 3 * kWpFineBox, &args.fmap[0], &full_bar[s], 0, 0, y0 + 1, n0);  // ky 3
-                tma_load_4d(sc + 0 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, 0, y0, n0);       // s = 0
-                tma_load_4d(sc + 1 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, -1, y0, n0);      // s = -1
-                tma_load_4d(sc + 2 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, 1, y0, n0);       // s = +1
+                tma_load_4d(sf + 0 * kWpFineBox, &args.fmap[0], &full_bar[s], 0, x0, y0, n0);      // ky 1
+                tma_load_4d(sf + 1 * kWpFineBox, &args.fmap[1], &full_bar[s], 0, x0, y0, n0);      // ky 2
+                tma_load_4d(sf + 2 * kWpFineBox, &args.fmap[1], &full_bar[s], 0, x0, y0 - 1, n0);  // ky 0
+                tma_load_4d(sf + 3 * kWpFineBox, &args.fmap[0], &full_bar[s], 0, x0, y0 + 1, n0);  // ky 3
+                tma_load_4d(sc + 0 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, x0, y0, n0);       // s = 0
+                tma_load_4d(sc + 1 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, x0 - 1, y0, n0);   // s = -1
+                tma_load_4d(sc + 2 * kWpCoarseBox, &args.cmap, &full_bar[s], 0, x0 + 1, y0, n0);   // s = +1
             }
             if (++s == kWpStages) {
                 s = 0;
@@ -196,10 +201,10 @@ bool wgrad_pair_supported(int cH, int cW, int Mc, int Nf) {
         const char* e = getenv("SIGGAN_WGRAD_PAIR");
         return !(e && e[0] == '0');
     }();
-    return on && Mc == 32 && Nf == 32 && cW == 32 && cH >= 4 && cH % 4 == 0;
+    return on && Mc == 32 && Nf == 32 && (cW == 32 || cW == 64) && cH >= 4 && cH % 4 == 0;
 }
-int wgrad_pair_ctas(int nimg, int cH) {
-    const int tiles = nimg * (cH / 4);
+int wgrad_pair_ctas(int nimg, int cH, int cW) {
+    const int tiles = nimg * (cH / 4) * (cW / 32);
     return tiles < sm_count_wp() ? tiles : sm_count_wp();
 }
 
@@ -210,7 +215,8 @@ int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, in
     memset(&a, 0, sizeof(a));
     a.cH = cH;
     a.nimg = nimg;
-    a.total_tiles = nimg * (cH / 4);
+    a.halves = cW / 32;
+    a.total_tiles = nimg * (cH / 4) * a.halves;
     a.partial = partial;
     const int fW = 2 * cW, fH = 2 * cH;
     const uint64_t row_bytes = static_cast<uint64_t>(fW) * 32 * 2;
@@ -233,7 +239,7 @@ int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, in
             return -1;
         attr_set = true;
     }
-    const int grid = wgrad_pair_ctas(nimg, cH);
+    const int grid = wgrad_pair_ctas(nimg, cH, cW);
     note_launch();
     wgrad_pair_kernel<<<grid, kWpThreads, kWpSmemBytes, stream>>>(a);
     if (cudaGetLastError() != cudaSuccess) return -1;
