@@ -1325,8 +1325,8 @@ int launch_wgrad_thin(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, in
 // sg_wgrad_pair.cu
 bool wgrad_pair_supported(int cH, int cW, int Mc, int Nf);
 int wgrad_pair_ctas(int nimg, int cH, int cW);
-int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, float* partial,
-                      float* dW, int accumulate, cudaStream_t stream);
+int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc,
+                      float* partial, float* dW, int accumulate, cudaStream_t stream);
 
 static bool wgrad_pairs(int Mc, int Nf);
 // Split-K factor: the launch is base * s CTAs (or CTA pairs) of one tile each on `slots` resident CTAs (pairs). Pick
@@ -1399,7 +1399,7 @@ int launch_wgrad(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nim
         if (dbias) SG_FAIL("wgrad: the pair kernel has no fused bias gradient");
         if (static_cast<size_t>(wgrad_pair_ctas(nimg, cH, cW)) * 16 * Mc * Nf > partial_floats)
             SG_FAIL("wgrad: partial workspace too small");
-        if (launch_wgrad_pair(coarse, fine, nimg, cH, cW, partial, dW, accumulate, stream))
+        if (launch_wgrad_pair(coarse, fine, nimg, cH, cW, Mc, partial, dW, accumulate, stream))
             SG_FAIL("wgrad_pair launch failed: %s (%s)", cudaGetErrorString(cudaGetLastError()), umma_last_error());
         return 0;
     }

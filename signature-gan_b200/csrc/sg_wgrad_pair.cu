@@ -34,22 +34,34 @@ void wgrad_reduce(const float* partial, float* dW, int S, int M, int N, int accu
 namespace {
 
 constexpr int kWpThreads = 64 + 32 * 4;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (once, at the end)
-constexpr int kWpFineBox = 128 * 128;    // 4 rows x 32 pairs x 128 bytes
-constexpr int kWpCoarseBox = 128 * 64;   // 4 rows x 32 pixels x 64 bytes
-constexpr int kWpStageBytes = 4 * kWpFineBox + 3 * kWpCoarseBox;
+constexpr int kWpFineBox = 128 * 128;    // 128 pair rows (4 rows x 32 pairs, or 8 rows x 16 pairs) x 128 bytes
 constexpr int kWpStages = 2;
-constexpr int kWpTmemCols = 256;
-constexpr int kWpSmemBytes = kWpStages * kWpStageBytes + 1024 + 256;
+// MC = channels of the coarse tensor: 32 (the last block: 64-byte pixel rows, 64-byte swizzle, N = 3 x 32 = 96) or 64 (the
+// block before it: 128-byte pixel rows, 128-byte swizzle, N = 3 x 64 = 192). PPR = pixel pairs (= coarse pixels) per
+// 32- or 16-wide row block of a tile; a tile is 128 / PPR coarse rows.
+template <int MC>
+struct WpCfg {
+    static constexpr int kCoarseBox = 128 * MC * 2;  // 128 coarse pixels x MC channels bf16
+    static constexpr int kStageBytes = 4 * kWpFineBox + 3 * kCoarseBox;
+    static constexpr int kSmemBytes = kWpStages * kStageBytes + 1024 + 256;
+    static constexpr int kN = 3 * MC;                 // [s][m]
+    static constexpr int kGrpCols = MC == 32 ? 128 : 256;  // TMEM column distance between the two accumulators
+    static constexpr int kTmemCols = 2 * kGrpCols;
+};
 
 struct WgradPairArgs {
     CUtensorMap fmap[2];  // fine tensor, row-parity planes: [64 (px,n)][32 pairs][cH rows][N]
     CUtensorMap cmap;     // coarse tensor NHWC [32][32][cH][N], box {32, 32, 4, 1}
     int cH, nimg, total_tiles;
-    int halves;      // 32-pixel column blocks per coarse row: 1 (coarse grid 32 wide) or 2 (64 wide: the 128 x 128 model)
-    float* partial;  // [gridDim.x][16][32][32]
+    int halves;      // PPR-pixel column blocks per coarse row: 1, or 2 (64-wide coarse rows of the 128 x 128 model)
+    float* partial;  // [gridDim.x][16][MC][32]
 };
 
+template <int MC, int PPR>
 __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_constant__ WgradPairArgs args) {
+    using Cfg = WpCfg<MC>;
+    constexpr int kWpStageBytes = Cfg::kStageBytes, kWpCoarseBox = Cfg::kCoarseBox, kWpTmemCols = Cfg::kTmemCols;
+    constexpr int kRows = 128 / PPR;  // coarse rows per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWpStages * kWpStageBytes);
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-    const int tpi = args.cH / 4;
+    const int tpi = args.cH / kRows;
     const int total_tiles = args.total_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -87,8 +99,8 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
             // tile = (image, 4 coarse rows, 32-column block): pair j of the block meets coarse pixel x0 + j + s, so the
             // shifted coarse boxes of an inner block edge read the neighbouring block's real pixels, and only the image
             // border is zero-filled
-            const int tb = t / args.halves, x0 = (t - tb * args.halves) * 32;
-            const int n0 = tb / tpi, y0 = (tb - n0 * tpi) * 4;
+            const int tb = t / args.halves, x0 = (t - tb * args.halves) * PPR;
+            const int n0 = tb / tpi, y0 = (tb - n0 * tpi) * kRows;
             mbar_wait(&empty_bar[s], ph ^ 1);
             if (issuer) {
                 mbar_arrive_expect_tx(&full_bar[s], kWpStageBytes);
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer: both operands MN-major ----------------
-        constexpr uint32_t idesc = make_idesc_bf16(128, 96, 1, 1);
+        constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::kN, 1, 1);
         const bool issuer = elect_one();
         int s = 0;
         uint32_t ph = 0;
@@ -129,8 +141,11 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
                         // A: 16 pair rows x 128 B per K step; two 64-wide atoms one box apart. B: 16 pixel rows x 64 B per
                         // K step (64-byte swizzle: 8-row groups of 512 B); three 32-wide blocks one coarse box apart.
                         const uint64_t da = make_smem_desc(f_addr + grp * 2 * kWpFineBox + k * 2048, kWpFineBox, 1024, kLayoutSW128);
-                        const uint64_t db = make_smem_desc(c_addr + k * 1024, kWpCoarseBox, 512, kLayoutSW64);
-                        umma_bf16_ss(tmem_base + grp * 128, da, db, idesc, !first || k != 0);
+                        // MC = 32: 16 pixel rows x 64 B per K step (64-byte swizzle: 8-row groups of 512 B), three 32-wide
+                        // blocks one coarse box apart; MC = 64: 16 rows x 128 B, three 64-wide atoms one box apart
+                        const uint64_t db = MC == 32 ? make_smem_desc(c_addr + k * 1024, kWpCoarseBox, 512, kLayoutSW64)
+                                                     : make_smem_desc(c_addr + k * 2048, kWpCoarseBox, 1024, kLayoutSW128);
+                        umma_bf16_ss(tmem_base + grp * Cfg::kGrpCols, da, db, idesc, !first || k != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
         }
         if (issuer) umma_commit(accum_bar);
     } else {
-        // ---------------- Epilogue (once): TMEM -> this CTA's partial [16][32 m][32 n] ----------------
+        // ---------------- Epilogue (once): TMEM -> this CTA's partial [16][MC m][32 n] ----------------
         const int q = warp & 3;  // TMEM lane quarter: rows [ky half][px][n] -> q = kyh * 2 + px, lane = n
         const int kyh = q >> 1, px = q & 1;
         const bool any = static_cast<int>(blockIdx.x) < total_tiles;
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        float* dst = args.partial + static_cast<size_t>(blockIdx.x) * 16 * 32 * 32;
+        float* dst = args.partial + static_cast<size_t>(blockIdx.x) * 16 * MC * 32;
 #pragma unroll 1
         for (int grp = 0; grp < 2; ++grp) {
             const int ky = grp == 0 ? (kyh == 0 ? 1 : 2) : (kyh == 0 ? 0 : 3);
@@ -162,18 +177,22 @@ __global__ void __launch_bounds__(kWpThreads, 1) wgrad_pair_kernel(const __grid_
                 if (si == 0) kx = px == 0 ? 1 : 2;
                 else if (si == 1) kx = px == 0 ? 3 : -1;
                 else kx = px == 1 ? 0 : -1;
-                uint32_t v[32];
-                if (any) {
-                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * 128 + si * 32, v);
-                    tmem_ld_wait();
-                } else {
+#pragma unroll 1
+                for (int mb = 0; mb < MC / 32; ++mb) {  // 32 columns (coarse channels m) at a time
+                    uint32_t v[32];
+                    if (any) {
+                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * Cfg::kGrpCols + si * MC + mb * 32,
+                                      v);
+                        tmem_ld_wait();
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0;
-                }
-                if (kx >= 0) {
-                    float* o = dst + static_cast<size_t>(ky * 4 + kx) * 32 * 32 + lane;  // [tap][m][n = lane]
+                        for (int j = 0; j < 32; ++j) v[j] = 0;
+                    }
+                    if (kx >= 0) {
+                        float* o = dst + (static_cast<size_t>(ky * 4 + kx) * MC + mb * 32) * 32 + lane;  // [tap][m][n = lane]
 #pragma unroll
-                    for (int m = 0; m < 32; ++m) o[m * 32] = __uint_as_float(v[m]);
+                        for (int m = 0; m < 32; ++m) o[m * 32] = __uint_as_float(v[m]);
+                    }
                 }
             }
         }
@@ -195,55 +214,75 @@ int sm_count_wp() {
 
 }  // namespace
 
-// coarse [nimg][cH][32][32], fine [nimg][2cH][64][32]
+// Shapes: fine tensor [nimg][2 cH][2 cW][32] (Nf = 32), coarse tensor [nimg][cH][cW][Mc] with
+//   Mc = 32, cW = 32 or 64  (the last block of the 64 x 64 / 128 x 128 generator), tiles of 4 rows x 32 pixels,
+//   Mc = 64, cW = 16 or 32  (the block before it), tiles of 8 rows x 16 pixels / 4 rows x 32 pixels.
 bool wgrad_pair_supported(int cH, int cW, int Mc, int Nf) {
     static const bool on = [] {
         const char* e = getenv("SIGGAN_WGRAD_PAIR");
         return !(e && e[0] == '0');
     }();
-    return on && Mc == 32 && Nf == 32 && (cW == 32 || cW == 64) && cH >= 4 && cH % 4 == 0;
+    if (!on || Nf != 32) return false;
+    if (Mc == 32) return (cW == 32 || cW == 64) && cH >= 4 && cH % 4 == 0;
+    if (Mc == 64) return (cW == 16 && cH % 8 == 0) || (cW == 32 && cH % 4 == 0);
+    return false;
 }
+static int wp_ppr(int cW) { return cW == 16 ? 16 : 32; }
 int wgrad_pair_ctas(int nimg, int cH, int cW) {
-    const int tiles = nimg * (cH / 4) * (cW / 32);
+    const int ppr = wp_ppr(cW);
+    const int tiles = nimg * (cH / (128 / ppr)) * (cW / ppr);
     return tiles < sm_count_wp() ? tiles : sm_count_wp();
 }
 
-// Same contract as launch_wgrad; `partial` must hold wgrad_pair_ctas() * 16 * 32 * 32 floats.
-int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, float* partial,
-                      float* dW, int accumulate, cudaStream_t stream) {
+template <int MC, int PPR>
+static int launch_wp(const WgradPairArgs& a, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_pair_kernel<MC, PPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 WpCfg<MC>::kSmemBytes) != cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    wgrad_pair_kernel<MC, PPR><<<grid, kWpThreads, WpCfg<MC>::kSmemBytes, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// Same contract as launch_wgrad; `partial` must hold wgrad_pair_ctas() * 16 * Mc * 32 floats.
+int launch_wgrad_pair(const __nv_bfloat16* coarse, const __nv_bfloat16* fine, int nimg, int cH, int cW, int Mc,
+                      float* partial, float* dW, int accumulate, cudaStream_t stream) {
     WgradPairArgs a;
     memset(&a, 0, sizeof(a));
+    const int ppr = wp_ppr(cW), rows = 128 / ppr;
     a.cH = cH;
     a.nimg = nimg;
-    a.halves = cW / 32;
-    a.total_tiles = nimg * (cH / 4) * a.halves;
+    a.halves = cW / ppr;
+    a.total_tiles = nimg * (cH / rows) * a.halves;
     a.partial = partial;
     const int fW = 2 * cW, fH = 2 * cH;
     const uint64_t row_bytes = static_cast<uint64_t>(fW) * 32 * 2;
     for (int py = 0; py < 2; ++py) {
         const uint64_t dims[4] = {64, static_cast<uint64_t>(fW / 2), static_cast<uint64_t>(cH), static_cast<uint64_t>(nimg)};
         const uint64_t strides[3] = {128, 2 * row_bytes, static_cast<uint64_t>(fH) * row_bytes};
-        const uint32_t box[4] = {64, 32, 4, 1};
+        const uint32_t box[4] = {64, static_cast<uint32_t>(ppr), static_cast<uint32_t>(rows), 1};
         if (make_map_tiled(&a.fmap[py], reinterpret_cast<const char*>(fine) + py * row_bytes, 4, dims, strides, box, 128))
             return -1;
     }
     {
-        const uint64_t dims[4] = {32, static_cast<uint64_t>(cW), static_cast<uint64_t>(cH), static_cast<uint64_t>(nimg)};
-        const uint64_t strides[3] = {64, static_cast<uint64_t>(cW) * 64, static_cast<uint64_t>(cH) * cW * 64};
-        const uint32_t box[4] = {32, 32, 4, 1};
-        if (make_map_tiled(&a.cmap, coarse, 4, dims, strides, box, 64)) return -1;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWpSmemBytes) != cudaSuccess)
-            return -1;
-        attr_set = true;
+        const uint64_t px_bytes = static_cast<uint64_t>(Mc) * 2;
+        const uint64_t dims[4] = {static_cast<uint64_t>(Mc), static_cast<uint64_t>(cW), static_cast<uint64_t>(cH),
+                                  static_cast<uint64_t>(nimg)};
+        const uint64_t strides[3] = {px_bytes, static_cast<uint64_t>(cW) * px_bytes, static_cast<uint64_t>(cH) * cW * px_bytes};
+        const uint32_t box[4] = {static_cast<uint32_t>(Mc), static_cast<uint32_t>(ppr), static_cast<uint32_t>(rows), 1};
+        if (make_map_tiled(&a.cmap, coarse, 4, dims, strides, box, Mc == 32 ? 64 : 128)) return -1;
     }
     const int grid = wgrad_pair_ctas(nimg, cH, cW);
     note_launch();
-    wgrad_pair_kernel<<<grid, kWpThreads, kWpSmemBytes, stream>>>(a);
-    if (cudaGetLastError() != cudaSuccess) return -1;
-    wgrad_reduce(partial, dW, grid, 32, 32, accumulate, stream);
+    int rc;
+    if (Mc == 32) rc = launch_wp<32, 32>(a, grid, stream);
+    else if (ppr == 16) rc = launch_wp<64, 16>(a, grid, stream);
+    else rc = launch_wp<64, 32>(a, grid, stream);
+    if (rc) return -1;
+    wgrad_reduce(partial, dW, grid, Mc, 32, accumulate, stream);
     return 0;
 }
 
